@@ -1,0 +1,447 @@
+// C ABI of libsgp (include/sgp.h): context, resident state, and the calls a ReactiveMP host makes in place of the
+// per-point rules.  Host pointers in, host pointers out; all device work on the context's own stream.
+#include "sgp_internal.cuh"
+#include <cmath>
+#include <cstring>
+#include <new>
+
+int sgp_gemm(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+             double beta, double* C, int ldc, int lower_only);
+int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double* mean, const double* cov, int D_out, const double* R,
+                        double* psi0, double* psi1, double* psi2, double* psi1_n);
+
+namespace {
+
+__global__ void axpby_kernel(double* __restrict__ out, const double* __restrict__ a, double alpha, const double* __restrict__ b, double beta, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = alpha * (a ? a[i] : 0.0) + beta * (b ? b[i] : 0.0);
+}
+__global__ void add_outer_kernel(double* __restrict__ A, const double* __restrict__ v, int M) {   // A += v v'
+    size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e < (size_t)M * M) A[e] = fma(v[e % M], v[e / M], A[e]);
+}
+__global__ void transpose_kernel(const double* __restrict__ A, double* __restrict__ B, int M) {
+    __shared__ double t[32][33];
+    int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) if (x < M && y0 + j < M) t[j][threadIdx.x] = A[(size_t)x + (size_t)(y0 + j) * M];
+    __syncthreads();
+    int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) if (xo < M && yo0 + j < M) B[(size_t)xo + (size_t)(yo0 + j) * M] = t[threadIdx.x][j];
+}
+__global__ void identity_kernel(double* __restrict__ A, int M) {
+    size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e < (size_t)M * M) A[e] = (e % M == e / M) ? 1.0 : 0.0;
+}
+// out[0] = sum_i a[i*stride_a] * b[i*stride_b]  (single block, fixed order -> deterministic)
+__global__ void dot_kernel(const double* __restrict__ a, size_t stride_a, const double* __restrict__ b, size_t stride_b, size_t n, double* __restrict__ out) {
+    __shared__ double s[256];
+    double v = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += 256) v = fma(a[i * stride_a], b ? b[i * stride_b] : 1.0, v);
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+// out[n] = sum_m k(x_n, z_m) mu[m]   (one thread per test point, inducing rows broadcast from shared memory)
+__global__ void predict_kernel(const double* __restrict__ Xt, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ out,
+                               long long Nt, int M, int D, int kind, double variance, const double* __restrict__ ell_inv) {
+    extern __shared__ double sh[];   // chunk of inducing rows: [MC][D] + mu[MC]
+    const int MC = 256;
+    long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double x[SGP_MAX_D];
+    for (int d = 0; d < D; ++d) x[d] = n < Nt ? Xt[n * D + d] * ell_inv[d] : 0.0;
+    double acc = 0.0;
+    for (int m0 = 0; m0 < M; m0 += MC) {
+        int mc = M - m0 < MC ? M - m0 : MC;
+        __syncthreads();
+        for (int e = threadIdx.x; e < mc * D; e += blockDim.x) sh[e] = Z[(size_t)m0 * D + e] * ell_inv[e % D];
+        for (int e = threadIdx.x; e < mc; e += blockDim.x) sh[MC * D + e] = mu[m0 + e];
+        __syncthreads();
+        for (int m = 0; m < mc; ++m) {
+            double r2 = 0.0;
+            for (int d = 0; d < D; ++d) { double t = x[d] - sh[m * D + d]; r2 = fma(t, t, r2); }
+            double k;
+            if (kind == SGP_KERNEL_SE) k = exp(-0.5 * r2);
+            else if (kind == SGP_KERNEL_MATERN32) { double s = sqrt(3.0 * r2); k = (1.0 + s) * exp(-s); }
+            else { double s = sqrt(5.0 * r2); k = (1.0 + s + s * s / 3.0) * exp(-s); }
+            acc = fma(k, sh[MC * D + m], acc);
+        }
+    }
+    if (n < Nt) out[n] = variance * acc;
+}
+
+inline unsigned nblocks(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+int check(sgp_ctx* ctx) { return ctx ? SGP_OK : SGP_ERR_ARG; }
+
+}  // namespace
+
+int sgp_ensure(sgp_ctx* ctx, double** p, size_t* cap, size_t need) {
+    if (*cap >= need && *p) return SGP_OK;
+    if (*p) SGP_CUDA(ctx, cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    SGP_CUDA(ctx, cudaMalloc((void**)p, need * sizeof(double)));
+    *cap = need;
+    return SGP_OK;
+}
+
+extern "C" {
+
+const char* sgp_version(void) { return "libsgp 0.1 sm_100a"; }
+
+const char* sgp_last_error(const sgp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sgp_create(sgp_ctx** out, int device_id) {
+    if (!out) return SGP_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device_id < 0 || device_id >= ndev) return SGP_ERR_CUDA;
+    sgp_ctx* ctx = new (std::nothrow) sgp_ctx();
+    if (!ctx) return SGP_ERR_CUDA;
+    ctx->dev = device_id;
+    auto fail = [&](const char*) { delete ctx; return SGP_ERR_CUDA; };
+    if (cudaSetDevice(device_id) != cudaSuccess) return fail("setdevice");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return fail("props");
+    if (prop.major < 10) { delete ctx; return SGP_ERR_UNSUPPORTED; }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail("event");
+    if (cudaMalloc((void**)&ctx->exptab_dev, SGP_EXP_TAB * sizeof(double)) != cudaSuccess) return fail("malloc");
+    if (cudaMalloc((void**)&ctx->info_dev, sizeof(int)) != cudaSuccess) return fail("malloc");
+    std::vector<double> tab(SGP_EXP_TAB);
+    for (int j = 0; j < SGP_EXP_TAB; ++j) tab[j] = std::exp2((double)j / SGP_EXP_TAB);
+    if (cudaMemcpy(ctx->exptab_dev, tab.data(), SGP_EXP_TAB * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return fail("memcpy");
+    *out = ctx;
+    return SGP_OK;
+}
+
+void sgp_destroy(sgp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->dev);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    sgp_comm_destroy(ctx);
+    if (ctx->own_data) { cudaFree(ctx->X_dev); cudaFree(ctx->y_dev); cudaFree(ctx->yv_dev); cudaFree(ctx->w_dev); }
+    cudaFree(ctx->Z_dev); cudaFree(ctx->stats_dev); cudaFree(ctx->work_dev); cudaFree(ctx->zrec_dev); cudaFree(ctx->exptab_dev);
+    cudaFree(ctx->dense_dev); cudaFree(ctx->info_dev); cudaFree(ctx->KuuL_dev); cudaFree(ctx->sp_X_dev); cudaFree(ctx->sp_w_dev);
+    cudaFree(ctx->sp_y_dev);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int sgp_set_kernel(sgp_ctx* ctx, int kind, int D, double variance, const double* lengthscale) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (kind < 0 || kind > 2 || D < 1 || D > SGP_MAX_D || !lengthscale || !(variance > 0.0)) SGP_FAIL(ctx, SGP_ERR_ARG, "set_kernel: bad kind / D (1..16) / variance");
+    for (int d = 0; d < D; ++d) if (!(lengthscale[d] > 0.0)) SGP_FAIL(ctx, SGP_ERR_ARG, "set_kernel: lengthscale must be positive");
+    if (ctx->have_Z && D != ctx->D) { ctx->have_Z = false; }
+    if (ctx->N > 0 && D != ctx->D) { ctx->N = 0; }
+    ctx->kind = kind; ctx->D = D; ctx->variance = variance;
+    for (int d = 0; d < D; ++d) ctx->ell[d] = lengthscale[d];
+    ctx->have_kernel = true; ctx->have_kuu = false; ctx->have_stats = false;
+    return SGP_OK;
+}
+
+int sgp_set_inducing(sgp_ctx* ctx, int M, const double* Z) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_kernel) SGP_FAIL(ctx, SGP_ERR_ARG, "set_inducing: set_kernel first (D is taken from it)");
+    if (M < 1 || !Z) SGP_FAIL(ctx, SGP_ERR_ARG, "set_inducing: M >= 1 and Z required");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const int D = ctx->D;
+    if (ctx->Z_dev) { SGP_CUDA(ctx, cudaFree(ctx->Z_dev)); ctx->Z_dev = nullptr; }
+    SGP_CUDA(ctx, cudaMalloc((void**)&ctx->Z_dev, (size_t)M * D * sizeof(double)));
+    SGP_CUDA(ctx, cudaMemcpyAsync(ctx->Z_dev, Z, (size_t)M * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    for (int d = 0; d < D; ++d) {
+        double s = 0.0;
+        for (int m = 0; m < M; ++m) s += Z[(size_t)m * D + d];
+        ctx->center[d] = s / M;
+    }
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->M = M; ctx->have_Z = true; ctx->have_kuu = false; ctx->have_stats = false;
+    size_t need = (size_t)4 * M * M + 4 * (size_t)M + 64;
+    return sgp_ensure(ctx, &ctx->dense_dev, &ctx->dense_cap, need);
+}
+
+static int alloc_data(sgp_ctx* ctx, int64_t N) {
+    int64_t cap = ((N + 31) / 32) * 32;
+    if (ctx->own_data && ctx->Ncap >= cap && ctx->X_dev && ctx->Dcap >= ctx->D) return SGP_OK;
+    if (ctx->own_data) { cudaFree(ctx->X_dev); cudaFree(ctx->y_dev); cudaFree(ctx->yv_dev); cudaFree(ctx->w_dev); }
+    ctx->X_dev = ctx->y_dev = ctx->yv_dev = ctx->w_dev = nullptr; ctx->own_data = true; ctx->Ncap = 0;
+    SGP_CUDA(ctx, cudaMalloc((void**)&ctx->X_dev, (size_t)cap * ctx->D * sizeof(double)));
+    SGP_CUDA(ctx, cudaMalloc((void**)&ctx->y_dev, (size_t)cap * sizeof(double)));
+    SGP_CUDA(ctx, cudaMalloc((void**)&ctx->yv_dev, (size_t)cap * sizeof(double)));
+    SGP_CUDA(ctx, cudaMalloc((void**)&ctx->w_dev, (size_t)cap * sizeof(double)));
+    ctx->Ncap = cap; ctx->Dcap = ctx->D;
+    return SGP_OK;
+}
+
+int sgp_set_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_kernel) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data: set_kernel first (D is taken from it)");
+    if (N < 0 || (N > 0 && !X)) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data: X required");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    if (!ctx->own_data) { ctx->X_dev = ctx->y_dev = ctx->yv_dev = ctx->w_dev = nullptr; ctx->Ncap = 0; }
+    int rc = alloc_data(ctx, N > 0 ? N : 32); if (rc) return rc;
+    const int D = ctx->D;
+    const size_t cap = (size_t)ctx->Ncap;
+    SGP_CUDA(ctx, cudaMemsetAsync(ctx->X_dev, 0, cap * D * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, cap * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaMemsetAsync(ctx->yv_dev, 0, cap * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaMemsetAsync(ctx->w_dev, 0, cap * sizeof(double), ctx->stream));
+    if (N > 0) {
+        SGP_CUDA(ctx, cudaMemcpyAsync(ctx->X_dev, X, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (ybar) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->y_dev, ybar, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (yvar) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->yv_dev, yvar, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (wts) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->w_dev, wts, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->N = N; ctx->have_yv = yvar != nullptr; ctx->have_w = wts != nullptr; ctx->have_stats = false;
+    return SGP_OK;
+}
+
+int sgp_set_targets(sgp_ctx* ctx, const double* ybar, const double* yvar) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->own_data || ctx->N <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "set_targets: needs data set with sgp_set_data");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const size_t N = (size_t)ctx->N;
+    if (ybar) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->y_dev, ybar, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, N * sizeof(double), ctx->stream));
+    if (yvar) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->yv_dev, yvar, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else SGP_CUDA(ctx, cudaMemsetAsync(ctx->yv_dev, 0, N * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_yv = yvar != nullptr; ctx->have_stats = false;
+    return SGP_OK;
+}
+
+int sgp_set_data_dev(sgp_ctx* ctx, int64_t N, const double* X_dev, const double* ybar_dev, const double* yvar_dev, const double* wts_dev) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_kernel) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data_dev: set_kernel first");
+    if (N <= 0 || !X_dev || !ybar_dev) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data_dev: X_dev and ybar_dev required");
+    if (N % 32) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data_dev: N must be a multiple of 32 (buffers are used in place, unpadded)");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    if (ctx->own_data) { cudaFree(ctx->X_dev); cudaFree(ctx->y_dev); cudaFree(ctx->yv_dev); cudaFree(ctx->w_dev); ctx->own_data = false; }
+    ctx->X_dev = const_cast<double*>(X_dev); ctx->y_dev = const_cast<double*>(ybar_dev);
+    ctx->yv_dev = const_cast<double*>(yvar_dev); ctx->w_dev = const_cast<double*>(wts_dev);
+    ctx->N = N; ctx->Ncap = N; ctx->have_yv = yvar_dev != nullptr; ctx->have_w = wts_dev != nullptr; ctx->have_stats = false;
+    return SGP_OK;
+}
+
+static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2) {
+    const size_t M = (size_t)ctx->M, Do = (size_t)ctx->Dout;
+    double* s2 = ctx->stats_dev; double* s1 = s2 + M * M; double* sc = s1 + M * Do;
+    if (psi2) SGP_CUDA(ctx, cudaMemcpyAsync(psi2, s2, M * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (psi1) SGP_CUDA(ctx, cudaMemcpyAsync(psi1, s1, M * Do * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    double sc_h[4] = {0, 0, 0, 0};
+    SGP_CUDA(ctx, cudaMemcpyAsync(sc_h, sc, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (psi0) *psi0 = sc_h[0];
+    if (sum_y2) *sum_y2 = sc_h[1];
+    return SGP_OK;
+}
+
+static int sweep_resident(sgp_ctx* ctx, bool time_main) {
+    if (ctx->N <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: no data (sgp_set_data)");
+    int rc = sgp_sweep_launch(ctx, ctx->X_dev, ctx->y_dev, ctx->have_yv ? ctx->yv_dev : nullptr, ctx->have_w ? ctx->w_dev : nullptr, ctx->N,
+                              ctx->Ncap, time_main);
+    if (rc) return rc;
+    if (ctx->comm) {
+        size_t cnt = (size_t)ctx->M * ctx->M + (size_t)ctx->M * ctx->Dout + 4;
+        rc = sgp_comm_allreduce(ctx, ctx->stats_dev, cnt); if (rc) return rc;
+        ctx->last_launches += 1;
+    }
+    return SGP_OK;
+}
+
+int sgp_sweep_psi(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    int rc = sweep_resident(ctx, false); if (rc) return rc;
+    return fetch_stats(ctx, psi0, psi1, psi2, sum_y2);
+}
+
+int sgp_sweep_psi_uncertain(sgp_ctx* ctx, int method, int p, int64_t N, const double* mean, const double* cov, int D_out, const double* R,
+                            double* psi0, double* psi1, double* psi2, double* psi1_n) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    return sgp_uncertain_sweep(ctx, method, p, N, mean, cov, D_out, R, psi0, psi1, psi2, psi1_n);
+}
+
+int sgp_sweep_timed(sgp_ctx* ctx, int reps, float* ms_per_sweep, float* ms_main_kernel) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (reps < 1) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep_timed: reps >= 1");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double main_sum = 0.0;
+    SGP_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (int r = 0; r < reps; ++r) {
+        int rc = sweep_resident(ctx, true); if (rc) return rc;
+        // main-kernel time needs its own pair of events per repetition; read it back after the sync below for r == reps-1
+        if (r + 1 < reps) {
+            SGP_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
+            float ms = 0.f; SGP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); main_sum += ms;
+        }
+    }
+    SGP_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    SGP_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    float ms = 0.f; SGP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); main_sum += ms;
+    float tot = 0.f; SGP_CUDA(ctx, cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[1]));
+    if (ms_per_sweep) *ms_per_sweep = tot / reps;
+    if (ms_main_kernel) *ms_main_kernel = (float)(main_sum / reps);
+    ctx->last_main_ms = (float)(main_sum / reps);
+    return SGP_OK;
+}
+
+int sgp_last_sweep_info(sgp_ctx* ctx, int* n_launches, int* grid, int* block, int* smem_bytes) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (n_launches) *n_launches = ctx->last_launches;
+    if (grid) *grid = ctx->last_grid;
+    if (block) *block = ctx->last_block;
+    if (smem_bytes) *smem_bytes = ctx->last_smem;
+    return SGP_OK;
+}
+
+int sgp_stats_dev(sgp_ctx* ctx, double** psi2_dev, double** psi1_dev, double** scal_dev) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "stats_dev: no sweep yet");
+    const size_t M = (size_t)ctx->M;
+    if (psi2_dev) *psi2_dev = ctx->stats_dev;
+    if (psi1_dev) *psi1_dev = ctx->stats_dev + M * M;
+    if (scal_dev) *scal_dev = ctx->stats_dev + M * M + M * ctx->Dout;
+    return SGP_OK;
+}
+
+// ---- M x M factorisations ---------------------------------------------------------------------------------------
+int sgp_kuu_factor(sgp_ctx* ctx, double jitter, double* L) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "kuu_factor: set_kernel and set_inducing first");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const int M = ctx->M;
+    if (ctx->KuuL_M != M) {
+        if (ctx->KuuL_dev) SGP_CUDA(ctx, cudaFree(ctx->KuuL_dev));
+        ctx->KuuL_dev = nullptr;
+        SGP_CUDA(ctx, cudaMalloc((void**)&ctx->KuuL_dev, (size_t)M * M * sizeof(double)));
+        ctx->KuuL_M = M;
+    }
+    ctx->have_kuu = false;
+    int rc = sgp_kuu_build(ctx, ctx->KuuL_dev, jitter); if (rc) return rc;
+    rc = sgp_potrf_lower(ctx, ctx->KuuL_dev, M); if (rc) return rc;
+    ctx->have_kuu = true;
+    if (L) {
+        SGP_CUDA(ctx, cudaMemcpyAsync(L, ctx->KuuL_dev, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SGP_OK;
+}
+
+int sgp_kuu_solve(sgp_ctx* ctx, int nrhs, double* B) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_kuu) SGP_FAIL(ctx, SGP_ERR_ARG, "kuu_solve: sgp_kuu_factor first");
+    if (nrhs < 1 || !B) SGP_FAIL(ctx, SGP_ERR_ARG, "kuu_solve: nrhs >= 1 and B required");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const int M = ctx->M;
+    double* tmp = nullptr;
+    size_t bytes = (size_t)M * nrhs * sizeof(double);
+    SGP_CUDA(ctx, cudaMalloc((void**)&tmp, bytes));
+    int rc = SGP_OK;
+    if (cudaMemcpyAsync(tmp, B, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
+    if (!rc) rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, tmp, M, nrhs, false);
+    if (!rc) rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, tmp, M, nrhs, true);
+    if (!rc && cudaMemcpyAsync(B, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = SGP_ERR_CUDA;
+    cudaFree(tmp);
+    if (rc == SGP_ERR_CUDA && ctx->err.empty()) ctx->err = "kuu_solve: CUDA failure";
+    return rc;
+}
+
+int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, double w, double* mu_v, double* Sigma_v, double* Uv) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v: run a sweep first");
+    if (ctx->Dout != 1) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "posterior_v: scalar-output statistics only (MultiSGP folds kron(W, Psi2) on the host)");
+    if (!xi0 || !Lambda0) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v: prior natural parameters required");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const int M = ctx->M; const size_t MM = (size_t)M * M;
+    double* d = ctx->dense_dev + 64;
+    double *Lam = d, *X = d + MM, *Sig = d + 2 * MM, *T = d + 3 * MM, *xi = d + 4 * MM, *mu = xi + M;
+    double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM;
+    SGP_CUDA(ctx, cudaMemcpyAsync(Lam, Lambda0, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(xi, xi0, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    axpby_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(Lam, Lam, 1.0, psi2, w, MM);        // Lambda = Lambda0 + w Psi2
+    axpby_kernel<<<nblocks(M), 256, 0, ctx->stream>>>(xi, xi, 1.0, psi1, w, M);            // xi = xi0 + w Psi1
+    int rc = sgp_potrf_lower(ctx, Lam, M); if (rc) return rc;                               // Lambda = L L'
+    identity_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(X, M);
+    rc = sgp_trsm_lower(ctx, Lam, X, M, M, false); if (rc) return rc;                       // X = L^-1
+    rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, X, M, X, M, 0.0, Sig, M, 0); if (rc) return rc;  // Sigma = X' X
+    rc = sgp_gemm(ctx, 0, 0, M, 1, M, 1.0, Sig, M, xi, M, 0.0, mu, M, 0); if (rc) return rc; // mu = Sigma xi
+    if (Sigma_v) SGP_CUDA(ctx, cudaMemcpyAsync(Sigma_v, Sig, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mu_v) SGP_CUDA(ctx, cudaMemcpyAsync(mu_v, mu, M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Uv) {
+        add_outer_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(Sig, mu, M);                 // R_v = Sigma + mu mu'
+        rc = sgp_potrf_lower(ctx, Sig, M); if (rc) return rc;
+        dim3 tg((M + 31) / 32, (M + 31) / 32), tb(32, 8);
+        transpose_kernel<<<tg, tb, 0, ctx->stream>>>(Sig, T, M);                            // Uv = L_R'
+        SGP_CUDA(ctx, cudaMemcpyAsync(Uv, T, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SGP_CUDA(ctx, cudaGetLastError());
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SGP_OK;
+}
+
+int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI1, double* sumI2) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: run a sweep first");
+    if (!ctx->have_kuu) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: sgp_kuu_factor first");
+    if (ctx->Dout != 1) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "w_terms: scalar-output statistics only");
+    if (!mu_v || !Uv) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: mu_v and Uv are inputs");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const int M = ctx->M; const size_t MM = (size_t)M * M;
+    double* d = ctx->dense_dev + 64;
+    double *A = d, *U = d + MM, *C = d + 2 * MM, *mu = d + 4 * MM, *res = mu + M;
+    double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM; double* scal = psi1 + M;
+    SGP_CUDA(ctx, cudaMemcpyAsync(A, psi2, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(U, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(mu, mu_v, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, A, M, M, false); if (rc) return rc;       // L^-1 Psi2
+    rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, A, M, M, true); if (rc) return rc;            // K_uu^-1 Psi2
+    dot_kernel<<<1, 256, 0, ctx->stream>>>(A, (size_t)M + 1, nullptr, 0, (size_t)M, res);              // trace
+    rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, U, M, psi2, M, 0.0, C, M, 0); if (rc) return rc; // Uv Psi2
+    dot_kernel<<<1, 256, 0, ctx->stream>>>(C, 1, U, 1, MM, res + 1);                                   // <Uv Psi2, Uv>
+    dot_kernel<<<1, 256, 0, ctx->stream>>>(mu, 1, psi1, 1, (size_t)M, res + 2);                        // mu' Psi1
+    double h[3], sc[4];
+    SGP_CUDA(ctx, cudaMemcpyAsync(h, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(sc, scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (sumI1) *sumI1 = sc[0] - h[0];
+    if (sumI2) *sumI2 = sc[1] - 2.0 * h[2] + h[1];
+    return SGP_OK;
+}
+
+int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* mu_v, double* out) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "predict_mean: set_kernel and set_inducing first");
+    if (Nt < 1 || !Xt || !mu_v || !out) SGP_FAIL(ctx, SGP_ERR_ARG, "predict_mean: bad arguments");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const int M = ctx->M, D = ctx->D;
+    double *xt = nullptr, *o = nullptr, *mu = nullptr;
+    SGP_CUDA(ctx, cudaMalloc((void**)&xt, (size_t)Nt * D * sizeof(double)));
+    cudaMalloc((void**)&o, (size_t)Nt * sizeof(double));
+    cudaMalloc((void**)&mu, ((size_t)M + SGP_MAX_D) * sizeof(double));
+    int rc = SGP_OK;
+    double inv[SGP_MAX_D];
+    for (int d = 0; d < D; ++d) inv[d] = 1.0 / ctx->ell[d];
+    if (!o || !mu) rc = SGP_ERR_CUDA;
+    if (!rc && cudaMemcpyAsync(xt, Xt, (size_t)Nt * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
+    if (!rc && cudaMemcpyAsync(mu, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
+    if (!rc && cudaMemcpyAsync(mu + M, inv, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
+    if (!rc) {
+        size_t sh = (size_t)256 * (D + 1) * sizeof(double);
+        predict_kernel<<<nblocks((size_t)Nt, 128), 128, sh, ctx->stream>>>(xt, ctx->Z_dev, mu, o, Nt, M, D, ctx->kind, ctx->variance, mu + M);
+        if (cudaGetLastError() != cudaSuccess) rc = SGP_ERR_CUDA;
+    }
+    if (!rc && cudaMemcpyAsync(out, o, (size_t)Nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = SGP_ERR_CUDA;
+    cudaFree(xt); cudaFree(o); cudaFree(mu);
+    if (rc == SGP_ERR_CUDA) ctx->err = "predict_mean: CUDA failure";
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// libsgp internals shared by the translation units (not part of the public ABI; see include/sgp.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/sgp.h"
+
+#define SGP_MAX_D 16
+#define SGP_EXP_TAB 2048                       // entries of the 2^(j/2048) table
+#define SGP_EXP_SCALE 2954.639443740597       // 2048 / ln 2
+
+struct SgpComm;                                // NCCL handle (comm.cu)
+
+struct sgp_ctx {
+    int dev = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+
+    // kernel(theta)
+    int kind = SGP_KERNEL_SE, D = 0;
+    double variance = 1.0;
+    double ell[SGP_MAX_D] = {0};
+    bool have_kernel = false;
+
+    // inducing inputs
+    int M = 0;
+    double* Z_dev = nullptr;        // M x D raw (point-major)
+    double center[SGP_MAX_D] = {0}; // mean of Z: both X and Z are shifted by it before scaling (shift invariance)
+    bool have_Z = false;
+
+    // data (resident)
+    int64_t N = 0, Ncap = 0;        // Ncap: allocated points (multiple of the chunk size, zero padded)
+    int Dcap = 0;                   // input dimension the owned X buffer was allocated for
+    double *X_dev = nullptr, *y_dev = nullptr, *yv_dev = nullptr, *w_dev = nullptr;
+    bool own_data = false, have_yv = false, have_w = false;
+
+    // statistics of the last sweep: stats_dev = [psi2 (M*M) | psi1 (M*Dout) | psi0 | sum_y2 | sum_w | n]
+    double* stats_dev = nullptr;
+    size_t stats_cap = 0;
+    int Dout = 1;
+    bool have_stats = false;
+
+    // scratch
+    double* work_dev = nullptr;  size_t work_cap = 0;      // split-N partials
+    double* zrec_dev = nullptr;  size_t zrec_cap = 0;      // prepared inducing rows
+    double* exptab_dev = nullptr;
+    double* dense_dev = nullptr; size_t dense_cap = 0;     // M x M scratch for factorisations
+    int* info_dev = nullptr;
+
+    // K_uu factor
+    double* KuuL_dev = nullptr; int KuuL_M = 0; bool have_kuu = false;
+
+    // uncertain-input scratch (sigma-point cloud)
+    double *sp_X_dev = nullptr, *sp_w_dev = nullptr, *sp_y_dev = nullptr; size_t sp_cap = 0;
+
+    SgpComm* comm = nullptr;
+
+    // last sweep launch record
+    int last_launches = 0, last_grid = 0, last_block = 0, last_smem = 0;
+    float last_main_ms = 0.f;
+};
+
+#define SGP_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return SGP_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+#define SGP_FAIL(ctx, code, msg) do { (ctx)->err = (msg); return (code); } while (0)
+
+int sgp_ensure(sgp_ctx* ctx, double** p, size_t* cap, size_t need_doubles);
+
+// sweep.cu
+int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const double* yv, const double* w, int64_t N,
+                     int64_t Ncap, bool time_main);
+// dense.cu
+int sgp_potrf_lower(sgp_ctx* ctx, double* A, int M);                              // in place, column-major, lower
+int sgp_trsm_lower(sgp_ctx* ctx, const double* L, double* B, int M, int nrhs, bool trans);  // L X = B or L' X = B
+int sgp_kuu_build(sgp_ctx* ctx, double* K, double jitter);
+// comm.cu
+int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count);
+void sgp_comm_destroy(sgp_ctx* ctx);
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// exp(t) for an argument ALREADY scaled by 2048/ln2 (tp = t * SGP_EXP_SCALE).  Range reduction by the magic-number
+// trick, 2^(j/2048) from a shared-memory table, cubic Taylor remainder (|x| <= ln2/4096: x^4/24 < 4e-17), exponent
+// patched with integer adds.  7 FP64-pipe instructions.  Returns 0 below exp(-677).
+__device__ __forceinline__ double exp_scaled(double tp, const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+    const double C1 = 3.384507717577858e-04;           // ln2/2048
+    const double C2 = 5.72744624517204e-08;           // C1^2 / 2
+    const double C3 = 6.461528672932365e-12;           // C1^3 / 6
+    double m = tp + MAGIC;
+    int n = __double2loint(m);
+    double nd = m - MAGIC;
+    double r = tp - nd;
+    double p = fma(r, C3, C2);
+    p = fma(p, r, C1);
+    p = p * r;
+    double T = tab[n & (SGP_EXP_TAB - 1)];
+    double res = fma(T, p, T);
+    int hi = __double2hiint(res) + ((n >> 11) << 20);
+    res = __hiloint2double(hi, __double2loint(res));
+    // tp < -2.0e6  <=>  sign set and magnitude above: compare the high word as an unsigned integer (ALU pipe)
+    return ((unsigned)__double2hiint(tp) > 0xC13E8480u) ? 0.0 : res;   // hi word of -2.0e6 = 0xC13E8480
+}
+// U interleaved evaluations of exp_scaled (independent chains written stage by stage so that ptxas interleaves them).
+template <int U>
+__device__ __forceinline__ void exp_scaled_v(const double (&tp)[U], double (&out)[U], const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;
+    const double C1 = 3.384507717577858e-04, C2 = 5.72744624517204e-08, C3 = 6.461528672932365e-12;
+    double m[U], r[U], p[U], T[U];
+    int n[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) m[u] = tp[u] + MAGIC;
+#pragma unroll
+    for (int u = 0; u < U; ++u) { n[u] = __double2loint(m[u]); T[u] = tab[n[u] & (SGP_EXP_TAB - 1)]; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) m[u] = m[u] - MAGIC;
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = tp[u] - m[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(r[u], C3, C2);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], C1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = p[u] * r[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        double res = fma(T[u], p[u], T[u]);
+        int hi = __double2hiint(res) + ((n[u] >> 11) << 20);
+        res = __hiloint2double(hi, __double2loint(res));
+        out[u] = ((unsigned)__double2hiint(tp[u]) > 0xC13E8480u) ? 0.0 : res;
+    }
+}
+#endif

@@ -1,0 +1,174 @@
+"""Thin object wrapper over the libsgp C ABI (host NumPy arrays in / out).  One SGPContext per GPU."""
+import ctypes
+import numpy as np
+
+from . import _lib
+
+SE, MATERN32, MATERN52 = 0, 1, 2
+SRCUBATURE, GENUT, GAUSSHERMITE, CLOSED_FORM_SE = 0, 1, 2, 3
+
+
+class SGPError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libsgp error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_lib.c_double_p)
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class SGPContext:
+    """Owns one ``sgp_ctx``.  Layout notes: the C ABI takes Julia's column-major D x N; a C-contiguous NumPy array of
+    shape (N, D) is the same memory, so inputs here are (N, D) / (M, D) row-per-point arrays.  M x M results come back
+    column-major; they are symmetric or explicitly triangular, and are returned as Fortran-ordered views."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.sgp_create(ctypes.byref(h), int(device))
+        if rc != 0:
+            raise SGPError(rc, "sgp_create failed (no CUDA device / not sm_100?)")
+        self.h = h
+        self.M = 0
+        self.D = 0
+        self.N = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sgp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SGPError(rc, self.lib.sgp_last_error(self.h).decode())
+
+    # ---- state ----
+    def set_kernel(self, variance, lengthscale, D=None, kind=SE):
+        ell = np.atleast_1d(np.asarray(lengthscale, dtype=np.float64))
+        D = ell.size if D is None else int(D)
+        ell = np.ascontiguousarray(np.broadcast_to(ell, (D,)))
+        self._ck(self.lib.sgp_set_kernel(self.h, int(kind), D, float(variance), _p(ell)))
+        self.D = D
+
+    def set_inducing(self, Z):
+        Z = _f64(Z)
+        Z = Z.reshape(-1, self.D)
+        self._ck(self.lib.sgp_set_inducing(self.h, Z.shape[0], _p(Z)))
+        self.M = Z.shape[0]
+
+    def set_data(self, X, ybar=None, yvar=None, wts=None):
+        X = _f64(X).reshape(-1, self.D)
+        N = X.shape[0]
+        ybar, yvar, wts = _f64(ybar, (N,)), _f64(yvar, (N,)), _f64(wts, (N,))
+        self._ck(self.lib.sgp_set_data(self.h, N, _p(X), _p(ybar), _p(yvar), _p(wts)))
+        self.N = N
+
+    def set_targets(self, ybar, yvar=None):
+        ybar, yvar = _f64(ybar, (self.N,)), _f64(yvar, (self.N,))
+        self._ck(self.lib.sgp_set_targets(self.h, _p(ybar), _p(yvar)))
+
+    def set_data_dev(self, N, X_ptr, y_ptr, yv_ptr=None, w_ptr=None):
+        self._ck(self.lib.sgp_set_data_dev(self.h, int(N), X_ptr, y_ptr, yv_ptr, w_ptr))
+        self.N = int(N)
+
+    # ---- sweep ----
+    def sweep_psi(self, fetch=True):
+        M = self.M
+        if not fetch:
+            self._ck(self.lib.sgp_sweep_psi(self.h, None, None, None, None))
+            return None
+        psi0, sy2 = ctypes.c_double(), ctypes.c_double()
+        psi1 = np.empty(M)
+        psi2 = np.empty((M, M), order="F")
+        self._ck(self.lib.sgp_sweep_psi(self.h, ctypes.byref(psi0), _p(psi1), _p(psi2), ctypes.byref(sy2)))
+        return psi0.value, psi1, psi2, sy2.value
+
+    def sweep_psi_uncertain(self, method, mean, cov, R=None, D_out=1, p=21, want_psi1_n=False):
+        mean = _f64(mean).reshape(-1, self.D)
+        N = mean.shape[0]
+        cov = _f64(cov).reshape(N, self.D, self.D)
+        M = self.M
+        if R is not None:
+            R = _f64(R).reshape(N, D_out)
+            R = np.ascontiguousarray(R.T).T if False else np.asfortranarray(R)   # N x D_out column-major
+        psi0 = ctypes.c_double()
+        psi1 = np.empty((M, D_out), order="F")
+        psi2 = np.empty((M, M), order="F")
+        psi1_n = np.empty((M, N), order="F") if want_psi1_n else None
+        self._ck(self.lib.sgp_sweep_psi_uncertain(self.h, int(method), int(p), N, _p(mean), _p(cov), int(D_out), _p(R),
+                                                  ctypes.byref(psi0), _p(psi1), _p(psi2), _p(psi1_n)))
+        return psi0.value, (psi1[:, 0] if D_out == 1 else psi1), psi2, (None if psi1_n is None else psi1_n.T)
+
+    def sweep_timed(self, reps=1):
+        a, b = ctypes.c_float(), ctypes.c_float()
+        self._ck(self.lib.sgp_sweep_timed(self.h, int(reps), ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def last_sweep_info(self):
+        v = [ctypes.c_int() for _ in range(4)]
+        self._ck(self.lib.sgp_last_sweep_info(self.h, *[ctypes.byref(x) for x in v]))
+        return dict(launches=v[0].value, grid=v[1].value, block=v[2].value, smem_bytes=v[3].value)
+
+    # ---- factorisations ----
+    def kuu_factor(self, jitter=0.0, fetch=True):
+        L = np.empty((self.M, self.M), order="F") if fetch else None
+        self._ck(self.lib.sgp_kuu_factor(self.h, float(jitter), _p(L)))
+        return L
+
+    def kuu_solve(self, B):
+        B = np.asfortranarray(np.array(B, dtype=np.float64).reshape(self.M, -1))
+        self._ck(self.lib.sgp_kuu_solve(self.h, B.shape[1], _p(B)))
+        return B
+
+    def posterior_v(self, xi0, Lambda0, w, want_Uv=True):
+        M = self.M
+        xi0 = _f64(xi0, (M,))
+        Lam0 = np.asfortranarray(np.asarray(Lambda0, dtype=np.float64).reshape(M, M))
+        mu = np.empty(M)
+        Sigma = np.empty((M, M), order="F")
+        Uv = np.empty((M, M), order="F") if want_Uv else None
+        self._ck(self.lib.sgp_posterior_v(self.h, _p(xi0), _p(Lam0), float(w), _p(mu), _p(Sigma), _p(Uv)))
+        return mu, Sigma, Uv
+
+    def w_terms(self, mu_v, Uv):
+        M = self.M
+        mu_v = _f64(mu_v, (M,))
+        Uv = np.asfortranarray(np.asarray(Uv, dtype=np.float64).reshape(M, M))
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._ck(self.lib.sgp_w_terms(self.h, _p(mu_v), _p(Uv), ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def predict_mean(self, Xt, mu_v):
+        Xt = _f64(Xt).reshape(-1, self.D)
+        mu_v = _f64(mu_v, (self.M,))
+        out = np.empty(Xt.shape[0])
+        self._ck(self.lib.sgp_predict_mean(self.h, Xt.shape[0], _p(Xt), _p(mu_v), _p(out)))
+        return out
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        rc = _lib.load().sgp_comm_unique_id(buf)
+        if rc != 0:
+            raise SGPError(rc, "sgp_comm_unique_id failed (libnccl.so.2 not found?)")
+        return buf.raw
+
+    def comm_init(self, nranks, rank, uid):
+        self._ck(self.lib.sgp_comm_init(self.h, int(nranks), int(rank), ctypes.create_string_buffer(uid, 128)))

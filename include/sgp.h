@@ -1,0 +1,124 @@
+/*
+ * libsgp -- C ABI of the B200-native data sweep for sparse variational GP factor nodes.
+ *
+ * Drop-in boundary for ONE hot path of biaslab/GaussianProcessNode: the per-iteration pass over N inputs that
+ * builds K_uf and accumulates Psi0 / Psi1 / Psi2, plus the M x M K_uu / posterior factorisations.  The reference
+ * has no FFI: the path sits behind ReactiveMP's @rule / @average_energy dispatch (Julia multiple dispatch).  Each
+ * entry point below states the reference code it replaces (file:line under /root/reference); INTEGRATION.md shows
+ * the `ccall` stubs a maintainer adds to GPnode/UniSGPnode.jl / MultiSGPnode.jl so the rule surface stays unchanged.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature; `int` return: 0 = ok, < 0 = error (see SGP_ERR_*),
+ *     human-readable text via sgp_last_error(ctx).
+ *   - every pointer is a HOST pointer owned by the caller unless the name ends in `_dev`; the library owns all
+ *     device memory.  Matrices are column-major Float64, exactly Julia's layout: X is D x N (point n = D
+ *     contiguous doubles), Z is D x M, Psi2 / L / Sigma are M x M.
+ *   - one sgp_ctx per GPU per host task; a ctx is NOT thread-safe.  All work of a ctx runs on its own stream.
+ *   - there is no CPU fallback: without a CUDA device every call fails with SGP_ERR_CUDA.
+ */
+#ifndef SGP_H
+#define SGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgp_ctx sgp_ctx;
+
+enum {
+    SGP_OK = 0,
+    SGP_ERR_ARG = -1,        /* bad argument / call order */
+    SGP_ERR_CUDA = -2,       /* CUDA runtime failure (no device, OOM, launch failure) */
+    SGP_ERR_NOT_PD = -3,     /* Cholesky met a non-positive pivot (reference: FastCholesky falls back silently) */
+    SGP_ERR_UNSUPPORTED = -4,
+    SGP_ERR_COMM = -5        /* NCCL failure */
+};
+
+/* kernel kinds: KernelFunctions convention, r = ||(x - z) ./ ell|| (experiments/regression_kin40k.ipynb:108) */
+enum { SGP_KERNEL_SE = 0, SGP_KERNEL_MATERN32 = 1, SGP_KERNEL_MATERN52 = 2 };
+
+/* expectation methods for uncertain inputs (ReactiveMP srcubature()/ghcubature(p), helper_functions/ut_approx.jl,
+ * closed-form SE-ARD extension) */
+enum { SGP_METHOD_SRCUBATURE = 0, SGP_METHOD_GENUT = 1, SGP_METHOD_GAUSSHERMITE = 2, SGP_METHOD_CLOSED_FORM_SE = 3 };
+
+/* ---- lifetime -------------------------------------------------------------------------------------------- */
+int sgp_create(sgp_ctx** ctx, int device_id);
+void sgp_destroy(sgp_ctx* ctx);
+const char* sgp_last_error(const sgp_ctx* ctx);
+/* library build string: "libsgp <version> sm_100a" */
+const char* sgp_version(void);
+
+/* ---- model state (what UniSGPMeta / MultiSGPMeta carry: helper_functions/gp_helperfunction.jl:33-73) ------ */
+/* kernel(theta) of the meta, already transformed by the host (softplus etc.): variance sigma^2, lengthscale[D]. */
+int sgp_set_kernel(sgp_ctx* ctx, int kind, int D, double variance, const double* lengthscale);
+/* meta.Xu flattened to D x M. */
+int sgp_set_inducing(sgp_ctx* ctx, int M, const double* Z);
+/* The data the N per-point rules would each see one element of: inputs X (D x N), targets ybar (y_n, or E[f_n] for
+ * classification; NULL = zeros), yvar (Var[f_n]; NULL = zeros), per-point weights wts (NULL = ones; sigma-point
+ * weights may be negative).  Copied to the device once and kept resident across VMP iterations. */
+int sgp_set_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts);
+/* replace only the targets (classification: E[f_n], Var[f_n] change every VMP iteration, X does not) */
+int sgp_set_targets(sgp_ctx* ctx, const double* ybar, const double* yvar);
+/* same as sgp_set_data but the pointers are device pointers on this ctx's device; data is used in place. */
+int sgp_set_data_dev(sgp_ctx* ctx, int64_t N, const double* X_dev, const double* ybar_dev, const double* yvar_dev,
+                     const double* wts_dev);
+
+/* ---- the sweep ------------------------------------------------------------------------------------------- */
+/* Replaces N invocations of `@rule UniSGP(:v)` (GPnode/UniSGPnode.jl:144-158, 161-173) and the running sums of
+ * `prod` (:62-73), and supplies what N invocations of `@rule UniSGP(:w)` (:196-238) need:
+ *   psi0 = sum_n w_n k(x_n,x_n),  psi1[M] = K_uf (w .* ybar),  psi2[M*M] = K_uf diag(w) K_uf' (full symmetric),
+ *   sum_y2 = sum_n w_n (ybar_n^2 + yvar_n).
+ * Any output pointer may be NULL (result stays on the device for the calls below).  With a communicator attached
+ * (sgp_comm_init) the statistics are all-reduced over ranks before they are returned. */
+int sgp_sweep_psi(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2);
+
+/* Uncertain inputs q(x_n) = N(mean_n, cov_n): replaces the cubature loop `approximate_kernel_expectation(!)`
+ * (GPnode/UniSGPnode.jl:11-37, GPnode/MultiSGPnode.jl:11-35) inside `@rule UniSGP(:v)` (:125-140) and
+ * `@rule MultiSGP(:v)/(:w)/(:out)` (GPnode/MultiSGPnode.jl:290-328, 367-444, 90-120), summed over the N nodes.
+ *   mean: d x N, cov: d x d x N (column-major per point), p: Gauss-Hermite order (method 2 only),
+ *   R: N x D_out row weights (MultiSGP: Y * W_bar, row n = (W_bar' mu_y_n)'; UniSGP: ybar; NULL = ones, D_out = 1)
+ *   psi1[M*D_out] = sum_n Psi1_n r_n' (column d = output d), psi2[M*M] = sum_n Psi2_n (no jitter added),
+ *   psi1_n[M*N] (optional, may be NULL) = per-point Psi1_n, needed by the :out / :w rules. */
+int sgp_sweep_psi_uncertain(sgp_ctx* ctx, int method, int p, int64_t N, const double* mean, const double* cov,
+                            int D_out, const double* R, double* psi0, double* psi1, double* psi2, double* psi1_n);
+
+/* ---- M x M factorisations --------------------------------------------------------------------------------- */
+/* K_uu = kernelmatrix(kernel(theta), Xu) + jitter*I ; L = fastcholesky!(K_uu).L
+ * (experiments/regression_kin40k.ipynb:183-184, classification_banana.ipynb:163-164).  L (M x M, lower, may be NULL). */
+int sgp_kuu_factor(sgp_ctx* ctx, double jitter, double* L);
+/* B <- K_uu^{-1} B for nrhs right-hand sides (M x nrhs); cholinv(Kuu) = solve with B = I
+ * (experiments/Pendulum_Wishart_2d.ipynb:2542-2543). */
+int sgp_kuu_solve(sgp_ctx* ctx, int nrhs, double* B);
+/* The N-th `prod` (GPnode/UniSGPnode.jl:62-73) on the statistics of the last sweep:
+ *   Lambda = Lambda0 + w Psi2, xi = xi0 + w Psi1, Sigma_v = cholinv(Lambda), mu_v = Sigma_v xi,
+ *   Uv = fastcholesky!(Sigma_v + mu_v mu_v').U.   Lambda0 (M x M) / xi0 (M) are the prior's natural parameters.
+ * Outputs may be NULL. */
+int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, double w, double* mu_v, double* Sigma_v,
+                    double* Uv);
+/* sum over n of the :w rule / energy ingredients (GPnode/UniSGPnode.jl:196-238, 337-387), from the last sweep:
+ *   sumI1 = Psi0 - tr(K_uu^{-1} Psi2),  sumI2 = sum_y2 - 2 mu_v' Psi1 + <Uv' Uv, Psi2>.
+ * mu_v / Uv are INPUTS (the previous sweep's posterior, as the VMP schedule has it); needs sgp_kuu_factor. */
+int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI1, double* sumI2);
+/* `@rule UniSGP(:out)` over a test set (GPnode/UniSGPnode.jl:96-104; regression_kin40k.ipynb:289-304): out = K_*u mu_v */
+int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* mu_v, double* out);
+
+/* ---- multi-GPU: N is sharded over ranks, one ctx per rank/GPU --------------------------------------------- */
+/* NCCL unique id (128 bytes) created on rank 0 and handed to the other ranks by the host. */
+int sgp_comm_unique_id(char id[128]);
+int sgp_comm_init(sgp_ctx* ctx, int nranks, int rank, const char id[128]);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------------ */
+/* Runs the sweep `reps` times on resident data without host copies and returns the mean device time of one sweep
+ * (CUDA events on the ctx stream) and of its dominant kernel alone. */
+int sgp_sweep_timed(sgp_ctx* ctx, int reps, float* ms_per_sweep, float* ms_main_kernel);
+/* number of kernels the last sweep launched, and the main kernel's launch geometry */
+int sgp_last_sweep_info(sgp_ctx* ctx, int* n_launches, int* grid, int* block, int* smem_bytes);
+/* device pointers of the resident statistics of the last sweep: [psi2 (M*M) | psi1 (M*D_out) | psi0 | sum_y2] */
+int sgp_stats_dev(sgp_ctx* ctx, double** psi2_dev, double** psi1_dev, double** scal_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGP_H */

@@ -1,0 +1,66 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/sgp.h declares,
+the ctypes table covers them all, and -- there being no CPU fallback -- creating a context without a GPU fails loudly."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "sgp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sgp_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from gaussianprocessnode_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_declares_the_expected_surface():
+    names = _declared()
+    for must in ("sgp_create", "sgp_destroy", "sgp_set_kernel", "sgp_set_inducing", "sgp_set_data", "sgp_sweep_psi",
+                 "sgp_sweep_psi_uncertain", "sgp_kuu_factor", "sgp_kuu_solve", "sgp_posterior_v", "sgp_w_terms",
+                 "sgp_predict_mean", "sgp_comm_unique_id", "sgp_comm_init"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from gaussianprocessnode_b200 import _lib
+    for name in _declared():
+        assert hasattr(lib, name), "libsgp.so does not export %s" % name
+        assert name in _lib.SIGNATURES, "ctypes table misses %s" % name
+    assert set(_lib.SIGNATURES) == set(_declared())
+    assert b"sm_100a" in lib.sgp_version()
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "sgp.h")).read()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", src, flags=re.S).lower()
+    assert "at::" not in src and "cudaStream_t" not in src
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    rc = lib.sgp_create(ctypes.byref(h), 0)
+    assert rc != 0 and not h.value
+    from gaussianprocessnode_b200 import SGPContext, SGPError
+    with pytest.raises(SGPError):
+        SGPContext(0)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "gaussianprocessnode_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f

@@ -1,0 +1,108 @@
+"""Parity of the M x M factorisations, posterior update, :w terms and prediction against the oracle / LAPACK.
+Solves are judged by scaled residual (backward error): two backward-stable solvers legitimately differ by cond * eps
+in the forward error ('Conditioning vs the 1e-10 gate')."""
+import numpy as np
+import pytest
+from scipy.linalg import solve_triangular
+
+from oracle import batched, kernels
+
+pytestmark = pytest.mark.gpu
+
+
+def fro(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gaussianprocessnode_b200 import SGPContext
+    c = SGPContext(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("M,D", [(1, 1), (20, 1), (48, 2), (64, 2), (65, 3), (200, 8), (512, 8), (600, 8), (1024, 8)])
+def test_kuu_factor_and_solve(ctx, M, D):
+    rng = np.random.default_rng(M)
+    Z = rng.normal(size=(M, D)) * (3.0 if D <= 2 else 1.0)
+    ell = np.full(D, 0.8)
+    jitter = 1e-8
+    ctx.set_kernel(1.3, ell, D=D); ctx.set_inducing(Z)
+    L = ctx.kuu_factor(jitter)
+    K = kernels.kuu(Z, 1.3, ell, jitter=jitter)
+    assert np.allclose(np.triu(L, 1), 0.0)
+    assert fro(L @ L.T, K) < 1e-13                                   # factorisation residual
+    if np.linalg.cond(K) < 1e6:
+        assert fro(L, np.linalg.cholesky(K)) < 1e-10                 # factor itself when well conditioned
+    B = rng.normal(size=(M, 3))
+    Xs = ctx.kuu_solve(B)
+    resid = np.linalg.norm(K @ Xs - B) / (np.linalg.norm(K) * np.linalg.norm(Xs) + np.linalg.norm(B))
+    assert resid < 1e-13
+
+
+def test_not_positive_definite_is_an_error(ctx):
+    from gaussianprocessnode_b200 import SGPError
+    Z = np.zeros((8, 1))                                             # identical inducing points, no jitter: singular
+    ctx.set_kernel(1.0, np.array([1.0])); ctx.set_inducing(Z)
+    with pytest.raises(SGPError) as e:
+        ctx.kuu_factor(0.0)
+    assert e.value.code == -3
+
+
+@pytest.mark.parametrize("N,D,M,w", [(50, 1, 20, 25.0), (2000, 2, 64, 3.0), (5000, 8, 256, 100.0), (10000, 8, 512, 1.0e4)])
+def test_posterior_and_w_terms(ctx, N, D, M, w):
+    rng = np.random.default_rng(N + M)
+    X = rng.normal(size=(N, D)); y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=N)
+    Z = X[rng.choice(N, M, replace=False)] if D > 1 else np.linspace(-2.5, 2.5, M)[:, None]
+    ell = np.full(D, 1.5 if D > 1 else 0.6); var = 1.2; jitter = 1e-6
+    ctx.set_kernel(var, ell, D=D); ctx.set_inducing(Z); ctx.set_data(X, y)
+    psi0, psi1, psi2, sy2 = ctx.sweep_psi()
+    xi0 = np.zeros(M); Lam0 = np.eye(M) / 50.0                       # prior N(0, 50 I) (regression_kin40k.ipynb:200-201)
+    mu, Sigma, Uv = ctx.posterior_v(xi0, Lam0, w)
+    o_mu, o_Sig, o_Uv, o_Lam, o_xi = batched.posterior_v(xi0, Lam0, w, psi1, psi2)
+    # backward errors: Lambda Sigma = I, Lambda mu = xi, Uv'Uv = Sigma + mu mu'
+    nL = np.linalg.norm(o_Lam, 2)
+    assert np.linalg.norm(o_Lam @ Sigma - np.eye(M)) / (nL * np.linalg.norm(Sigma, 2) * M) < 1e-13
+    assert np.linalg.norm(o_Lam @ mu - o_xi) / (nL * np.linalg.norm(mu) + np.linalg.norm(o_xi)) < 1e-11
+    assert fro(Uv.T @ Uv, Sigma + np.outer(mu, mu)) < 1e-12
+    assert np.allclose(np.tril(Uv, -1), 0.0)
+    cond = np.linalg.cond(o_Lam)
+    assert fro(Sigma, o_Sig) < max(1e-10, 50 * cond * 2.2e-16)        # forward error bounded by conditioning
+    assert fro(mu, o_mu) < max(1e-10, 50 * cond * 2.2e-16)
+    # :w terms with the posterior as input
+    L = ctx.kuu_factor(jitter)
+    s1, s2 = ctx.w_terms(o_mu, o_Uv)
+    Lo = np.linalg.cholesky(kernels.kuu(Z, var, ell, jitter=jitter))
+    o1, o2 = batched.w_terms(psi0, psi1, psi2, sy2, Lo, o_mu, o_Uv)
+    scale = abs(psi0) + abs(sy2)
+    # tr(K_uu^-1 Psi2) inherits cond(K_uu) * eps from ANY backward-stable solver: tolerance is conditioning-aware
+    condK = np.linalg.cond(kernels.kuu(Z, var, ell, jitter=jitter))
+    tol1 = max(1e-10 * scale, 50 * condK * 2.2e-16 * abs(psi0 - o1))
+    assert abs(s1 - o1) < tol1, (s1, o1, condK)
+    assert abs(s2 - o2) < 1e-10 * max(abs(o2), scale), (s2, o2)
+    # free energy of the regression model (<= 1e-8 relative, north_star)
+    a, b = batched.gamma_posterior(1.0, 1.0, N, o1, o2)
+    a2, b2 = batched.gamma_posterior(1.0, 1.0, N, s1, s2)
+    F_o = batched.free_energy_regression(N, o1, o2, (a, b), (1.0, 1.0), o_mu, o_Sig, np.zeros(M), 50.0 * np.eye(M))
+    F_g = batched.free_energy_regression(N, s1, s2, (a2, b2), (1.0, 1.0), mu, 0.5 * (Sigma + Sigma.T), np.zeros(M), 50.0 * np.eye(M))
+    assert abs(F_g - F_o) <= 1e-8 * abs(F_o) + (a / b) * tol1, (F_g, F_o)   # + the conditioning-limited part of sumI1
+
+
+def test_kin40k_golden_chain_on_gpu(ctx, kin40k):
+    """K_*u mu_v over the 30000 test points with the reference's saved posterior reproduces the notebook's SMSE."""
+    sp = kernels.softplus(kin40k["theta_raw"])
+    Xu = kin40k["xtrain"][kin40k["xu_ids"]]
+    ctx.set_kernel(sp[0], sp[1:]); ctx.set_inducing(Xu)
+    pred = ctx.predict_mean(kin40k["xtest"], kin40k["mu_v"])
+    assert abs(batched.smse(kin40k["ytest"], pred) - 0.08343114079545057) < 1e-12
+    assert fro(pred, batched.predict_mean(kin40k["xtest"], Xu, sp[0], sp[1:], kin40k["mu_v"])) < 1e-12
+
+
+def test_banana_golden_chain_on_gpu(ctx, banana):
+    sp = kernels.softplus(banana["theta_raw"])
+    x = banana["x"]; Xu = x[:4000][banana["xu_ids"]]
+    ctx.set_kernel(sp[0], sp[1:]); ctx.set_inducing(Xu)
+    m = ctx.predict_mean(x[4000:5300], banana["mu_v"])
+    yt = (banana["label"][4000:5300] > 0).astype(float)
+    assert int(np.sum(np.abs((m > 0).astype(float) - yt))) == 125

@@ -1,0 +1,143 @@
+"""Parity of the CUDA sweep (through the C ABI) against the oracle.  Tolerance from BASELINE.json's north_star:
+relative Frobenius error <= 1e-10 on the Psi statistics."""
+import numpy as np
+import pytest
+
+from oracle import batched, kernels
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def fro(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gaussianprocessnode_b200 import SGPContext
+    c = SGPContext(0)
+    yield c
+    c.close()
+
+
+def _check(ctx, X, y, Z, var, ell, yvar=None, w=None, tol=TOL):
+    D = Z.shape[1]
+    ctx.set_kernel(var, ell, D=D)
+    ctx.set_inducing(Z)
+    ctx.set_data(X, y, yvar, w)
+    psi0, psi1, psi2, sy2 = ctx.sweep_psi()
+    o0, o1, o2, oy = batched.psi_stats_point(X, y, Z, var, ell, weights=w, yvar=yvar)
+    assert abs(psi0 - o0) <= tol * max(abs(o0), 1.0)
+    assert abs(sy2 - oy) <= tol * max(abs(oy), 1.0)
+    assert fro(psi1, o1) <= tol, fro(psi1, o1)
+    assert fro(psi2, o2) <= tol, fro(psi2, o2)
+    assert np.array_equal(psi2, psi2.T)           # exactly symmetric (mirrored, not recomputed)
+    return fro(psi2, o2)
+
+
+def test_toy_regression(ctx, toy):
+    # configs[0]: toy 1-D regression, N = 50, M = 20 (GPT_regression.ipynb:765-767), theta = [1, 1]
+    X = toy["xtrain_toyregression"][:, None]; y = toy["ytrain_toyregression"]
+    Z = np.linspace(-4, 4, 20)[:, None]
+    _check(ctx, X, y, Z, 1.0, np.array([1.0]))
+    _check(ctx, X, y, Z, 0.0362, np.array([0.5398]))          # the notebook's optimum
+
+
+def test_kin40k_shape(ctx, kin40k):
+    # configs[1]: D = 8, N = 10000, M = 512 (first 512 fixture rows) and the notebook's M = 600
+    X, y = kin40k["xtrain"], kin40k["ytrain"]
+    sp = kernels.softplus(kin40k["theta_raw"])
+    for M in (512, 600):
+        Z = X[kin40k["xu_ids"][:M]]
+        _check(ctx, X, y, Z, 1.0, np.ones(8))                 # theta_init (regression_kin40k.ipynb:112)
+        _check(ctx, X, y, Z, sp[0], sp[1:])                   # fixture optimum
+    # the reference's schedule: 20 mini-batches of 500 sum to the full sweep
+    Z = X[kin40k["xu_ids"][:512]]
+    ctx.set_kernel(sp[0], sp[1:]); ctx.set_inducing(Z)
+    acc2 = np.zeros((512, 512)); acc1 = np.zeros(512)
+    for b in range(20):
+        ctx.set_data(X[500 * b:500 * (b + 1)], y[500 * b:500 * (b + 1)])
+        _, p1, p2, _ = ctx.sweep_psi()
+        acc1 += p1; acc2 += p2
+    ctx.set_data(X, y)
+    _, p1, p2, _ = ctx.sweep_psi()
+    assert fro(acc2, p2) < 1e-13 and fro(acc1, p1) < 1e-13
+
+
+def test_banana_shape(ctx, banana):
+    # configs[2]: D = 2, N = 4000, M = 64 and the notebook's M = 500; pseudo-targets E[f], Var[f] as in classification
+    X = banana["x"][:4000]; lab = (banana["label"][:4000] > 0).astype(float)
+    sp = kernels.softplus(banana["theta_raw"])
+    rng = np.random.default_rng(1)
+    Ef, Vf = batched.probit_moments(rng.normal(size=4000), np.full(4000, 0.5), lab)
+    for M in (64, 500):
+        Z = X[banana["xu_ids"][:M]]
+        _check(ctx, X, Ef, Z, sp[0], sp[1:], yvar=Vf)
+
+
+@pytest.mark.parametrize("N,D,M", [(1, 1, 1), (31, 3, 7), (33, 2, 65), (1000, 8, 129), (4097, 5, 200), (777, 12, 300), (50, 16, 48)])
+def test_ragged_shapes(ctx, N, D, M):
+    rng = np.random.default_rng(N + D + M)
+    X = rng.normal(size=(N, D)); Z = rng.normal(size=(M, D)); y = rng.normal(size=N)
+    ell = 0.7 + rng.random(D) * 2.0
+    _check(ctx, X, y, Z, 1.7, ell)
+
+
+def test_weights_including_negative(ctx):
+    rng = np.random.default_rng(5)
+    N, D, M = 1500, 2, 48
+    X = rng.normal(size=(N, D)); Z = rng.normal(size=(M, D)); y = rng.normal(size=N)
+    w = rng.normal(size=N)                                     # sigma-point weights can be negative (GenUT)
+    _check(ctx, X, y, Z, 1.0, np.array([1.0, 1.3]), w=w, tol=1e-9)   # cancellation: Psi2 is no longer a sum of positives
+    _check(ctx, X, y, Z, 1.0, np.array([1.0, 1.3]), w=np.abs(w))
+
+
+def test_far_from_origin_inputs(ctx):
+    # the expanded-square form is evaluated after centring on the inducing-point mean: offsets must not cost accuracy
+    rng = np.random.default_rng(6)
+    X = rng.normal(size=(600, 3)) + 1.0e4; Z = rng.normal(size=(40, 3)) + 1.0e4; y = rng.normal(size=600)
+    _check(ctx, X, y, Z, 2.0, np.array([1.0, 2.0, 0.5]), tol=1e-9)
+
+
+def test_far_points_underflow_to_zero(ctx):
+    X = np.array([[0.0], [1.0e3], [-5.0e4]]); Z = np.array([[0.0], [1.0]]); y = np.ones(3)
+    _check(ctx, X, y, Z, 1.0, np.array([1.0]))
+
+
+def test_determinism(ctx):
+    rng = np.random.default_rng(8)
+    X = rng.normal(size=(20000, 8)); Z = rng.normal(size=(256, 8)); y = rng.normal(size=20000)
+    ctx.set_kernel(1.0, np.full(8, 2.0)); ctx.set_inducing(Z); ctx.set_data(X, y)
+    a = ctx.sweep_psi(); b = ctx.sweep_psi()
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1])
+
+
+def test_synthetic_M1024_exact_on_a_slice_and_properties_at_scale(ctx):
+    # configs[4] shape: D = 8, M = 1024, ell = 2, X ~ N(0, I).  Exact check where the oracle finishes in seconds
+    # (N = 60k), then size-independent properties at N = 2M: additivity over a partition and permutation invariance.
+    rng = np.random.default_rng(0)
+    D, M = 8, 1024
+    N = 2_000_000
+    X = rng.normal(size=(N, D)); y = np.sin(X @ rng.normal(size=D)) + 0.1 * rng.normal(size=N)
+    Z = X[np.random.default_rng(1).choice(N, M, replace=False)]
+    ell = np.full(D, 2.0)
+    err = _check(ctx, X[:60_000], y[:60_000], Z, 1.0, ell)
+    assert err < 1e-12
+    ctx.set_kernel(1.0, ell); ctx.set_inducing(Z)
+    ctx.set_data(X, y); full = ctx.sweep_psi()
+    parts2 = np.zeros((M, M)); parts1 = np.zeros(M); parts0 = 0.0
+    for lo, hi in ((0, 700_001), (700_001, 1_500_000), (1_500_000, N)):
+        ctx.set_data(X[lo:hi], y[lo:hi]); p = ctx.sweep_psi()
+        parts0 += p[0]; parts1 += p[1]; parts2 += p[2]
+    assert fro(parts2, full[2]) < 1e-12 and fro(parts1, full[1]) < 1e-11 and abs(parts0 - full[0]) < 1e-6
+    perm = np.random.default_rng(2).permutation(N)
+    ctx.set_data(X[perm], y[perm]); q = ctx.sweep_psi()
+    assert fro(q[2], full[2]) < 1e-12 and fro(q[1], full[1]) < 1e-11
+    # trace identity: tr(Psi2) = sum_n |k_n|^2, checked on a column sample of K
+    assert abs(np.trace(full[2]) - np.sum(np.diag(full[2]))) == 0.0
+    cols = np.arange(0, M, 128)
+    K = kernels.kernel_matrix(X, Z[cols], 1.0, ell)
+    np.testing.assert_allclose(np.diag(full[2])[cols], np.sum(K * K, axis=0), rtol=1e-11)
+    np.testing.assert_allclose(full[1][cols], K.T @ y, rtol=1e-9, atol=1e-7)
