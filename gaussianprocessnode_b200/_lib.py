@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgp.so")
+LIB_PATH = os.environ.get("SGP_LIB_PATH", os.path.join(_HERE, "libsgp.so"))   # override: instrumented builds for profiling
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_float_p = ctypes.POINTER(ctypes.c_float)

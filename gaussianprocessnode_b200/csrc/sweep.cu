@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kStages = 4;
 
 struct SweepParams {
@@ -72,7 +72,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
 //   Kt   [NB][LD]           generated K_uf tile, point-major; LD = 2*TM + 4 keeps DMMA fragment loads conflict-free
 //   tab  [2048]             2^(j/2048)
 //   zrec [2*TM][DPAD+1]     scaled inducing rows of blocks I and J (+ b_m)
-//   rec  [NB][REC]          scaled point records: x~[DPAD], a, w*y, w, pad
+//   rec  [2][NB][REC]       scaled point records (double-buffered): x~[DPAD], a, w*y, w, pad
 //   stage[kStages]: X raw [NB*D] | y [NB] | w [NB]
 //   mbarrier full[kStages]
 template <int TM, int NB, int DPAD>
@@ -85,7 +85,7 @@ struct Smem {
     static constexpr size_t tab = kt + (size_t)NB * LD;
     static constexpr size_t zrec = tab + SGP_EXP_TAB;
     static constexpr size_t rec = zrec + (size_t)2 * TM * ZR;
-    static constexpr size_t stage = rec + (size_t)NB * REC;
+    static constexpr size_t stage = rec + (size_t)2 * NB * REC;
     static constexpr size_t bars = stage + (size_t)kStages * STAGE;
     static constexpr size_t red = bars + kStages;             // psi1 cross-group reduction [kThreads]
     static constexpr size_t total_doubles = red + kThreads;
@@ -96,13 +96,13 @@ template <int TM, int NB, int DPAD, bool WEIGHTED>
 __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepParams p) {
     using S = Smem<TM, NB, DPAD>;
     constexpr int LD = S::LD, REC = S::REC, ZR = S::ZR;
-    constexpr int WM = TM / 2, WN = TM / 4;          // warp tile: 2 x 4 warps over the TM x TM CTA tile
+    constexpr int WM = TM / 4, WN = TM / 4;          // warp tile: 4 x 4 warps over the TM x TM CTA tile
     constexpr int MI = WM / 8, NJ = WN / 8;          // 8x8 DMMA blocks per warp tile
     extern __shared__ __align__(128) double smem[];
     double* Kt = smem + S::kt;
     double* tab = smem + S::tab;
     double* zrec = smem + S::zrec;
-    double* rec = smem + S::rec;
+    double* rec = smem + S::rec;                     // two record buffers: [2][NB][REC]
     double* stage = smem + S::stage;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + S::bars);
     double* red = smem + S::red;
@@ -143,20 +143,40 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepParams p)
         tma_load_1d(st + NB * SGP_MAX_D, p.y + n0, NB * 8, &full[s]);
         if (WEIGHTED) tma_load_1d(st + NB * SGP_MAX_D + NB, p.w + n0, NB * 8, &full[s]);
     };
+    // raw staged block -> scaled records, spread over all threads: one (point, dimension) element each, |x~|^2 by a
+    // shuffle reduction over the DPAD lanes of a point
+    auto prep = [&](int c) {
+        const int s = c % kStages;
+        mbar_wait(&full[s], (unsigned)((c / kStages) & 1));
+        const double* st = stage + (size_t)s * S::STAGE;
+        double* rb = rec + (size_t)(c & 1) * NB * REC;
+        for (int e = tid; e < NB * DPAD; e += kThreads) {      // NB*DPAD is a multiple of 32: whole warps take part
+            const int pt = e / DPAD, d = e % DPAD;
+            double v = 0.0;
+            if (d < D) v = (st[pt * D + d] - p.center[d]) * p.inv_ell_s[d];
+            rb[pt * REC + d] = v;
+            double a = v * v;
+#pragma unroll
+            for (int o = DPAD / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (d == 0) {
+                const long long n = (c_begin + c) * NB + pt;
+                const double wn = WEIGHTED ? st[NB * SGP_MAX_D + NB + pt] : 1.0;
+                rb[pt * REC + DPAD] = (n < p.N) ? -0.5 * a : -1.0e300;      // padded points generate exact zeros
+                rb[pt * REC + DPAD + 1] = wn * st[NB * SGP_MAX_D + pt];
+                rb[pt * REC + DPAD + 2] = wn;
+            }
+        }
+    };
     if (tid == 0)
         for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
 
     // generator mapping: rows_needed rows (TM on the diagonal, 2*TM otherwise), tpr threads per row
     const int rows_needed = diag ? TM : 2 * TM;
-    const int tpr = kThreads / rows_needed;            // 1, 2 or 4
+    const int tpr = kThreads / rows_needed;
     const int grow = tid % rows_needed;                // row inside [I-block | J-block]
     const int ggrp = tid / rows_needed;
-    const int npts = NB / tpr;                         // points per thread per chunk
+    const int npts = NB / tpr;                         // points per thread per chunk (multiple of 4)
     const int pt0 = ggrp * npts;
-    double zr[DPAD];
-#pragma unroll
-    for (int d = 0; d < DPAD; ++d) zr[d] = zrec[grow * ZR + d];
-    const double zb = zrec[grow * ZR + DPAD];
     double psi1_acc = 0.0;
 
     // MMA mapping
@@ -170,53 +190,54 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepParams p)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    if (nchunks > 0) prep(0);
+    __syncthreads();
+
+#ifdef SGP_PHASE_CLOCKS
+    long long pc[6] = {0, 0, 0, 0, 0, 0}; long long t0c = clock64(), t1c;
+#define PCLK(i) do { t1c = clock64(); pc[i] += t1c - t0c; t0c = t1c; } while (0)
+#else
+#define PCLK(i) do { } while (0)
+#endif
     for (int c = 0; c < nchunks; ++c) {
-        const int s = c % kStages;
-        if (tid == 0 && c + kStages - 1 < nchunks) issue(c + kStages - 1);
-        mbar_wait(&full[s], (unsigned)((c / kStages) & 1));
-        // ---- prep: raw staged block -> scaled records (NB threads) ---------------------------------------------
-        if (tid < NB) {
-            const double* st = stage + (size_t)s * S::STAGE;
-            const long long n = (c_begin + c) * NB + tid;
-            double a = 0.0;
-            double* r = rec + tid * REC;
-#pragma unroll
-            for (int d = 0; d < DPAD; ++d) {
-                double v = 0.0;
-                if (d < D) v = (st[tid * D + d] - p.center[d]) * p.inv_ell_s[d];
-                r[d] = v;
-                a = fma(v, v, a);
-            }
-            const double wn = WEIGHTED ? st[NB * SGP_MAX_D + NB + tid] : 1.0;
-            r[DPAD] = (n < p.N) ? -0.5 * a : -1.0e300;      // padded points generate exact zeros
-            r[DPAD + 1] = wn * st[NB * SGP_MAX_D + tid];
-            r[DPAD + 2] = wn;
-        }
-        __syncthreads();   // records ready; every warp is past the previous chunk's MMA, so Kt may be overwritten
+        const double* rb = rec + (size_t)(c & 1) * NB * REC;
         // ---- generate: K_uf tile rows for blocks I and J ------------------------------------------------------
-        // U independent dependency chains per thread: the FP64 pipe has ~10 cycles of latency and only two warps per
-        // scheduler are resident, so the 16-instruction chain of one value must be interleaved with others by hand
-        constexpr int U = 4;
+        {
+            double zr[DPAD];
+#pragma unroll
+            for (int d = 0; d < DPAD; ++d) zr[d] = zrec[grow * ZR + d];
+            const double zb = zrec[grow * ZR + DPAD];
+            // U independent dependency chains per thread: the FP64 pipe has ~30 cycles of dependent-issue latency, so
+            // the 16-instruction chain of one value is interleaved with others by hand (4 per thread x 4 warps per
+            // scheduler = 16 chains in flight)
+            constexpr int U = 4;
 #pragma unroll 1
-        for (int q = 0; q < npts; q += U) {
-            const double* r = rec + (pt0 + q) * REC;
-            double t[U];
+            for (int q = 0; q < npts; q += U) {
+                const double* r = rb + (pt0 + q) * REC;
+                double t[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) t[u] = r[u * REC + DPAD] + zb;
+                for (int u = 0; u < U; ++u) t[u] = r[u * REC + DPAD] + zb;
 #pragma unroll
-            for (int d = 0; d < DPAD; ++d)
+                for (int d = 0; d < DPAD; ++d)
 #pragma unroll
-                for (int u = 0; u < U; ++u) t[u] = fma(r[u * REC + d], zr[d], t[u]);
-            double k[U];
-            exp_scaled_v<U>(t, k, tab);
+                    for (int u = 0; u < U; ++u) t[u] = fma(r[u * REC + d], zr[d], t[u]);
+                double k[U];
+                exp_scaled_v<U>(t, k, tab);
 #pragma unroll
-            for (int u = 0; u < U; ++u) Kt[(pt0 + q + u) * LD + grow] = k[u];
-            if (diag) {
+                for (int u = 0; u < U; ++u) Kt[(pt0 + q + u) * LD + grow] = k[u];
+                if (diag) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) psi1_acc = fma(k[u], r[u * REC + DPAD + 1], psi1_acc);
+                    for (int u = 0; u < U; ++u) psi1_acc = fma(k[u], r[u * REC + DPAD + 1], psi1_acc);
+                }
             }
         }
-        __syncthreads();
+        PCLK(0);
+        __syncthreads();   // tile complete
+        PCLK(1);
+        // ---- stage + prepare the next chunk's records while the tile is consumed -------------------------------
+        if (tid == 0 && c + kStages - 1 < nchunks) issue(c + kStages - 1);
+        if (c + 1 < nchunks) prep(c + 1);
+        PCLK(2);
         // ---- consume: Psi2 tile += K_I diag(w) K_J'  (DMMA.8x8x4) ----------------------------------------------
 #pragma unroll 2
         for (int ks = 0; ks < NB / 4; ++ks) {
@@ -227,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepParams p)
 #pragma unroll
             for (int j = 0; j < NJ; ++j) b[j] = row[b_off + 8 * j];
             if (WEIGHTED) {
-                const double wn = rec[(ks * 4 + kq) * REC + DPAD + 2];
+                const double wn = rb[(ks * 4 + kq) * REC + DPAD + 2];
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) b[j] *= wn;
             }
@@ -236,7 +257,15 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepParams p)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+        PCLK(3);
+        __syncthreads();   // every warp is done with the tile and the next records are complete
+        PCLK(4);
     }
+#ifdef SGP_PHASE_CLOCKS
+    if (lane == 0 && (warp == 0 || warp == 15) && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == 8))
+        printf("cta %d (tile %d diag %d) warp %d chunks %d: per-chunk clk gen %lld | wait B %lld | prep %lld | mma %lld | wait A %lld\n", blockIdx.x, tile,
+               (int)diag, warp, nchunks, pc[0] / nchunks, pc[1] / nchunks, pc[2] / nchunks, pc[3] / nchunks, pc[4] / nchunks);
+#endif
 
     // ---- epilogue: register tile -> split-N workspace (row-major TM x TM) ---------------------------------------
     double* out = p.partial + ((size_t)split * p.ntiles + tile) * (TM * TM);
@@ -248,7 +277,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepParams p)
             *reinterpret_cast<double2*>(out + rr * TM + cc) = make_double2(acc[i][j][0], acc[i][j][1]);
         }
     if (diag) {
-        __syncthreads();
         red[tid] = psi1_acc;
         __syncthreads();
         if (tid < TM) {
