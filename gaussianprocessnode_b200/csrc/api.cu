@@ -124,7 +124,7 @@ void sgp_destroy(sgp_ctx* ctx) {
     if (ctx->own_data) { cudaFree(ctx->X_dev); cudaFree(ctx->y_dev); cudaFree(ctx->yv_dev); cudaFree(ctx->w_dev); }
     cudaFree(ctx->Z_dev); cudaFree(ctx->stats_dev); cudaFree(ctx->work_dev); cudaFree(ctx->zrec_dev); cudaFree(ctx->exptab_dev);
     cudaFree(ctx->dense_dev); cudaFree(ctx->info_dev); cudaFree(ctx->KuuL_dev); cudaFree(ctx->sp_X_dev); cudaFree(ctx->sp_w_dev);
-    cudaFree(ctx->sp_y_dev);
+    cudaFree(ctx->sp_y_dev); cudaFree(ctx->sweep_dbg_dev);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -297,6 +297,25 @@ int sgp_last_sweep_info(sgp_ctx* ctx, int* n_launches, int* grid, int* block, in
     if (grid) *grid = ctx->last_grid;
     if (block) *block = ctx->last_block;
     if (smem_bytes) *smem_bytes = ctx->last_smem;
+    return SGP_OK;
+}
+
+int sgp_sweep_debug_clocks(sgp_ctx* ctx, int64_t* out, int cap, int* nrec) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    constexpr int kMaxSlots = 8192;
+    if (nrec) *nrec = 0;
+    if (!ctx->sweep_dbg_dev) {
+        SGP_CUDA(ctx, cudaMalloc(&ctx->sweep_dbg_dev, (size_t)kMaxSlots * 4 * sizeof(long long)));
+        SGP_CUDA(ctx, cudaMemsetAsync(ctx->sweep_dbg_dev, 0xff, (size_t)kMaxSlots * 4 * sizeof(long long), ctx->stream));
+        return SGP_OK;
+    }
+    int n = ctx->sweep_dbg_slots < cap ? ctx->sweep_dbg_slots : cap;
+    if (n > 0 && out) {
+        SGP_CUDA(ctx, cudaMemcpyAsync(out, ctx->sweep_dbg_dev, (size_t)n * 4 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (nrec) *nrec = n;
     return SGP_OK;
 }
 

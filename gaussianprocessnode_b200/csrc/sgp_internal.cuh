@@ -62,6 +62,8 @@ struct sgp_ctx {
     // last sweep launch record
     int last_launches = 0, last_grid = 0, last_block = 0, last_smem = 0;
     float last_main_ms = 0.f;
+    long long* sweep_dbg_dev = nullptr;   // optional per-segment clocks (sgp_sweep_debug_clocks)
+    int sweep_dbg_slots = 0;
 };
 
 #define SGP_CUDA(ctx, call)                                                                          \

@@ -2,45 +2,69 @@
 //
 // Replaces the reference's per-data-point schedule -- `kernelmatrix!(Psi1_trans, kernel(theta), Xu, [x_n])` followed by
 // the rank-1 `mul!(meta.Psi2, k, k', w, 0)` and the M x M add inside `prod` (GPnode/UniSGPnode.jl:144-173, 62-73;
-// cubature variant GPnode/MultiSGPnode.jl:15-24) -- by one pass that never materialises K_uf in HBM:
+// cubature variant GPnode/MultiSGPnode.jl:15-24) -- by one pass that never materialises K_uf in HBM.
 //
-//   CTA (tile (I,J) of the lower triangle of Psi2, split s of the N range) loops over chunks of NB points:
-//     1. cp.async.bulk (TMA, 1-D) stages the raw x / y / w blocks into shared memory, 4 stages deep, mbarrier-tracked
-//     2. NB threads turn them into scaled records  x~ = s (x - c)/ell,  a = -s/2 |.|^2      (s = 2048/ln 2)
-//     3. all 256 threads generate the K_uf tile rows of blocks I and J for the chunk straight into shared memory:
-//        k = exp(a_n + b_m + x~_n . z~_m) (SE-ARD; 16 FP64 instructions per value with the table-driven exp) --
-//        diagonal tiles also fold Psi1 += k * (w y) here
-//     4. all 8 warps consume the tile with DMMA.8x8x4 (mma.sync m8n8k4 f64 -- the only FP64 MMA sm_100a has; the
-//        m16n8k* PTX shapes are split into it by ptxas) into a 64x32 register accumulator per warp.
-//   After the last chunk the 128x128 partial goes to the split-N workspace; a second kernel adds the splits in a fixed
-//   order (deterministic, no FP64 atomics), mirrors the triangle and finishes Psi1.
+// One persistent CTA per SM (256 threads = 8 warps, 2 per scheduler).  The work is the lower triangle of Psi2 cut into
+// TM x TM tiles times the N range cut into chunks of NB = 32 points; every (tile, chunk) pair has a cost weight
+// (diagonal tiles generate half the rows and skip the MMA blocks above the diagonal) and each CTA takes one contiguous,
+// equally heavy slice of the (tile, chunk) sequence -- at most a few "segments" (tile, chunk range) per CTA.
 //
-// Roofline: FP64 DMMA pipe (measured 37.0 TFLOP/s on this pool's B200; cuBLAS DGEMM 35.5).  DFMA and DMMA share that
-// pipe (tools/fp64_microbench.cu: mixed streams add up to ~35 TFLOP/s), so the generator's 16 instructions per value are
-// paid from the same budget: (TI+TJ)*16 / (TI*TJ) = 25 % on top of the MMA work for a 128x128 tile.
+// Per segment, software-pipelined over chunks (one __syncthreads per chunk):
+//     1. cp.async.bulk (TMA, 1-D, SASS UBLKCP) stages the raw x / y / w blocks, 4 stages deep, mbarrier-tracked
+//     2. raw block -> scaled records  x~ = sqrt(s) (x - c)/ell,  a = -|x~|^2/2                (s = 2048/ln 2)
+//     3. every thread owns one inducing row and generates K_uf values of chunk c+1 into the other half of a
+//        double-buffered shared-memory tile:   k = exp(a_n + b_m + x~_n . z~_m)   (16 FP64-pipe instructions per value
+//        with the table-driven exp); diagonal tiles also fold Psi1 += k (w y) here
+//     4. ... INTERLEAVED, k-step by k-step, with the DMMA.8x8x4 (mma.sync m8n8k4 f64 -- the only FP64 MMA sm_100a has)
+//        consumption of chunk c into a 64x32 register accumulator per warp.  DFMA and DMMA share one pipe
+//        (tools/fp64_microbench.cu), so the only way to keep it full is to feed it both streams at once: the DMMAs
+//        hide the dependent-issue latency of the generator chains and vice versa.
+//   After its last chunk a segment's partial tile goes to the workspace; a second kernel adds the partials of each
+//   tile in a fixed order (deterministic, no FP64 atomics), mirrors the triangle and finishes Psi1.
+//
+// Roofline: FP64 DMMA pipe (measured 37.0 TFLOP/s on this pool's B200; cuBLAS DGEMM 35.5).  The generator's 16
+// instructions per value are paid from the same budget: (TI+TJ)*16 / (TI*TJ) = 25 % on top of the MMA work for a 128x128
+// off-diagonal tile.
 #include "sgp_internal.cuh"
 #include <cmath>
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+#include <utility>
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kStages = 4;
+constexpr int kMaxThreads = 512;
+constexpr int kStages = 4;       // TMA stages of raw points
+constexpr int kRecBufs = 3;      // record buffers: written two chunks ahead, read by the generator and by the MMA (weights)
 
 struct SweepParams {
     const double* X; const double* y; const double* w;   // device, point-major, padded to a chunk multiple
     const double* zt;                                    // [Mpad][DPAD] scaled + centred inducing inputs
     const double* zb;                                    // [Mpad]       s * (ln sigma^2 - |z~|^2 / 2)
     const double* exptab;
-    double* partial;                                     // [nsplit][ntiles][TM*TM]
-    double* psi1_partial;                                // [nsplit][Mpad]
+    double* partial;                                     // [nslots][TM*TM]   slot = cta + tile
+    double* psi1_partial;                                // [nslots][TM]
+    long long* dbg;                                      // optional [nslots][4]: chunks, clocks, diag, cta
     long long N;
     long long chunks;
-    int M, D, ntiles, nsplit, nblk;
+    long long total_cost;                                // chunks * sum of tile weights
+    int M, D, ntiles, nblk, ncta;
+    int w_diag, w_off;                                   // cost weights of one chunk of a diagonal / off-diagonal tile
     double inv_ell_s[SGP_MAX_D];                         // sqrt(s) / ell_d  (both operands carry sqrt(s))
     double center[SGP_MAX_D];
-    double half_s_dummy;
 };
+
+// ---- work partition (shared by the sweep and the reduce kernels, so that both see the same segments) -------------
+__host__ __device__ inline long long cta_pos(long long total_cost, int ncta, int b) { return total_cost / ncta * b + total_cost % ncta * b / ncta; }
+// chunk range [lo, hi) that the cost interval [p0, p1) covers inside a tile whose cost prefix is `pre`
+__host__ __device__ inline void seg_range(long long p0, long long p1, long long pre, int wt, long long chunks, long long& lo, long long& hi) {
+    long long d0 = p0 - pre, d1 = p1 - pre;
+    lo = d0 <= 0 ? 0 : (d0 + wt - 1) / wt;
+    hi = d1 <= 0 ? 0 : (d1 + wt - 1) / wt;
+    if (lo > chunks) lo = chunks;
+    if (hi > chunks) hi = chunks;
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -67,12 +91,18 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// DMMA the compiler may schedule freely between the generator's instructions (no `volatile`: the accumulators carry the
+// dependences)
+__device__ __forceinline__ void dmma884_nv(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 // Shared-memory plan (doubles unless noted):
-//   Kt   [NB][LD]           generated K_uf tile, point-major; LD = 2*TM + 4 keeps DMMA fragment loads conflict-free
+//   Kt   [2][NB][LD]        generated K_uf tile, point-major, double-buffered; LD = 2*TM + 4 keeps the DMMA fragment
+//                           loads (and the generator's stores) bank-conflict-free
 //   tab  [2048]             2^(j/2048)
 //   zrec [2*TM][DPAD+1]     scaled inducing rows of blocks I and J (+ b_m)
-//   rec  [2][NB][REC]       scaled point records (double-buffered): x~[DPAD], a, w*y, w, pad
+//   rec  [3][NB][REC]       scaled point records: x~[DPAD], a, w*y, w, pad
 //   stage[kStages]: X raw [NB*D] | y [NB] | w [NB]
 //   mbarrier full[kStages]
 template <int TM, int NB, int DPAD>
@@ -82,236 +112,367 @@ struct Smem {
     static constexpr int ZR = DPAD + 1;
     static constexpr int STAGE = NB * SGP_MAX_D + 2 * NB;     // doubles per stage (X sized for the largest D)
     static constexpr size_t kt = 0;
-    static constexpr size_t tab = kt + (size_t)NB * LD;
-    static constexpr size_t zrec = tab + SGP_EXP_TAB;
-    static constexpr size_t rec = zrec + (size_t)2 * TM * ZR;
-    static constexpr size_t stage = rec + (size_t)2 * NB * REC;
+    static constexpr size_t tab = kt + (size_t)2 * NB * LD;
+    static constexpr size_t rec = tab + SGP_EXP_TAB;
+    static constexpr size_t stage = rec + (size_t)kRecBufs * NB * REC;
     static constexpr size_t bars = stage + (size_t)kStages * STAGE;
-    static constexpr size_t red = bars + kStages;             // psi1 cross-group reduction [kThreads]
-    static constexpr size_t total_doubles = red + kThreads;
+    static constexpr size_t red = bars + kStages;             // psi1 cross-group reduction [threads]
+    static constexpr size_t zrec = red + kMaxThreads;
+    static constexpr size_t total_doubles = zrec + (size_t)2 * TM * ZR;
     static constexpr size_t bytes = total_doubles * sizeof(double);
 };
 
-template <int TM, int NB, int DPAD, bool WEIGHTED>
-__global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const SweepParams p) {
+// compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{})
+template <class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) { (f(std::integral_constant<int, Is>{}), ...); }
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
+
+struct SmemPtrs {
+    double *Kt, *tab, *zrec, *rec, *stage, *red;
+    unsigned long long* full;
+};
+
+// One segment: tile (I, J), chunks [c_begin, c_begin + nchunks) of the N range.  `g` = chunks this CTA has already
+// pushed through the pipeline (selects stage / record / tile buffers and the mbarrier parity).
+template <int TM, int NB, int DPAD, int NT, bool WEIGHTED, bool DIAG>
+__device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs& sm, const int I, const int J, const long long c_begin,
+                                            const int nchunks, const unsigned g, const int slot) {
     using S = Smem<TM, NB, DPAD>;
     constexpr int LD = S::LD, REC = S::REC, ZR = S::ZR;
-    constexpr int WM = TM / 4, WN = TM / 4;          // warp tile: 4 x 4 warps over the TM x TM CTA tile
+    constexpr int kThreads = NT;
+    constexpr int WR = NT / 128;                     // warp grid: WR x 4 warps over the TM x TM CTA tile
+    constexpr int WM = TM / WR, WN = TM / 4;
     constexpr int MI = WM / 8, NJ = WN / 8;          // 8x8 DMMA blocks per warp tile
-    extern __shared__ __align__(128) double smem[];
-    double* Kt = smem + S::kt;
-    double* tab = smem + S::tab;
-    double* zrec = smem + S::zrec;
-    double* rec = smem + S::rec;                     // two record buffers: [2][NB][REC]
-    double* stage = smem + S::stage;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + S::bars);
-    double* red = smem + S::red;
+    constexpr int ROWS = DIAG ? TM : 2 * TM;         // K_uf rows this tile needs per point
+    constexpr int GROUPS = kThreads / ROWS;          // threads per row
+    constexpr int V = 4 / GROUPS;                    // values a thread generates per k-step (4 points)
+    constexpr int KS = NB / 4;
+    static_assert(GROUPS >= 1 && GROUPS <= 4 && V * GROUPS == 4, "generator mapping");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x % p.ntiles, split = blockIdx.x / p.ntiles;
-    // lower-triangular tile index -> (I, J), I >= J
-    int I = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
-    while ((I + 1) * (I + 2) / 2 <= tile) ++I;
-    while (I * (I + 1) / 2 > tile) --I;
-    const int J = tile - I * (I + 1) / 2;
-    const bool diag = (I == J);
     const int D = p.D;
-
-    const long long c_begin = p.chunks * split / p.nsplit, c_end = p.chunks * (split + 1) / p.nsplit;
-    const int nchunks = (int)(c_end - c_begin);
     const unsigned stage_bytes = (unsigned)(NB * D * 8 + NB * 8 + (WEIGHTED ? NB * 8 : 0));
-
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    for (int i = tid; i < SGP_EXP_TAB; i += kThreads) tab[i] = p.exptab[i];
-    // inducing rows: block I -> zrec rows [0,TM), block J -> rows [TM, 2TM)
-    for (int i = tid; i < 2 * TM * ZR; i += kThreads) {
-        int r = i / ZR, d = i - r * ZR;
-        int g = (r < TM ? I * TM + r : J * TM + (r - TM));
-        zrec[i] = (d < DPAD) ? p.zt[(size_t)g * DPAD + d] : p.zb[g];
-    }
-    __syncthreads();
+    long long t_start = 0;
+    if (p.dbg) t_start = clock64();
 
     auto issue = [&](int c) {   // thread 0 only: stage chunk c_begin + c
-        int s = c % kStages;
-        double* st = stage + (size_t)s * S::STAGE;
-        long long n0 = (c_begin + c) * NB;
-        mbar_expect_tx(&full[s], stage_bytes);
-        tma_load_1d(st, p.X + n0 * D, NB * D * 8, &full[s]);
-        tma_load_1d(st + NB * SGP_MAX_D, p.y + n0, NB * 8, &full[s]);
-        if (WEIGHTED) tma_load_1d(st + NB * SGP_MAX_D + NB, p.w + n0, NB * 8, &full[s]);
+        const int s = (g + c) % kStages;
+        double* st = sm.stage + (size_t)s * S::STAGE;
+        const long long n0 = (c_begin + c) * NB;
+        mbar_expect_tx(&sm.full[s], stage_bytes);
+        tma_load_1d(st, p.X + n0 * D, NB * D * 8, &sm.full[s]);
+        tma_load_1d(st + NB * SGP_MAX_D, p.y + n0, NB * 8, &sm.full[s]);
+        if (WEIGHTED) tma_load_1d(st + NB * SGP_MAX_D + NB, p.w + n0, NB * 8, &sm.full[s]);
     };
-    // raw staged block -> scaled records, spread over all threads: one (point, dimension) element each, |x~|^2 by a
-    // shuffle reduction over the DPAD lanes of a point
+    // raw staged block -> scaled records, ONE warp per chunk (the warps take turns): a lane owns a point.  The other seven
+    // warps go straight on; the late warp catches up because the scheduler's FP64 pipe, not issue, is the bottleneck.
     auto prep = [&](int c) {
-        const int s = c % kStages;
-        mbar_wait(&full[s], (unsigned)((c / kStages) & 1));
-        const double* st = stage + (size_t)s * S::STAGE;
-        double* rb = rec + (size_t)(c & 1) * NB * REC;
-        for (int e = tid; e < NB * DPAD; e += kThreads) {      // NB*DPAD is a multiple of 32: whole warps take part
-            const int pt = e / DPAD, d = e % DPAD;
-            double v = 0.0;
-            if (d < D) v = (st[pt * D + d] - p.center[d]) * p.inv_ell_s[d];
-            rb[pt * REC + d] = v;
-            double a = v * v;
+        const unsigned gc = g + c;
+        const int s = gc % kStages;
+        mbar_wait(&sm.full[s], (gc / kStages) & 1u);
+        const double* st = sm.stage + (size_t)s * S::STAGE;
+        double* r = sm.rec + (size_t)(gc % kRecBufs) * NB * REC + lane * REC;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-            for (int o = DPAD / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (d == 0) {
-                const long long n = (c_begin + c) * NB + pt;
-                const double wn = WEIGHTED ? st[NB * SGP_MAX_D + NB + pt] : 1.0;
-                rb[pt * REC + DPAD] = (n < p.N) ? -0.5 * a : -1.0e300;      // padded points generate exact zeros
-                rb[pt * REC + DPAD + 1] = wn * st[NB * SGP_MAX_D + pt];
-                rb[pt * REC + DPAD + 2] = wn;
+        for (int d = 0; d < DPAD; d += 2) {
+            double v0 = 0.0, v1 = 0.0;
+            if (d < D) v0 = (st[lane * D + d] - p.center[d]) * p.inv_ell_s[d];
+            if (d + 1 < D) v1 = (st[lane * D + d + 1] - p.center[d + 1]) * p.inv_ell_s[d + 1];
+            *reinterpret_cast<double2*>(r + d) = make_double2(v0, v1);
+            a0 = fma(v0, v0, a0);
+            a1 = fma(v1, v1, a1);
+        }
+        const long long n = (c_begin + c) * NB + lane;
+        const double wn = WEIGHTED ? st[NB * SGP_MAX_D + NB + lane] : 1.0;
+        r[DPAD] = (n < p.N) ? -0.5 * (a0 + a1) : -1.0e300;      // padded points generate exact zeros
+        r[DPAD + 1] = wn * st[NB * SGP_MAX_D + lane];
+        r[DPAD + 2] = wn;
+    };
+
+    __syncthreads();   // the previous segment is completely done with zrec / red / the tile buffers
+    // inducing rows: block I -> zrec rows [0,TM), block J -> rows [TM, 2TM)
+    for (int i = tid; i < ROWS * ZR; i += kThreads) {
+        const int r = i / ZR, d = i - r * ZR;
+        const int gm = (r < TM ? I * TM + r : J * TM + (r - TM));
+        sm.zrec[i] = (d < DPAD) ? p.zt[(size_t)gm * DPAD + d] : p.zb[gm];
+    }
+    if (tid == 0)
+        for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
+    if (warp == 0) prep(0);
+    if (warp == 1 && nchunks > 1) prep(1);
+    __syncthreads();
+
+    // generator mapping: thread -> row `grow` of [I-block | J-block], point group `ggrp`
+    const int grow = tid % ROWS;
+    const int ggrp = tid / ROWS;
+    const double* zrow = sm.zrec + grow * ZR;        // z~ row: re-read from shared memory stage by stage (registers are scarce)
+    double psi1_acc = 0.0;
+
+    // ---- staged generator ------------------------------------------------------------------------------------------
+    // A thread generates its values in groups of U = 8 independent chains advanced ONE instruction at a time (stage by
+    // stage), each stage followed by a few DMMAs: under a DMMA stream the FP64 pipe answers a dependent instruction
+    // only after ~90 cycles (everything queues behind the 16-cycle DMMAs), so a chain must never wait for itself.
+    //   stage 0: t = a_n + b_m     stages 1..DPAD: t += x~_d z~_d     then the 7 steps of exp_scaled (sgp_internal.cuh)
+    constexpr int U = (NT == 256) ? 8 : 4;
+    constexpr int KSPAN = U / V;                     // k-steps one group is spread over
+    constexpr int NST = DPAD + 8;                    // stages of one chain
+    static_assert(KS % KSPAN == 0 && KSPAN * MI * NJ >= NST, "group span");
+    struct Chains { double t[U], q[U]; int n[U]; };
+    auto pt_of = [&](int ks0, int u) { return (ks0 + u / V) * 4 + ggrp * V + (u % V); };
+    auto gen_stage = [&](auto st_tag, Chains& ch, const double* __restrict__ rn, double* __restrict__ Kn, const int ks0) {
+        constexpr int st = decltype(st_tag)::value;
+        const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+        const double C1 = 3.384507717577858e-04, C2 = 5.72744624517204e-08, C3 = 6.461528672932365e-12;
+        if constexpr (st == 0) {
+            const double zb = zrow[DPAD];
+#pragma unroll
+            for (int u = 0; u < U; ++u) ch.t[u] = rn[pt_of(ks0, u) * REC + DPAD] + zb;
+        } else if constexpr (st <= DPAD) {
+            const double z = zrow[st - 1];
+#pragma unroll
+#ifdef SGP_DBG_NOXLOAD
+            for (int u = 0; u < U; ++u) ch.t[u] = fma(z, z, ch.t[u]);      // timing experiment only
+#else
+            for (int u = 0; u < U; ++u) ch.t[u] = fma(rn[pt_of(ks0, u) * REC + st - 1], z, ch.t[u]);
+#endif
+        } else if constexpr (st == DPAD + 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) ch.q[u] = ch.t[u] + MAGIC;
+        } else if constexpr (st == DPAD + 2) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                // t < -2.0e6 (result below exp(-677): flushed to zero) <=> sign set and magnitude above: compare the high
+                // word as an unsigned integer (ALU pipe); hi word of -2.0e6 = 0xC13E8480
+                const bool tiny = (unsigned)__double2hiint(ch.t[u]) > 0xC13E8480u;
+                const int nn = __double2loint(ch.q[u]);
+                ch.n[u] = tiny ? (int)0x80000000 : nn;
+                ch.q[u] = ch.q[u] - MAGIC;
+            }
+        } else if constexpr (st == DPAD + 3) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) ch.t[u] = ch.t[u] - ch.q[u];          // r
+        } else if constexpr (st == DPAD + 4) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) ch.q[u] = fma(ch.t[u], C3, C2);
+        } else if constexpr (st == DPAD + 5) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) ch.q[u] = fma(ch.q[u], ch.t[u], C1);
+        } else if constexpr (st == DPAD + 6) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) ch.q[u] = ch.q[u] * ch.t[u];
+        } else {
+#pragma unroll
+            double T[U];
+#pragma unroll
+#ifdef SGP_DBG_NOTAB
+            for (int u = 0; u < U; ++u) T[u] = ch.t[u];                    // timing experiment only
+#else
+            for (int u = 0; u < U; ++u) T[u] = sm.tab[ch.n[u] & (SGP_EXP_TAB - 1)];
+#endif
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                double res = fma(T[u], ch.q[u], T[u]);
+                const int hi = __double2hiint(res) + ((ch.n[u] >> 11) << 20);
+                res = __hiloint2double(hi, __double2loint(res));
+                if (ch.n[u] == (int)0x80000000) res = 0.0;
+                const int pt = pt_of(ks0, u);
+                Kn[pt * LD + grow] = res;
+                if (DIAG) psi1_acc = fma(res, rn[pt * REC + DPAD + 1], psi1_acc);
             }
         }
     };
-    if (tid == 0)
-        for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
-
-    // generator mapping: rows_needed rows (TM on the diagonal, 2*TM otherwise), tpr threads per row
-    const int rows_needed = diag ? TM : 2 * TM;
-    const int tpr = kThreads / rows_needed;
-    const int grow = tid % rows_needed;                // row inside [I-block | J-block]
-    const int ggrp = tid / rows_needed;
-    const int npts = NB / tpr;                         // points per thread per chunk (multiple of 4)
-    const int pt0 = ggrp * npts;
-    double psi1_acc = 0.0;
 
     // MMA mapping
     const int wr = warp >> 2, wc = warp & 3;
     const int a_off = wr * WM + (lane >> 2);                        // + 8*i
-    const int b_off = (diag ? 0 : TM) + wc * WN + (lane >> 2);      // + 8*j
+    const int b_off = (DIAG ? 0 : TM) + wc * WN + (lane >> 2);      // + 8*j
     const int kq = lane & 3;
+    // diagonal tiles: 8x8 blocks strictly above the diagonal are never needed (the reduce kernel mirrors the lower
+    // triangle); bit (i*NJ + j) of the mask = block (i, j) of this warp's tile is computed
+    unsigned long long mask = ~0ull;
+    if (DIAG) {
+        mask = 0ull;
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+                if (wc * WN + 8 * j <= wr * WM + 8 * i + 7) mask |= 1ull << (i * NJ + j);
+    }
     double acc[MI][NJ][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    if (nchunks > 0) prep(0);
+    // prologue: tile of chunk 0 (nothing to overlap with)
+    {
+        double* K0 = sm.Kt + (size_t)(g & 1u) * NB * LD;
+        const double* r0 = sm.rec + (size_t)(g % kRecBufs) * NB * REC;
+#pragma unroll 1
+        for (int gi = 0; gi < KS / KSPAN; ++gi) {
+            Chains ch;
+            static_for<NST>([&](auto st) { gen_stage(st, ch, r0, K0, gi * KSPAN); });
+        }
+    }
     __syncthreads();
 
-#ifdef SGP_PHASE_CLOCKS
-    long long pc[6] = {0, 0, 0, 0, 0, 0}; long long t0c = clock64(), t1c;
-#define PCLK(i) do { t1c = clock64(); pc[i] += t1c - t0c; t0c = t1c; } while (0)
-#else
-#define PCLK(i) do { } while (0)
-#endif
-    for (int c = 0; c < nchunks; ++c) {
-        const double* rb = rec + (size_t)(c & 1) * NB * REC;
-        // ---- generate: K_uf tile rows for blocks I and J ------------------------------------------------------
-        {
-            double zr[DPAD];
-#pragma unroll
-            for (int d = 0; d < DPAD; ++d) zr[d] = zrec[grow * ZR + d];
-            const double zb = zrec[grow * ZR + DPAD];
-            // U independent dependency chains per thread: the FP64 pipe has ~30 cycles of dependent-issue latency, so
-            // the 16-instruction chain of one value is interleaved with others by hand (4 per thread x 4 warps per
-            // scheduler = 16 chains in flight)
-            constexpr int U = 4;
-#pragma unroll 1
-            for (int q = 0; q < npts; q += U) {
-                const double* r = rb + (pt0 + q) * REC;
-                double t[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) t[u] = r[u * REC + DPAD] + zb;
-#pragma unroll
-                for (int d = 0; d < DPAD; ++d)
-#pragma unroll
-                    for (int u = 0; u < U; ++u) t[u] = fma(r[u * REC + d], zr[d], t[u]);
-                double k[U];
-                exp_scaled_v<U>(t, k, tab);
-#pragma unroll
-                for (int u = 0; u < U; ++u) Kt[(pt0 + q + u) * LD + grow] = k[u];
-                if (diag) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) psi1_acc = fma(k[u], r[u * REC + DPAD + 1], psi1_acc);
-                }
-            }
-        }
-        PCLK(0);
-        __syncthreads();   // tile complete
-        PCLK(1);
-        // ---- stage + prepare the next chunk's records while the tile is consumed -------------------------------
+    // one pipeline step: consume chunk c (DMMA.8x8x4) while generating chunk c+1 (GEN)
+    auto body = [&](auto gen_tag, const int c) {
+        constexpr bool GEN = decltype(gen_tag)::value;
+        constexpr int DPK = MI * NJ;                  // DMMAs per k-step
+        constexpr int TOTAL = KSPAN * DPK;            // DMMAs one generator group is interleaved with
+        const unsigned gc = g + c;
+        const double* Kc = sm.Kt + (size_t)(gc & 1u) * NB * LD;
+        double* Kn = sm.Kt + (size_t)((gc + 1) & 1u) * NB * LD;
+        const double* rc = sm.rec + (size_t)(gc % kRecBufs) * NB * REC;
+        const double* rn = sm.rec + (size_t)((gc + 1) % kRecBufs) * NB * REC;
         if (tid == 0 && c + kStages - 1 < nchunks) issue(c + kStages - 1);
-        if (c + 1 < nchunks) prep(c + 1);
-        PCLK(2);
-        // ---- consume: Psi2 tile += K_I diag(w) K_J'  (DMMA.8x8x4) ----------------------------------------------
-#pragma unroll 2
-        for (int ks = 0; ks < NB / 4; ++ks) {
-            const double* row = Kt + (ks * 4 + kq) * LD;
-            double a[MI], b[NJ];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) a[i] = row[a_off + 8 * i];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) b[j] = row[b_off + 8 * j];
-            if (WEIGHTED) {
-                const double wn = rb[(ks * 4 + kq) * REC + DPAD + 2];
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) b[j] *= wn;
-            }
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-        PCLK(3);
-        __syncthreads();   // every warp is done with the tile and the next records are complete
-        PCLK(4);
-    }
-#ifdef SGP_PHASE_CLOCKS
-    if (lane == 0 && (warp == 0 || warp == 15) && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == 8))
-        printf("cta %d (tile %d diag %d) warp %d chunks %d: per-chunk clk gen %lld | wait B %lld | prep %lld | mma %lld | wait A %lld\n", blockIdx.x, tile,
-               (int)diag, warp, nchunks, pc[0] / nchunks, pc[1] / nchunks, pc[2] / nchunks, pc[3] / nchunks, pc[4] / nchunks);
-#endif
+        if (c + 2 < nchunks && warp == (int)(gc % (NT / 32))) prep(c + 2);
 
-    // ---- epilogue: register tile -> split-N workspace (row-major TM x TM) ---------------------------------------
-    double* out = p.partial + ((size_t)split * p.ntiles + tile) * (TM * TM);
+#pragma unroll 1
+        for (int gi = 0; gi < KS / KSPAN; ++gi) {
+            const int ks0 = gi * KSPAN;
+            Chains ch;
+            double a[MI], b[NJ];
+            static_for<TOTAL>([&](auto d_tag) {
+                constexpr int d = decltype(d_tag)::value;
+                constexpr int kk = d / DPK, dd = d % DPK, i = dd / NJ, j = dd % NJ;
+                if constexpr (dd == 0) {
+                    const double* row = Kc + ((ks0 + kk) * 4 + kq) * LD;
+#pragma unroll
+                    for (int ii = 0; ii < MI; ++ii) a[ii] = row[a_off + 8 * ii];
+#pragma unroll
+                    for (int jj = 0; jj < NJ; ++jj) b[jj] = row[b_off + 8 * jj];
+                    if (WEIGHTED) {
+                        const double wn = rc[((ks0 + kk) * 4 + kq) * REC + DPAD + 2];
+#pragma unroll
+                        for (int jj = 0; jj < NJ; ++jj) b[jj] *= wn;
+                    }
+                }
+                // the stage (at most one: TOTAL >= NST) whose slot floor(st * TOTAL / NST) is this DMMA
+                constexpr int st = (d * NST + TOTAL - 1) / TOTAL;
+#ifndef SGP_DBG_NOGEN
+                if constexpr (GEN && st < NST && (st * TOTAL) / NST == d) gen_stage(std::integral_constant<int, st>{}, ch, rn, Kn, ks0);
+#endif
+#ifndef SGP_DBG_NOMMA
+                if (!DIAG || ((mask >> dd) & 1ull)) dmma884_nv(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+#else
+                acc[i][j][0] += a[i]; acc[i][j][1] += b[j];      // timing experiment only: keeps the fragment loads alive
+#endif
+            });
+        }
+        __syncthreads();   // chunk c consumed by every warp, chunk c+1 generated, records of chunk c+2 complete
+    };
+    for (int c = 0; c + 1 < nchunks; ++c) body(std::true_type{}, c);
+    body(std::false_type{}, nchunks - 1);
+
+    // ---- epilogue: register tile -> workspace slot (row-major TM x TM) ------------------------------------------
+    double* out = p.partial + (size_t)slot * (TM * TM);
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            int rr = wr * WM + 8 * i + (lane >> 2), cc = wc * WN + 8 * j + 2 * (lane & 3);
+            const int rr = wr * WM + 8 * i + (lane >> 2), cc = wc * WN + 8 * j + 2 * (lane & 3);
             *reinterpret_cast<double2*>(out + rr * TM + cc) = make_double2(acc[i][j][0], acc[i][j][1]);
         }
-    if (diag) {
-        red[tid] = psi1_acc;
+    if (DIAG) {
+        sm.red[tid] = psi1_acc;
         __syncthreads();
         if (tid < TM) {
             double v = 0.0;
-            for (int g = 0; g < tpr; ++g) v += red[g * rows_needed + tid];
-            p.psi1_partial[(size_t)split * (p.nblk * TM) + I * TM + tid] = v;
+#pragma unroll
+            for (int gq = 0; gq < GROUPS; ++gq) v += sm.red[gq * ROWS + tid];
+            p.psi1_partial[(size_t)slot * TM + tid] = v;
         }
+    }
+    if (p.dbg && tid == 0) {
+        p.dbg[4 * slot + 0] = nchunks;
+        p.dbg[4 * slot + 1] = clock64() - t_start;
+        p.dbg[4 * slot + 2] = DIAG ? 1 : 0;
+        p.dbg[4 * slot + 3] = blockIdx.x;
     }
 }
 
-// Fixed-order sum over the N splits, mirror to the full symmetric matrix, finish Psi1.
+template <int TM, int NB, int DPAD, int NT, bool WEIGHTED>
+__global__ void __launch_bounds__(NT, 1) sweep_kernel(const __grid_constant__ SweepParams p) {
+    using S = Smem<TM, NB, DPAD>;
+    extern __shared__ __align__(128) double smem[];
+    SmemPtrs sm;
+    sm.Kt = smem + S::kt; sm.tab = smem + S::tab; sm.zrec = smem + S::zrec; sm.rec = smem + S::rec; sm.stage = smem + S::stage;
+    sm.red = smem + S::red;
+    sm.full = reinterpret_cast<unsigned long long*>(smem + S::bars);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < SGP_EXP_TAB; i += NT) sm.tab[i] = p.exptab[i];
+    // (run_segment starts with a __syncthreads)
+
+    const int bcta = blockIdx.x;
+    const long long p0 = cta_pos(p.total_cost, p.ncta, bcta), p1 = cta_pos(p.total_cost, p.ncta, bcta + 1);
+    unsigned g = 0;
+    long long pre = 0;
+    int I = 0, J = 0;
+    for (int t = 0; t < p.ntiles && pre < p1; ++t) {
+        const bool diag = (I == J);
+        const int wt = diag ? p.w_diag : p.w_off;
+        long long lo, hi;
+        seg_range(p0, p1, pre, wt, p.chunks, lo, hi);
+        if (lo < hi) {
+            const int n = (int)(hi - lo);
+            if (diag) run_segment<TM, NB, DPAD, NT, WEIGHTED, true>(p, sm, I, J, lo, n, g, bcta + t);
+            else run_segment<TM, NB, DPAD, NT, WEIGHTED, false>(p, sm, I, J, lo, n, g, bcta + t);
+            g += (unsigned)n;
+        }
+        pre += (long long)wt * p.chunks;
+        if (++J > I) { ++I; J = 0; }
+    }
+}
+
+// Fixed-order sum over the segments of a tile, mirror to the full symmetric matrix, finish Psi1.
 template <int TM>
 __global__ void reduce_kernel(const double* __restrict__ partial, const double* __restrict__ psi1_partial, double* __restrict__ psi2,
-                              double* __restrict__ psi1, int M, int ntiles, int nsplit, int nblk) {
+                              double* __restrict__ psi1, int M, long long chunks, long long total_cost, int ncta, int w_diag, int w_off) {
+    __shared__ int slots[1024];
+    __shared__ int nslots;
     const int tile = blockIdx.x;
-    int I = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
-    while ((I + 1) * (I + 2) / 2 <= tile) ++I;
-    while (I * (I + 1) / 2 > tile) --I;
-    const int J = tile - I * (I + 1) / 2;
+    int I = 0, J = 0;
+    long long pre = 0;
+    for (int t = 0; t < tile; ++t) {
+        pre += (long long)(I == J ? w_diag : w_off) * chunks;
+        if (++J > I) { ++I; J = 0; }
+    }
+    if (threadIdx.x == 0) {
+        const int wt = (I == J) ? w_diag : w_off;
+        int n = 0;
+        for (int b = 0; b < ncta; ++b) {
+            long long lo, hi;
+            seg_range(cta_pos(total_cost, ncta, b), cta_pos(total_cost, ncta, b + 1), pre, wt, chunks, lo, hi);
+            if (lo < hi) slots[n++] = b + tile;
+        }
+        nslots = n;
+    }
+    __syncthreads();
+    const int ns = nslots;
     for (int e = threadIdx.x; e < TM * TM; e += blockDim.x) {
-        int r = e / TM, c = e - r * TM;
-        int gi = I * TM + r, gj = J * TM + c;
+        const int r = e / TM, c = e - r * TM;
+        const int gi = I * TM + r, gj = J * TM + c;
         if (gi >= M || gj >= M) continue;
         if (I == J && c > r) continue;
         double v = 0.0;
-        for (int s = 0; s < nsplit; ++s) v += partial[((size_t)s * ntiles + tile) * (TM * TM) + e];
+        for (int s = 0; s < ns; ++s) v += partial[(size_t)slots[s] * (TM * TM) + e];
         psi2[(size_t)gi + (size_t)gj * M] = v;
         psi2[(size_t)gj + (size_t)gi * M] = v;
     }
     if (I == J) {
         for (int r = threadIdx.x; r < TM; r += blockDim.x) {
-            int gi = I * TM + r;
+            const int gi = I * TM + r;
             if (gi >= M) continue;
             double v = 0.0;
-            for (int s = 0; s < nsplit; ++s) v += psi1_partial[(size_t)s * (nblk * TM) + gi];
+            for (int s = 0; s < ns; ++s) v += psi1_partial[(size_t)slots[s] * TM + r];
             psi1[gi] = v;
         }
     }
@@ -371,24 +532,24 @@ __global__ void scalar_finish_kernel(const double* __restrict__ partial, int nbl
     }
 }
 
-template <int TM, int NB, int DPAD>
+template <int TM, int NB, int DPAD, int NT>
 int launch_t(sgp_ctx* ctx, const SweepParams& p, bool weighted, int grid) {
     using S = Smem<TM, NB, DPAD>;
-    auto kern = weighted ? sweep_kernel<TM, NB, DPAD, true> : sweep_kernel<TM, NB, DPAD, false>;
+    auto kern = weighted ? sweep_kernel<TM, NB, DPAD, NT, true> : sweep_kernel<TM, NB, DPAD, NT, false>;
     SGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
-    kern<<<grid, kThreads, S::bytes, ctx->stream>>>(p);
-    ctx->last_grid = grid; ctx->last_block = kThreads; ctx->last_smem = (int)S::bytes;
+    kern<<<grid, NT, S::bytes, ctx->stream>>>(p);
+    ctx->last_grid = grid; ctx->last_block = NT; ctx->last_smem = (int)S::bytes;
     SGP_CUDA(ctx, cudaGetLastError());
     return SGP_OK;
 }
 
-template <int TM, int NB>
+template <int TM, int NB, int NT>
 int launch_d(sgp_ctx* ctx, const SweepParams& p, bool weighted, int grid, int dpad) {
     switch (dpad) {
-        case 2: return launch_t<TM, NB, 2>(ctx, p, weighted, grid);
-        case 4: return launch_t<TM, NB, 4>(ctx, p, weighted, grid);
-        case 8: return launch_t<TM, NB, 8>(ctx, p, weighted, grid);
-        default: return launch_t<TM, NB, 16>(ctx, p, weighted, grid);
+        case 2: return launch_t<TM, NB, 2, NT>(ctx, p, weighted, grid);
+        case 4: return launch_t<TM, NB, 4, NT>(ctx, p, weighted, grid);
+        case 8: return launch_t<TM, NB, 8, NT>(ctx, p, weighted, grid);
+        default: return launch_t<TM, NB, 16, NT>(ctx, p, weighted, grid);
     }
 }
 
@@ -409,21 +570,17 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     const int ntiles = nblk * (nblk + 1) / 2;
     const long long chunks = (N + NB - 1) / NB;
     if (chunks * NB > Ncap) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: data buffers must be padded to a multiple of 32 points");
-    // split N so that tiles * splits fills the SMs: one wave of CTAs unless a CTA would still get >= 256 chunks in a
-    // multi-wave launch (every CTA pays a fixed set-up -- exp table, inducing rows -- and a 128 KB partial tile)
-    int best = 1; double best_eff = 0.0;
-    for (int s = 1; s <= 64 && s <= chunks; ++s) {
-        long long ctas = (long long)ntiles * s;
-        long long waves = (ctas + ctx->num_sms - 1) / ctx->num_sms;
-        if (waves > 1 && (s > 1 && chunks / s < 256)) break;
-        if (waves > 4) break;
-        double eff = (double)ctas / ((double)ctx->num_sms * (double)waves);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
-    }
-    const int nsplit = best;
-    const int grid = ntiles * nsplit;
+    // one persistent CTA per SM; the (tile, chunk) sequence is cut into equally heavy contiguous slices.  Cost weights
+    // of one chunk (measured per-chunk clocks, see profiles/): off-diagonal 2*TM generated rows + TM^2 MMA, diagonal TM
+    // rows + the MMA blocks on or below the diagonal
+    int w_diag = 11, w_off = 16;
+    if (const char* e = std::getenv("SGP_SWEEP_WEIGHTS")) { int a_ = 0, b_ = 0; if (std::sscanf(e, "%d,%d", &a_, &b_) == 2 && a_ > 0 && b_ > 0) { w_diag = a_; w_off = b_; } }
+    const long long total_cost = chunks * ((long long)nblk * w_diag + (long long)(ntiles - nblk) * w_off);
+    const int ncta = (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, chunks * ntiles));
+    const int grid = ncta;
+    const int nslots = ncta + ntiles;
 
-    size_t need_work = (size_t)nsplit * ntiles * TM * TM + (size_t)nsplit * Mpad + 2 * 1024;
+    size_t need_work = (size_t)nslots * TM * TM + (size_t)nslots * TM + 2 * 1024;
     int rc = sgp_ensure(ctx, &ctx->work_dev, &ctx->work_cap, need_work); if (rc) return rc;
     rc = sgp_ensure(ctx, &ctx->zrec_dev, &ctx->zrec_cap, (size_t)Mpad * (16 + 1)); if (rc) return rc;
     size_t need_stats = (size_t)M * M + (size_t)M + 8;
@@ -431,25 +588,30 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     ctx->Dout = 1;
 
     SweepParams p{};
-    p.X = X; p.y = y; p.w = w; p.N = N; p.chunks = chunks; p.M = M; p.D = D; p.ntiles = ntiles; p.nsplit = nsplit; p.nblk = nblk;
+    p.X = X; p.y = y; p.w = w; p.N = N; p.chunks = chunks; p.M = M; p.D = D; p.ntiles = ntiles; p.nblk = nblk; p.ncta = ncta;
+    p.total_cost = total_cost; p.w_diag = w_diag; p.w_off = w_off; p.dbg = (nslots <= 8192) ? ctx->sweep_dbg_dev : nullptr;
+    if (p.dbg) { SGP_CUDA(ctx, cudaMemsetAsync(p.dbg, 0xff, (size_t)nslots * 4 * sizeof(long long), ctx->stream)); ctx->sweep_dbg_slots = nslots; }
     const double sq = std::sqrt(SGP_EXP_SCALE);
     for (int d = 0; d < SGP_MAX_D; ++d) { p.inv_ell_s[d] = d < D ? sq / ctx->ell[d] : 0.0; p.center[d] = d < D ? ctx->center[d] : 0.0; }
     double* zt = ctx->zrec_dev; double* zb = ctx->zrec_dev + (size_t)Mpad * 16;
     p.zt = zt; p.zb = zb; p.exptab = ctx->exptab_dev;
-    p.partial = ctx->work_dev; p.psi1_partial = ctx->work_dev + (size_t)nsplit * ntiles * TM * TM;
-    double* scal_partial = p.psi1_partial + (size_t)nsplit * Mpad;
+    p.partial = ctx->work_dev; p.psi1_partial = ctx->work_dev + (size_t)nslots * TM * TM;
+    double* scal_partial = p.psi1_partial + (size_t)nslots * TM;
     double* psi2 = ctx->stats_dev; double* psi1 = psi2 + (size_t)M * M; double* scal = psi1 + M;
 
     int launches = 0;
     zprep_kernel<<<(Mpad + 127) / 128, 128, 0, ctx->stream>>>(ctx->Z_dev, zt, zb, M, Mpad, D, dpad, p, std::log(ctx->variance)); ++launches;
     if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (TM == 128) rc = launch_d<128, NB>(ctx, p, w != nullptr, grid, dpad);
-    else rc = launch_d<64, NB>(ctx, p, w != nullptr, grid, dpad);
+    int nthreads = 256;
+    if (const char* e = std::getenv("SGP_SWEEP_THREADS")) nthreads = std::atoi(e);
+    if (TM == 128 && nthreads == 512) rc = launch_d<128, NB, 512>(ctx, p, w != nullptr, grid, dpad);
+    else if (TM == 128) rc = launch_d<128, NB, 256>(ctx, p, w != nullptr, grid, dpad);
+    else rc = launch_d<64, NB, 256>(ctx, p, w != nullptr, grid, dpad);
     if (rc) return rc;
     ++launches;
     if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (TM == 128) reduce_kernel<128><<<ntiles, 256, 0, ctx->stream>>>(p.partial, p.psi1_partial, psi2, psi1, M, ntiles, nsplit, nblk);
-    else reduce_kernel<64><<<ntiles, 256, 0, ctx->stream>>>(p.partial, p.psi1_partial, psi2, psi1, M, ntiles, nsplit, nblk);
+    if (TM == 128) reduce_kernel<128><<<ntiles, 256, 0, ctx->stream>>>(p.partial, p.psi1_partial, psi2, psi1, M, chunks, total_cost, ncta, w_diag, w_off);
+    else reduce_kernel<64><<<ntiles, 256, 0, ctx->stream>>>(p.partial, p.psi1_partial, psi2, psi1, M, chunks, total_cost, ncta, w_diag, w_off);
     ++launches;
     int sb = (int)std::min<long long>(1024, (N + 255) / 256); if (sb < 1) sb = 1;
     scalar_sums_kernel<<<sb, 256, 0, ctx->stream>>>(y, yv, w, N, scal_partial); ++launches;

@@ -120,6 +120,15 @@ class SGPContext:
         self._ck(self.lib.sgp_sweep_timed(self.h, int(reps), ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def sweep_debug_clocks(self, cap=8192):
+        """First call switches per-segment clock recording on; later calls return an (n, 4) int64 array
+        {chunks, SM clocks, is_diagonal_tile, cta} of the last sweep (rows of -1 = unused slots)."""
+        import numpy as np
+        out = np.full((cap, 4), -1, dtype=np.int64)
+        n = ctypes.c_int(0)
+        self._ck(self.lib.sgp_sweep_debug_clocks(self.h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), cap, ctypes.byref(n)))
+        return out[:n.value]
+
     def last_sweep_info(self):
         v = [ctypes.c_int() for _ in range(4)]
         self._ck(self.lib.sgp_last_sweep_info(self.h, *[ctypes.byref(x) for x in v]))

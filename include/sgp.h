@@ -115,6 +115,10 @@ int sgp_comm_init(sgp_ctx* ctx, int nranks, int rank, const char id[128]);
 int sgp_sweep_timed(sgp_ctx* ctx, int reps, float* ms_per_sweep, float* ms_main_kernel);
 /* number of kernels the last sweep launched, and the main kernel's launch geometry */
 int sgp_last_sweep_info(sgp_ctx* ctx, int* n_launches, int* grid, int* block, int* smem_bytes);
+/* per-segment clock counters of the fused sweep kernel (load-balance tuning).  The first call switches the
+ * recording on; later calls copy out up to `cap` records {chunks, SM clocks, is_diagonal_tile, cta} (-1 = unused slot)
+ * of the last sweep and return their number in *nrec. */
+int sgp_sweep_debug_clocks(sgp_ctx* ctx, int64_t* out, int cap, int* nrec);
 /* device pointers of the resident statistics of the last sweep: [psi2 (M*M) | psi1 (M*D_out) | psi0 | sum_y2] */
 int sgp_stats_dev(sgp_ctx* ctx, double** psi2_dev, double** psi1_dev, double** scal_dev);
 
