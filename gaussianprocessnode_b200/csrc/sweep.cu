@@ -98,17 +98,17 @@ __device__ __forceinline__ void dmma884_nv(double& c0, double& c1, double a, dou
 }
 
 // Shared-memory plan (doubles unless noted):
-//   Kt   [2][NB][LD]        generated K_uf tile, point-major, double-buffered; LD = 2*TM + 4 keeps the DMMA fragment
-//                           loads (and the generator's stores) bank-conflict-free
-//   tab  [2048]             2^(j/2048)
-//   zrec [2*TM][DPAD+1]     scaled inducing rows of blocks I and J (+ b_m)
-//   rec  [3][NB][REC]       scaled point records: x~[DPAD], a, w*y, w, pad
-//   stage[kStages]: X raw [NB*D] | y [NB] | w [NB]
+//   Kt    [2][NB][LD]       generated K_uf tile, point-major, double-buffered; LD = 2*TM + 4 keeps the DMMA fragment
+//                           loads (and the generator's 16-byte stores) bank-conflict-free
+//   tab   [2048]            2^(j/2048)
+//   zrec  [2*TM][DPAD+1]    scaled inducing rows of blocks I and J;  zbias [2*TM] their b_m
+//   rec   [3][NB][REC]      scaled point records: x~[DPAD], a, w*y, w, pad (REC = 12 or 20: conflict-free A fragments)
+//   stage [kStages]: X raw [NB*D] | y [NB] | w [NB]
 //   mbarrier full[kStages]
 template <int TM, int NB, int DPAD>
 struct Smem {
     static constexpr int LD = 2 * TM + 4;
-    static constexpr int REC = DPAD + 4;
+    static constexpr int REC = DPAD <= 8 ? 12 : 20;
     static constexpr int ZR = DPAD + 1;
     static constexpr int STAGE = NB * SGP_MAX_D + 2 * NB;     // doubles per stage (X sized for the largest D)
     static constexpr size_t kt = 0;
@@ -116,8 +116,8 @@ struct Smem {
     static constexpr size_t rec = tab + SGP_EXP_TAB;
     static constexpr size_t stage = rec + (size_t)kRecBufs * NB * REC;
     static constexpr size_t bars = stage + (size_t)kStages * STAGE;
-    static constexpr size_t red = bars + kStages;             // psi1 cross-group reduction [threads]
-    static constexpr size_t zrec = red + kMaxThreads;
+    static constexpr size_t zbias = bars + kStages;
+    static constexpr size_t zrec = zbias + (size_t)2 * TM;
     static constexpr size_t total_doubles = zrec + (size_t)2 * TM * ZR;
     static constexpr size_t bytes = total_doubles * sizeof(double);
 };
@@ -129,7 +129,7 @@ template <int N, class F>
 __device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
 
 struct SmemPtrs {
-    double *Kt, *tab, *zrec, *rec, *stage, *red;
+    double *Kt, *tab, *zrec, *zbias, *rec, *stage;
     unsigned long long* full;
 };
 
@@ -140,15 +140,19 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
                                             const int nchunks, const unsigned g, const int slot) {
     using S = Smem<TM, NB, DPAD>;
     constexpr int LD = S::LD, REC = S::REC, ZR = S::ZR;
-    constexpr int kThreads = NT;
+    constexpr int NWARPS = NT / 32;
     constexpr int WR = NT / 128;                     // warp grid: WR x 4 warps over the TM x TM CTA tile
     constexpr int WM = TM / WR, WN = TM / 4;
     constexpr int MI = WM / 8, NJ = WN / 8;          // 8x8 DMMA blocks per warp tile
-    constexpr int ROWS = DIAG ? TM : 2 * TM;         // K_uf rows this tile needs per point
-    constexpr int GROUPS = kThreads / ROWS;          // threads per row
-    constexpr int V = 4 / GROUPS;                    // values a thread generates per k-step (4 points)
-    constexpr int KS = NB / 4;
-    static_assert(GROUPS >= 1 && GROUPS <= 4 && V * GROUPS == 4, "generator mapping");
+    constexpr int ROWS = DIAG ? TM : 2 * TM;         // K_uf rows this tile needs per point: the "panel" [I-block | J-block]
+    constexpr int RB = ROWS / (8 * NWARPS);          // 8-row blocks of the panel one warp generates
+    constexpr int KS = NB / 4;                       // k-steps (4 points) per chunk
+    constexpr int KQ = (DPAD + 3) / 4;               // DMMA k-quarters of the dot product x~ . z~
+    constexpr int NPB = 4 / RB;                      // 8-point blocks per generator unit
+    constexpr int KSPAN = KS / RB;                   // k-steps one generator unit is spread over
+    constexpr int NST = KQ + 8;                      // stages of a generator unit
+    static_assert(RB == 1 || RB == 2 || RB == 4, "generator mapping");
+    static_assert(NB == 32 && KSPAN * MI * NJ >= NST, "generator schedule");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D;
@@ -165,7 +169,7 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
         tma_load_1d(st + NB * SGP_MAX_D, p.y + n0, NB * 8, &sm.full[s]);
         if (WEIGHTED) tma_load_1d(st + NB * SGP_MAX_D + NB, p.w + n0, NB * 8, &sm.full[s]);
     };
-    // raw staged block -> scaled records, ONE warp per chunk (the warps take turns): a lane owns a point.  The other seven
+    // raw staged block -> scaled records, ONE warp per chunk (the warps take turns): a lane owns a point.  The other
     // warps go straight on; the late warp catches up because the scheduler's FP64 pipe, not issue, is the bottleneck.
     auto prep = [&](int c) {
         const unsigned gc = g + c;
@@ -188,14 +192,16 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
         r[DPAD] = (n < p.N) ? -0.5 * (a0 + a1) : -1.0e300;      // padded points generate exact zeros
         r[DPAD + 1] = wn * st[NB * SGP_MAX_D + lane];
         r[DPAD + 2] = wn;
+        r[DPAD + 3] = 0.0;
     };
 
-    __syncthreads();   // the previous segment is completely done with zrec / red / the tile buffers
-    // inducing rows: block I -> zrec rows [0,TM), block J -> rows [TM, 2TM)
-    for (int i = tid; i < ROWS * ZR; i += kThreads) {
+    __syncthreads();   // the previous segment is completely done with zrec / zbias / the tile buffers
+    // inducing rows: block I -> panel rows [0,TM), block J -> rows [TM, 2TM)
+    for (int i = tid; i < ROWS * ZR; i += NT) {
         const int r = i / ZR, d = i - r * ZR;
         const int gm = (r < TM ? I * TM + r : J * TM + (r - TM));
-        sm.zrec[i] = (d < DPAD) ? p.zt[(size_t)gm * DPAD + d] : p.zb[gm];
+        if (d < DPAD) sm.zrec[i] = p.zt[(size_t)gm * DPAD + d];
+        else sm.zbias[r] = p.zb[gm];
     }
     if (tid == 0)
         for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
@@ -203,82 +209,97 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     if (warp == 1 && nchunks > 1) prep(1);
     __syncthreads();
 
-    // generator mapping: thread -> row `grow` of [I-block | J-block], point group `ggrp`
-    const int grow = tid % ROWS;
-    const int ggrp = tid / ROWS;
-    const double* zrow = sm.zrec + grow * ZR;        // z~ row: re-read from shared memory stage by stage (registers are scarce)
-    double psi1_acc = 0.0;
+    // ---- generator: the dot products x~ . z~ are themselves DMMAs ----------------------------------------------------
+    // A warp owns RB 8-row blocks of the panel.  One 8-point x 8-row tile of exponents is   C = a_n + b_m  (DADD),
+    // C += X~ Z~'  (KQ DMMA.8x8x4: A = 8 points x 4 dims from the records, B = 4 dims x 8 rows held in registers for the
+    // whole segment), then the 7 steps of exp_scaled (sgp_internal.cuh) on the two values a thread holds, which are two
+    // adjacent rows of one point = one 16-byte store into the point-major tile.  Four tiles (8 independent chains) form a
+    // unit that is advanced one stage at a time between the DMMAs of the SYRK.  Compared with one DFMA chain per value
+    // this needs no broadcast loads of x~ (12 instead of ~300 shared-memory loads per warp and chunk) at the same FP64
+    // pipe cost.   Row i of A / C is point  8*pb + perm(i),  perm = 0,2,1,3,4,6,5,7:  the eight lanes of a quarter-warp
+    // then store to points two apart, which LD = 4 (mod 16) maps to disjoint banks.
+    const int grow0 = warp * (8 * RB);
+    const int prow = ((lane >> 2) & 4) | ((lane >> 3) & 1) | ((lane >> 1) & 2);     // perm(lane / 4)
+    double zf[RB][KQ];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+        for (int kk = 0; kk < KQ; ++kk) {
+            const int d = kk * 4 + (lane & 3);
+            zf[rb][kk] = (d < DPAD) ? sm.zrec[(grow0 + rb * 8 + (lane >> 2)) * ZR + d] : 0.0;
+        }
+    double psi1_acc[RB][2];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) psi1_acc[rb][0] = psi1_acc[rb][1] = 0.0;
 
-    // ---- staged generator ------------------------------------------------------------------------------------------
-    // A thread generates its values in groups of U = 8 independent chains advanced ONE instruction at a time (stage by
-    // stage), each stage followed by a few DMMAs: under a DMMA stream the FP64 pipe answers a dependent instruction
-    // only after ~90 cycles (everything queues behind the 16-cycle DMMAs), so a chain must never wait for itself.
-    //   stage 0: t = a_n + b_m     stages 1..DPAD: t += x~_d z~_d     then the 7 steps of exp_scaled (sgp_internal.cuh)
-    constexpr int U = (NT == 256) ? 8 : 4;
-    constexpr int KSPAN = U / V;                     // k-steps one group is spread over
-    constexpr int NST = DPAD + 8;                    // stages of one chain
-    static_assert(KS % KSPAN == 0 && KSPAN * MI * NJ >= NST, "group span");
-    struct Chains { double t[U], q[U]; int n[U]; };
-    auto pt_of = [&](int ks0, int u) { return (ks0 + u / V) * 4 + ggrp * V + (u % V); };
-    auto gen_stage = [&](auto st_tag, Chains& ch, const double* __restrict__ rn, double* __restrict__ Kn, const int ks0) {
+    struct Unit { double t[8], q[8], xa[NPB][KQ]; int n[8]; };
+    auto gen_stage = [&](auto st_tag, Unit& u, const double* __restrict__ rn, double* __restrict__ Kn, const int ui) {
         constexpr int st = decltype(st_tag)::value;
         const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
         const double C1 = 3.384507717577858e-04, C2 = 5.72744624517204e-08, C3 = 6.461528672932365e-12;
+        // tile q of the unit: point block ui*NPB + q/RB, row block q%RB; this thread's point in a point block: prow
         if constexpr (st == 0) {
-            const double zb = zrow[DPAD];
 #pragma unroll
-            for (int u = 0; u < U; ++u) ch.t[u] = rn[pt_of(ks0, u) * REC + DPAD] + zb;
-        } else if constexpr (st <= DPAD) {
-            const double z = zrow[st - 1];
+            for (int pb = 0; pb < NPB; ++pb) {
+                const double* r = rn + ((ui * NPB + pb) * 8 + prow) * REC;
 #pragma unroll
-#ifdef SGP_DBG_NOXLOAD
-            for (int u = 0; u < U; ++u) ch.t[u] = fma(z, z, ch.t[u]);      // timing experiment only
-#else
-            for (int u = 0; u < U; ++u) ch.t[u] = fma(rn[pt_of(ks0, u) * REC + st - 1], z, ch.t[u]);
-#endif
-        } else if constexpr (st == DPAD + 1) {
+                for (int kk = 0; kk < KQ; ++kk) u.xa[pb][kk] = r[kk * 4 + (lane & 3)];
+                const double an = r[DPAD];
 #pragma unroll
-            for (int u = 0; u < U; ++u) ch.q[u] = ch.t[u] + MAGIC;
-        } else if constexpr (st == DPAD + 2) {
+                for (int rb = 0; rb < RB; ++rb) {
+                    const double2 b2 = *reinterpret_cast<const double2*>(sm.zbias + grow0 + rb * 8 + 2 * (lane & 3));
+                    u.t[2 * (pb * RB + rb)] = an + b2.x;
+                    u.t[2 * (pb * RB + rb) + 1] = an + b2.y;
+                }
+            }
+        } else if constexpr (st <= KQ) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
+            for (int q = 0; q < 4; ++q) dmma884_nv(u.t[2 * q], u.t[2 * q + 1], u.xa[q / RB][st - 1], zf[q % RB][st - 1]);
+        } else if constexpr (st == KQ + 1) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u.q[c] = u.t[c] + MAGIC;
+        } else if constexpr (st == KQ + 2) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
                 // t < -2.0e6 (result below exp(-677): flushed to zero) <=> sign set and magnitude above: compare the high
                 // word as an unsigned integer (ALU pipe); hi word of -2.0e6 = 0xC13E8480
-                const bool tiny = (unsigned)__double2hiint(ch.t[u]) > 0xC13E8480u;
-                const int nn = __double2loint(ch.q[u]);
-                ch.n[u] = tiny ? (int)0x80000000 : nn;
-                ch.q[u] = ch.q[u] - MAGIC;
+                const bool tiny = (unsigned)__double2hiint(u.t[c]) > 0xC13E8480u;
+                const int nn = __double2loint(u.q[c]);
+                u.n[c] = tiny ? (int)0x80000000 : nn;
+                u.q[c] = u.q[c] - MAGIC;
             }
-        } else if constexpr (st == DPAD + 3) {
+        } else if constexpr (st == KQ + 3) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) ch.t[u] = ch.t[u] - ch.q[u];          // r
-        } else if constexpr (st == DPAD + 4) {
+            for (int c = 0; c < 8; ++c) u.t[c] = u.t[c] - u.q[c];          // r
+        } else if constexpr (st == KQ + 4) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) ch.q[u] = fma(ch.t[u], C3, C2);
-        } else if constexpr (st == DPAD + 5) {
+            for (int c = 0; c < 8; ++c) u.q[c] = fma(u.t[c], C3, C2);
+        } else if constexpr (st == KQ + 5) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) ch.q[u] = fma(ch.q[u], ch.t[u], C1);
-        } else if constexpr (st == DPAD + 6) {
+            for (int c = 0; c < 8; ++c) u.q[c] = fma(u.q[c], u.t[c], C1);
+        } else if constexpr (st == KQ + 6) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) ch.q[u] = ch.q[u] * ch.t[u];
+            for (int c = 0; c < 8; ++c) u.q[c] = u.q[c] * u.t[c];
         } else {
+            double T[8], res[8];
 #pragma unroll
-            double T[U];
+            for (int c = 0; c < 8; ++c) T[c] = sm.tab[u.n[c] & (SGP_EXP_TAB - 1)];
 #pragma unroll
-#ifdef SGP_DBG_NOTAB
-            for (int u = 0; u < U; ++u) T[u] = ch.t[u];                    // timing experiment only
-#else
-            for (int u = 0; u < U; ++u) T[u] = sm.tab[ch.n[u] & (SGP_EXP_TAB - 1)];
-#endif
+            for (int c = 0; c < 8; ++c) {
+                res[c] = fma(T[c], u.q[c], T[c]);
+                const int hi = __double2hiint(res[c]) + ((u.n[c] >> 11) << 20);
+                res[c] = __hiloint2double(hi, __double2loint(res[c]));
+                if (u.n[c] == (int)0x80000000) res[c] = 0.0;
+            }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                double res = fma(T[u], ch.q[u], T[u]);
-                const int hi = __double2hiint(res) + ((ch.n[u] >> 11) << 20);
-                res = __hiloint2double(hi, __double2loint(res));
-                if (ch.n[u] == (int)0x80000000) res = 0.0;
-                const int pt = pt_of(ks0, u);
-                Kn[pt * LD + grow] = res;
-                if (DIAG) psi1_acc = fma(res, rn[pt * REC + DPAD + 1], psi1_acc);
+            for (int q = 0; q < 4; ++q) {
+                const int pt = (ui * NPB + q / RB) * 8 + prow;
+                *reinterpret_cast<double2*>(Kn + pt * LD + grow0 + (q % RB) * 8 + 2 * (lane & 3)) = make_double2(res[2 * q], res[2 * q + 1]);
+                if (DIAG) {
+                    const double wy = rn[pt * REC + DPAD + 1];
+                    psi1_acc[q % RB][0] = fma(res[2 * q], wy, psi1_acc[q % RB][0]);
+                    psi1_acc[q % RB][1] = fma(res[2 * q + 1], wy, psi1_acc[q % RB][1]);
+                }
             }
         }
     };
@@ -288,17 +309,6 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     const int a_off = wr * WM + (lane >> 2);                        // + 8*i
     const int b_off = (DIAG ? 0 : TM) + wc * WN + (lane >> 2);      // + 8*j
     const int kq = lane & 3;
-    // diagonal tiles: 8x8 blocks strictly above the diagonal are never needed (the reduce kernel mirrors the lower
-    // triangle); bit (i*NJ + j) of the mask = block (i, j) of this warp's tile is computed
-    unsigned long long mask = ~0ull;
-    if (DIAG) {
-        mask = 0ull;
-#pragma unroll
-        for (int i = 0; i < MI; ++i)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j)
-                if (wc * WN + 8 * j <= wr * WM + 8 * i + 7) mask |= 1ull << (i * NJ + j);
-    }
     double acc[MI][NJ][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
@@ -310,9 +320,9 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
         double* K0 = sm.Kt + (size_t)(g & 1u) * NB * LD;
         const double* r0 = sm.rec + (size_t)(g % kRecBufs) * NB * REC;
 #pragma unroll 1
-        for (int gi = 0; gi < KS / KSPAN; ++gi) {
-            Chains ch;
-            static_for<NST>([&](auto st) { gen_stage(st, ch, r0, K0, gi * KSPAN); });
+        for (int ui = 0; ui < RB; ++ui) {
+            Unit u;
+            static_for<NST>([&](auto st) { gen_stage(st, u, r0, K0, ui); });
         }
     }
     __syncthreads();
@@ -321,19 +331,19 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     auto body = [&](auto gen_tag, const int c) {
         constexpr bool GEN = decltype(gen_tag)::value;
         constexpr int DPK = MI * NJ;                  // DMMAs per k-step
-        constexpr int TOTAL = KSPAN * DPK;            // DMMAs one generator group is interleaved with
+        constexpr int TOTAL = KSPAN * DPK;            // DMMAs one generator unit is interleaved with
         const unsigned gc = g + c;
         const double* Kc = sm.Kt + (size_t)(gc & 1u) * NB * LD;
         double* Kn = sm.Kt + (size_t)((gc + 1) & 1u) * NB * LD;
         const double* rc = sm.rec + (size_t)(gc % kRecBufs) * NB * REC;
         const double* rn = sm.rec + (size_t)((gc + 1) % kRecBufs) * NB * REC;
         if (tid == 0 && c + kStages - 1 < nchunks) issue(c + kStages - 1);
-        if (c + 2 < nchunks && warp == (int)(gc % (NT / 32))) prep(c + 2);
+        if (c + 2 < nchunks && warp == (int)(gc % NWARPS)) prep(c + 2);
 
 #pragma unroll 1
-        for (int gi = 0; gi < KS / KSPAN; ++gi) {
-            const int ks0 = gi * KSPAN;
-            Chains ch;
+        for (int ui = 0; ui < RB; ++ui) {
+            const int ks0 = ui * KSPAN;
+            Unit u;
             double a[MI], b[NJ];
             static_for<TOTAL>([&](auto d_tag) {
                 constexpr int d = decltype(d_tag)::value;
@@ -353,10 +363,10 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
                 // the stage (at most one: TOTAL >= NST) whose slot floor(st * TOTAL / NST) is this DMMA
                 constexpr int st = (d * NST + TOTAL - 1) / TOTAL;
 #ifndef SGP_DBG_NOGEN
-                if constexpr (GEN && st < NST && (st * TOTAL) / NST == d) gen_stage(std::integral_constant<int, st>{}, ch, rn, Kn, ks0);
+                if constexpr (GEN && st < NST && (st * TOTAL) / NST == d) gen_stage(std::integral_constant<int, st>{}, u, rn, Kn, ui);
 #endif
 #ifndef SGP_DBG_NOMMA
-                if (!DIAG || ((mask >> dd) & 1ull)) dmma884_nv(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                dmma884_nv(acc[i][j][0], acc[i][j][1], a[i], b[j]);
 #else
                 acc[i][j][0] += a[i]; acc[i][j][1] += b[j];      // timing experiment only: keeps the fragment loads alive
 #endif
@@ -376,15 +386,17 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
             const int rr = wr * WM + 8 * i + (lane >> 2), cc = wc * WN + 8 * j + 2 * (lane & 3);
             *reinterpret_cast<double2*>(out + rr * TM + cc) = make_double2(acc[i][j][0], acc[i][j][1]);
         }
-    if (DIAG) {
-        sm.red[tid] = psi1_acc;
-        __syncthreads();
-        if (tid < TM) {
-            double v = 0.0;
+    if (DIAG) {   // Psi1 rows of this warp: sum over the eight point positions (lane / 4), lanes 0..3 hold two rows each
 #pragma unroll
-            for (int gq = 0; gq < GROUPS; ++gq) v += sm.red[gq * ROWS + tid];
-            p.psi1_partial[(size_t)slot * TM + tid] = v;
-        }
+        for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                double x = psi1_acc[rb][v];
+                x += __shfl_xor_sync(0xffffffffu, x, 4);
+                x += __shfl_xor_sync(0xffffffffu, x, 8);
+                x += __shfl_xor_sync(0xffffffffu, x, 16);
+                if (lane < 4) p.psi1_partial[(size_t)slot * TM + grow0 + rb * 8 + 2 * lane + v] = x;
+            }
     }
     if (p.dbg && tid == 0) {
         p.dbg[4 * slot + 0] = nchunks;
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const __grid_constant__ Sw
     extern __shared__ __align__(128) double smem[];
     SmemPtrs sm;
     sm.Kt = smem + S::kt; sm.tab = smem + S::tab; sm.zrec = smem + S::zrec; sm.rec = smem + S::rec; sm.stage = smem + S::stage;
-    sm.red = smem + S::red;
+    sm.zbias = smem + S::zbias;
     sm.full = reinterpret_cast<unsigned long long*>(smem + S::bars);
 
     const int tid = threadIdx.x;
