@@ -152,7 +152,7 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     constexpr int KSPAN = KS / RB;                   // k-steps one generator unit is spread over
     constexpr int NST = KQ + 8;                      // stages of a generator unit
     static_assert(RB == 1 || RB == 2 || RB == 4, "generator mapping");
-    static_assert(NB == 32 && KSPAN * MI * NJ >= NST, "generator schedule");
+    static_assert(NB == 32, "generator schedule");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D;
@@ -304,16 +304,25 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
         }
     };
 
-    // MMA mapping
+    // MMA mapping.  Off-diagonal tile: WR x 4 warps, a WM x WN register tile each.  Diagonal tile: only the lower triangle
+    // is needed (the reduce kernel mirrors it), i.e. 10 of the 16 SB x SB sub-blocks (SB = TM/4).  They are dealt out so
+    // that every scheduler (warps w and w+4) gets at most 3: slot 0 for every warp, slot 1 for warps 0 and 1 only.
+    constexpr int SB = TM / 4, SI = SB / 8;
+    static_assert(!DIAG || NWARPS == 8, "diagonal sub-block schedule is written for 8 warps");
     const int wr = warp >> 2, wc = warp & 3;
-    const int a_off = wr * WM + (lane >> 2);                        // + 8*i
-    const int b_off = (DIAG ? 0 : TM) + wc * WN + (lane >> 2);      // + 8*j
+    const int s0r = (0x32103321 >> (4 * warp)) & 0xf, s0c = (0x32102110 >> (4 * warp)) & 0xf;   // warps 7..0: rows 3,2,1,0,3,3,2,1
+    const int s1r = warp == 0 ? 2 : 3, s1c = 0;                                               // slot 1: (2,0) / (3,0)
+    const bool has1 = DIAG && warp < 2;
+    const int a_off = (DIAG ? s0r * SB : wr * WM) + (lane >> 2);              // + 8*i
+    const int b_off = (DIAG ? s0c * SB : TM + wc * WN) + (lane >> 2);         // + 8*j
+    const int a1_off = s1r * SB + (lane >> 2), b1_off = s1c * SB + (lane >> 2);
     const int kq = lane & 3;
-    double acc[MI][NJ][2];
+    constexpr int AI = DIAG ? 2 * SI : MI, AJ = DIAG ? SI : NJ;      // accumulator blocks (diagonal: slot s = rows [s*SI, (s+1)*SI))
+    double acc[AI][AJ][2];
 #pragma unroll
-    for (int i = 0; i < MI; ++i)
+    for (int i = 0; i < AI; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < AJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // prologue: tile of chunk 0 (nothing to overlap with)
     {
@@ -330,8 +339,10 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     // one pipeline step: consume chunk c (DMMA.8x8x4) while generating chunk c+1 (GEN)
     auto body = [&](auto gen_tag, const int c) {
         constexpr bool GEN = decltype(gen_tag)::value;
-        constexpr int DPK = MI * NJ;                  // DMMAs per k-step
+        constexpr int FI = DIAG ? SI : MI, FJ = DIAG ? SI : NJ;   // fragment blocks of the (slot-0) tile
+        constexpr int DPK = FI * FJ;                  // DMMAs per k-step (diagonal: of slot 0)
         constexpr int TOTAL = KSPAN * DPK;            // DMMAs one generator unit is interleaved with
+        static_assert(TOTAL >= NST, "generator schedule");
         const unsigned gc = g + c;
         const double* Kc = sm.Kt + (size_t)(gc & 1u) * NB * LD;
         double* Kn = sm.Kt + (size_t)((gc + 1) & 1u) * NB * LD;
@@ -344,20 +355,37 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
         for (int ui = 0; ui < RB; ++ui) {
             const int ks0 = ui * KSPAN;
             Unit u;
-            double a[MI], b[NJ];
+            double a[FI], b[FJ];
             static_for<TOTAL>([&](auto d_tag) {
                 constexpr int d = decltype(d_tag)::value;
-                constexpr int kk = d / DPK, dd = d % DPK, i = dd / NJ, j = dd % NJ;
+                constexpr int kk = d / DPK, dd = d % DPK, i = dd / FJ, j = dd % FJ;
                 if constexpr (dd == 0) {
                     const double* row = Kc + ((ks0 + kk) * 4 + kq) * LD;
+                    if (DIAG && kk > 0 && has1) {      // slot 1 of the previous k-step (a, b are free to be overwritten)
+                        const double* prow_ = row - 4 * LD;
+                        double a1[FI], b1[FJ];
 #pragma unroll
-                    for (int ii = 0; ii < MI; ++ii) a[ii] = row[a_off + 8 * ii];
+                        for (int ii = 0; ii < FI; ++ii) a1[ii] = prow_[a1_off + 8 * ii];
 #pragma unroll
-                    for (int jj = 0; jj < NJ; ++jj) b[jj] = row[b_off + 8 * jj];
+                        for (int jj = 0; jj < FJ; ++jj) b1[jj] = prow_[b1_off + 8 * jj];
+                        if (WEIGHTED) {
+                            const double wn = rc[((ks0 + kk - 1) * 4 + kq) * REC + DPAD + 2];
+#pragma unroll
+                            for (int jj = 0; jj < FJ; ++jj) b1[jj] *= wn;
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < FI; ++ii)
+#pragma unroll
+                            for (int jj = 0; jj < FJ; ++jj) dmma884_nv(acc[(DIAG ? FI : 0) + ii][jj][0], acc[(DIAG ? FI : 0) + ii][jj][1], a1[ii], b1[jj]);
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < FI; ++ii) a[ii] = row[a_off + 8 * ii];
+#pragma unroll
+                    for (int jj = 0; jj < FJ; ++jj) b[jj] = row[b_off + 8 * jj];
                     if (WEIGHTED) {
                         const double wn = rc[((ks0 + kk) * 4 + kq) * REC + DPAD + 2];
 #pragma unroll
-                        for (int jj = 0; jj < NJ; ++jj) b[jj] *= wn;
+                        for (int jj = 0; jj < FJ; ++jj) b[jj] *= wn;
                     }
                 }
                 // the stage (at most one: TOTAL >= NST) whose slot floor(st * TOTAL / NST) is this DMMA
@@ -371,21 +399,55 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
                 acc[i][j][0] += a[i]; acc[i][j][1] += b[j];      // timing experiment only: keeps the fragment loads alive
 #endif
             });
+            if (has1) {      // slot 1 of the unit's last k-step
+                const double* row = Kc + ((ks0 + KSPAN - 1) * 4 + kq) * LD;
+                double a1[FI], b1[FJ];
+#pragma unroll
+                for (int ii = 0; ii < FI; ++ii) a1[ii] = row[a1_off + 8 * ii];
+#pragma unroll
+                for (int jj = 0; jj < FJ; ++jj) b1[jj] = row[b1_off + 8 * jj];
+                if (WEIGHTED) {
+                    const double wn = rc[((ks0 + KSPAN - 1) * 4 + kq) * REC + DPAD + 2];
+#pragma unroll
+                    for (int jj = 0; jj < FJ; ++jj) b1[jj] *= wn;
+                }
+#pragma unroll
+                for (int ii = 0; ii < FI; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < FJ; ++jj) dmma884_nv(acc[(DIAG ? FI : 0) + ii][jj][0], acc[(DIAG ? FI : 0) + ii][jj][1], a1[ii], b1[jj]);
+            }
         }
+#ifndef SGP_DBG_NOBAR
         __syncthreads();   // chunk c consumed by every warp, chunk c+1 generated, records of chunk c+2 complete
+#endif
     };
     for (int c = 0; c + 1 < nchunks; ++c) body(std::true_type{}, c);
     body(std::false_type{}, nchunks - 1);
 
     // ---- epilogue: register tile -> workspace slot (row-major TM x TM) ------------------------------------------
     double* out = p.partial + (size_t)slot * (TM * TM);
+    if (DIAG) {
 #pragma unroll
-    for (int i = 0; i < MI; ++i)
+        for (int sl = 0; sl < 2; ++sl) {
+            if (sl == 1 && !has1) break;
+            const int r0 = (sl ? s1r : s0r) * SB, c0 = (sl ? s1c : s0c) * SB;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int rr = wr * WM + 8 * i + (lane >> 2), cc = wc * WN + 8 * j + 2 * (lane & 3);
-            *reinterpret_cast<double2*>(out + rr * TM + cc) = make_double2(acc[i][j][0], acc[i][j][1]);
+            for (int i = 0; i < SI; ++i)
+#pragma unroll
+                for (int j = 0; j < SI; ++j) {
+                    const int rr = r0 + 8 * i + (lane >> 2), cc = c0 + 8 * j + 2 * (lane & 3);
+                    *reinterpret_cast<double2*>(out + rr * TM + cc) = make_double2(acc[sl * SI + i][j][0], acc[sl * SI + i][j][1]);
+                }
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < AI; ++i)
+#pragma unroll
+            for (int j = 0; j < AJ; ++j) {
+                const int rr = wr * WM + 8 * i + (lane >> 2), cc = wc * WN + 8 * j + 2 * (lane & 3);
+                *reinterpret_cast<double2*>(out + rr * TM + cc) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+    }
     if (DIAG) {   // Psi1 rows of this warp: sum over the eight point positions (lane / 4), lanes 0..3 hold two rows each
 #pragma unroll
         for (int rb = 0; rb < RB; ++rb)
@@ -585,7 +647,7 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     // one persistent CTA per SM; the (tile, chunk) sequence is cut into equally heavy contiguous slices.  Cost weights
     // of one chunk (measured per-chunk clocks, see profiles/): off-diagonal 2*TM generated rows + TM^2 MMA, diagonal TM
     // rows + the MMA blocks on or below the diagonal
-    int w_diag = 11, w_off = 16;
+    int w_diag = 17, w_off = 24;
     if (const char* e = std::getenv("SGP_SWEEP_WEIGHTS")) { int a_ = 0, b_ = 0; if (std::sscanf(e, "%d,%d", &a_, &b_) == 2 && a_ > 0 && b_ > 0) { w_diag = a_; w_off = b_; } }
     const long long total_cost = chunks * ((long long)nblk * w_diag + (long long)(ntiles - nblk) * w_off);
     const int ncta = (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, chunks * ntiles));
@@ -614,10 +676,7 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     int launches = 0;
     zprep_kernel<<<(Mpad + 127) / 128, 128, 0, ctx->stream>>>(ctx->Z_dev, zt, zb, M, Mpad, D, dpad, p, std::log(ctx->variance)); ++launches;
     if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    int nthreads = 256;
-    if (const char* e = std::getenv("SGP_SWEEP_THREADS")) nthreads = std::atoi(e);
-    if (TM == 128 && nthreads == 512) rc = launch_d<128, NB, 512>(ctx, p, w != nullptr, grid, dpad);
-    else if (TM == 128) rc = launch_d<128, NB, 256>(ctx, p, w != nullptr, grid, dpad);
+    if (TM == 128) rc = launch_d<128, NB, 256>(ctx, p, w != nullptr, grid, dpad);
     else rc = launch_d<64, NB, 256>(ctx, p, w != nullptr, grid, dpad);
     if (rc) return rc;
     ++launches;
