@@ -31,20 +31,22 @@
 #include <cstdlib>
 #include <type_traits>
 #include <utility>
+#include <cooperative_groups.h>
 
 namespace {
 
-constexpr int kMaxThreads = 512;
 constexpr int kStages = 4;       // TMA stages of raw points
 constexpr int kRecBufs = 3;      // record buffers: written two chunks ahead, read by the generator and by the MMA (weights)
 
 struct SweepParams {
     const double* X; const double* y; const double* w;   // device, point-major, padded to a chunk multiple
-    const double* zt;                                    // [Mpad][DPAD] scaled + centred inducing inputs
-    const double* zb;                                    // [Mpad]       s * (ln sigma^2 - |z~|^2 / 2)
+    const double* yv;                                    // Var[y_n] or nullptr (only enters sum_n w (y^2 + yv))
+    const double* Z;                                     // [M][D] raw inducing inputs
     const double* exptab;
     double* partial;                                     // [nslots][TM*TM]   slot = cta + tile
     double* psi1_partial;                                // [nslots][TM]
+    double* scal_partial;                                // [nslots][2]       sum w, sum w (y^2 + yv) of tile 0's segments
+    double *psi2, *psi1, *scal;                          // results: M x M column-major (full symmetric), M, {Psi0, sum_y2, sum_w, N}
     long long* dbg;                                      // optional [nslots][4]: chunks, clocks, diag, cta
     long long N;
     long long chunks;
@@ -53,6 +55,8 @@ struct SweepParams {
     int w_diag, w_off;                                   // cost weights of one chunk of a diagonal / off-diagonal tile
     double inv_ell_s[SGP_MAX_D];                         // sqrt(s) / ell_d  (both operands carry sqrt(s))
     double center[SGP_MAX_D];
+    double log_var_s;                                    // s * ln sigma^2
+    double variance;
 };
 
 // ---- work partition (shared by the sweep and the reduce kernels, so that both see the same segments) -------------
@@ -196,12 +200,19 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     };
 
     __syncthreads();   // the previous segment is completely done with zrec / zbias / the tile buffers
-    // inducing rows: block I -> panel rows [0,TM), block J -> rows [TM, 2TM)
-    for (int i = tid; i < ROWS * ZR; i += NT) {
-        const int r = i / ZR, d = i - r * ZR;
+    // inducing rows: block I -> panel rows [0,TM), block J -> rows [TM, 2TM);  z~ = sqrt(s) (z - c)/ell,
+    // b = s (ln sigma^2 - |(z-c)/ell|^2 / 2); rows >= M are padding that generates exact zeros
+    for (int r = tid; r < ROWS; r += NT) {
         const int gm = (r < TM ? I * TM + r : J * TM + (r - TM));
-        if (d < DPAD) sm.zrec[i] = p.zt[(size_t)gm * DPAD + d];
-        else sm.zbias[r] = p.zb[gm];
+        double a = 0.0;
+#pragma unroll
+        for (int d = 0; d < DPAD; ++d) {
+            double v = 0.0;
+            if (gm < p.M && d < D) v = (p.Z[(size_t)gm * D + d] - p.center[d]) * p.inv_ell_s[d];
+            sm.zrec[r * ZR + d] = v;
+            a = fma(v, v, a);
+        }
+        sm.zbias[r] = (gm < p.M) ? (p.log_var_s - 0.5 * a) : -1.0e300;
     }
     if (tid == 0)
         for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
@@ -460,11 +471,119 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
                 if (lane < 4) p.psi1_partial[(size_t)slot * TM + grow0 + rb * 8 + 2 * lane + v] = x;
             }
     }
+    if (DIAG && I == 0) {   // tile 0 sees every point once: sum_n w_n and sum_n w_n (y_n^2 + yv_n) of this segment's points
+        const long long n_lo = c_begin * NB, n_hi = min(p.N, (c_begin + nchunks) * (long long)NB);
+        double sw = 0.0, sy = 0.0;
+        for (long long n = n_lo + tid; n < n_hi; n += NT) {
+            const double wn = WEIGHTED ? p.w[n] : 1.0, yn = p.y[n], vn = p.yv ? p.yv[n] : 0.0;
+            sw += wn;
+            sy = fma(wn, fma(yn, yn, vn), sy);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sw += __shfl_xor_sync(0xffffffffu, sw, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        }
+        double* red = sm.stage;            // the staging buffers are idle here
+        __syncthreads();
+        if (lane == 0) { red[2 * warp] = sw; red[2 * warp + 1] = sy; }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0, b = 0.0;
+            for (int wq = 0; wq < NWARPS; ++wq) { a += red[2 * wq]; b += red[2 * wq + 1]; }
+            p.scal_partial[2 * slot] = a;
+            p.scal_partial[2 * slot + 1] = b;
+        }
+    }
     if (p.dbg && tid == 0) {
         p.dbg[4 * slot + 0] = nchunks;
         p.dbg[4 * slot + 1] = clock64() - t_start;
         p.dbg[4 * slot + 2] = DIAG ? 1 : 0;
         p.dbg[4 * slot + 3] = blockIdx.x;
+    }
+
+}
+
+// Second phase, after a grid-wide barrier: every CTA takes an equal share of the (tile, 4-row stripe) items, adds the
+// partials of the tile's segments in slot (= CTA) order -- deterministic, no FP64 atomics --, mirrors the triangle into the
+// full symmetric Psi2 and finishes Psi1 and the scalars.
+template <int TM, int NT>
+__device__ __forceinline__ void reduce_items(const SweepParams& p, double* __restrict__ S_, int* __restrict__ ibuf) {
+    constexpr int SR = 4, STRIPES = TM / SR, NWARPS = NT / 32, LDS_ = TM + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nitems = p.ntiles * STRIPES;
+    const int it0 = (int)((long long)nitems * blockIdx.x / gridDim.x), it1 = (int)((long long)nitems * (blockIdx.x + 1) / gridDim.x);
+    int* slots = ibuf + NWARPS;
+    int cur_tile = -1, nseg = 0, I = 0, J = 0;
+    for (int it = it0; it < it1; ++it) {
+        const int tile = it / STRIPES, stripe = it - tile * STRIPES;
+        if (tile != cur_tile) {      // the tile's workspace slots in CTA order: one candidate CTA per thread (ncta <= NT)
+            cur_tile = tile;
+            long long pre = 0;
+            I = 0; J = 0;
+            for (int t = 0; t < tile; ++t) {
+                pre += (long long)(I == J ? p.w_diag : p.w_off) * p.chunks;
+                if (++J > I) { ++I; J = 0; }
+            }
+            int mine = 0;
+            if (tid < p.ncta) {
+                long long lo, hi;
+                seg_range(cta_pos(p.total_cost, p.ncta, tid), cta_pos(p.total_cost, p.ncta, tid + 1), pre, I == J ? p.w_diag : p.w_off, p.chunks, lo, hi);
+                mine = lo < hi;
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, mine);
+            __syncthreads();                                     // the previous item is done with ibuf / S_
+            if (lane == 0) ibuf[warp] = (int)ballot;
+            nseg = __syncthreads_count(mine);
+            if (mine) {
+                int before = __popc(ballot & ((1u << lane) - 1u));
+                for (int wq = 0; wq < warp; ++wq) before += __popc((unsigned)ibuf[wq]);
+                slots[before] = tid + tile;
+            }
+        }
+        __syncthreads();
+        const bool diag = (I == J);
+        const int r0 = stripe * SR;
+        if (tid < SR * TM / 2) {
+            const int e = 2 * tid, rl = e / TM, c = e - rl * TM, r = r0 + rl;
+            double2 v = make_double2(0.0, 0.0);
+            if (!diag || c <= r) {
+                const double* src = p.partial + (size_t)r * TM + c;
+#pragma unroll 8
+                for (int sq = 0; sq < nseg; ++sq) {
+                    const double2 x = __ldcg(reinterpret_cast<const double2*>(src + (size_t)slots[sq] * (TM * TM)));
+                    v.x += x.x; v.y += x.y;
+                }
+            }
+            S_[rl * LDS_ + c] = v.x; S_[rl * LDS_ + c + 1] = v.y;
+        }
+        __syncthreads();
+        for (int e = tid; e < SR * TM; e += NT) {
+            {   // psi2[gi + gj*M]: SR consecutive rows = one 32-byte sector per column
+                const int rl = e % SR, c = e / SR, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
+                if (gi < p.M && gj < p.M && (!diag || c <= r)) p.psi2[(size_t)gi + (size_t)gj * p.M] = S_[rl * LDS_ + c];
+            }
+            {   // mirror psi2[gj + gi*M]: consecutive threads -> consecutive columns
+                const int rl = e / TM, c = e % TM, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
+                if (gi < p.M && gj < p.M && (diag ? c < r : true)) p.psi2[(size_t)gj + (size_t)gi * p.M] = S_[rl * LDS_ + c];
+            }
+        }
+        if (diag && tid < SR) {
+            const int r = r0 + tid, gi = I * TM + r;
+            if (gi < p.M) {
+                double v = 0.0;
+                for (int sq = 0; sq < nseg; ++sq) v += __ldcg(p.psi1_partial + (size_t)slots[sq] * TM + r);
+                p.psi1[gi] = v;
+            }
+        }
+        if (tile == 0 && stripe == 0 && tid == 0) {
+            double sw = 0.0, sy = 0.0;
+            for (int sq = 0; sq < nseg; ++sq) { sw += __ldcg(p.scal_partial + 2 * slots[sq]); sy += __ldcg(p.scal_partial + 2 * slots[sq] + 1); }
+            p.scal[0] = p.variance * sw;   // Psi0 = sum_n w_n k(x_n, x_n)
+            p.scal[1] = sy;                // sum_n w_n (ybar^2 + yvar)
+            p.scal[2] = sw;
+            p.scal[3] = (double)p.N;
+        }
     }
 }
 
@@ -504,106 +623,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const __grid_constant__ Sw
         pre += (long long)wt * p.chunks;
         if (++J > I) { ++I; J = 0; }
     }
-}
-
-// Fixed-order sum over the segments of a tile, mirror to the full symmetric matrix, finish Psi1.
-template <int TM>
-__global__ void reduce_kernel(const double* __restrict__ partial, const double* __restrict__ psi1_partial, double* __restrict__ psi2,
-                              double* __restrict__ psi1, int M, long long chunks, long long total_cost, int ncta, int w_diag, int w_off) {
-    __shared__ int slots[1024];
-    __shared__ int nslots;
-    const int tile = blockIdx.x;
-    int I = 0, J = 0;
-    long long pre = 0;
-    for (int t = 0; t < tile; ++t) {
-        pre += (long long)(I == J ? w_diag : w_off) * chunks;
-        if (++J > I) { ++I; J = 0; }
-    }
-    if (threadIdx.x == 0) {
-        const int wt = (I == J) ? w_diag : w_off;
-        int n = 0;
-        for (int b = 0; b < ncta; ++b) {
-            long long lo, hi;
-            seg_range(cta_pos(total_cost, ncta, b), cta_pos(total_cost, ncta, b + 1), pre, wt, chunks, lo, hi);
-            if (lo < hi) slots[n++] = b + tile;
-        }
-        nslots = n;
-    }
-    __syncthreads();
-    const int ns = nslots;
-    for (int e = threadIdx.x; e < TM * TM; e += blockDim.x) {
-        const int r = e / TM, c = e - r * TM;
-        const int gi = I * TM + r, gj = J * TM + c;
-        if (gi >= M || gj >= M) continue;
-        if (I == J && c > r) continue;
-        double v = 0.0;
-        for (int s = 0; s < ns; ++s) v += partial[(size_t)slots[s] * (TM * TM) + e];
-        psi2[(size_t)gi + (size_t)gj * M] = v;
-        psi2[(size_t)gj + (size_t)gi * M] = v;
-    }
-    if (I == J) {
-        for (int r = threadIdx.x; r < TM; r += blockDim.x) {
-            const int gi = I * TM + r;
-            if (gi >= M) continue;
-            double v = 0.0;
-            for (int s = 0; s < ns; ++s) v += psi1_partial[(size_t)slots[s] * TM + r];
-            psi1[gi] = v;
-        }
-    }
-}
-
-// z~ = sqrt(s) (z - c)/ell,  b = s (ln sigma^2 - |(z-c)/ell|^2 / 2); rows >= M are padding that generates exact zeros.
-__global__ void zprep_kernel(const double* __restrict__ Z, double* __restrict__ zt, double* __restrict__ zb, int M, int Mpad, int D,
-                             int DPAD, SweepParams p, double log_var) {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= Mpad) return;
-    double a = 0.0;
-    for (int d = 0; d < DPAD; ++d) {
-        double v = 0.0;
-        if (m < M && d < D) v = (Z[(size_t)m * D + d] - p.center[d]) * p.inv_ell_s[d];
-        zt[(size_t)m * DPAD + d] = v;
-        a = fma(v, v, a);
-    }
-    zb[m] = (m < M) ? (SGP_EXP_SCALE * log_var - 0.5 * a) : -1.0e300;
-}
-
-// sum_w, sum_w (y^2 + yv): warp-shuffle + block reduction, one partial per block, fixed-order finish
-__global__ void scalar_sums_kernel(const double* __restrict__ y, const double* __restrict__ yv, const double* __restrict__ w, long long N,
-                                   double* __restrict__ partial) {
-    double sw = 0.0, sy = 0.0;
-    for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
-        double wn = w ? w[n] : 1.0, yn = y[n], vn = yv ? yv[n] : 0.0;
-        sw += wn;
-        sy = fma(wn, fma(yn, yn, vn), sy);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        sw += __shfl_xor_sync(0xffffffffu, sw, o);
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
-    }
-    __shared__ double s_w[32], s_y[32];
-    int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    if (lane == 0) { s_w[wp] = sw; s_y[wp] = sy; }
-    __syncthreads();
-    if (wp == 0) {
-        int nw = blockDim.x >> 5;
-        sw = lane < nw ? s_w[lane] : 0.0;
-        sy = lane < nw ? s_y[lane] : 0.0;
-        for (int o = 16; o > 0; o >>= 1) {
-            sw += __shfl_xor_sync(0xffffffffu, sw, o);
-            sy += __shfl_xor_sync(0xffffffffu, sy, o);
-        }
-        if (lane == 0) { partial[2 * blockIdx.x] = sw; partial[2 * blockIdx.x + 1] = sy; }
-    }
-}
-__global__ void scalar_finish_kernel(const double* __restrict__ partial, int nblocks, double variance, long long N, double* __restrict__ scal) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double sw = 0.0, sy = 0.0;
-        for (int b = 0; b < nblocks; ++b) { sw += partial[2 * b]; sy += partial[2 * b + 1]; }
-        scal[0] = variance * sw;   // Psi0 = sum_n w_n k(x_n, x_n)
-        scal[1] = sy;              // sum_n w_n (ybar^2 + yvar)
-        scal[2] = sw;
-        scal[3] = (double)N;
-    }
+    // every partial tile of the sweep is in the workspace once all CTAs are here (cooperative launch: all CTAs resident)
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    reduce_items<TM, NT>(p, sm.Kt, reinterpret_cast<int*>(sm.stage));
 }
 
 template <int TM, int NB, int DPAD, int NT>
@@ -611,7 +634,8 @@ int launch_t(sgp_ctx* ctx, const SweepParams& p, bool weighted, int grid) {
     using S = Smem<TM, NB, DPAD>;
     auto kern = weighted ? sweep_kernel<TM, NB, DPAD, NT, true> : sweep_kernel<TM, NB, DPAD, NT, false>;
     SGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
-    kern<<<grid, NT, S::bytes, ctx->stream>>>(p);
+    void* args[] = {const_cast<SweepParams*>(&p)};
+    SGP_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NT), args, S::bytes, ctx->stream));
     ctx->last_grid = grid; ctx->last_block = NT; ctx->last_smem = (int)S::bytes;
     SGP_CUDA(ctx, cudaGetLastError());
     return SGP_OK;
@@ -640,7 +664,7 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     const int M = ctx->M, D = ctx->D;
     const int dpad = D <= 2 ? 2 : D <= 4 ? 4 : D <= 8 ? 8 : 16;
     const int TM = (M > 192) ? 128 : 64;
-    const int nblk = (M + TM - 1) / TM, Mpad = nblk * TM;
+    const int nblk = (M + TM - 1) / TM;
     const int ntiles = nblk * (nblk + 1) / 2;
     const long long chunks = (N + NB - 1) / NB;
     if (chunks * NB > Ncap) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: data buffers must be padded to a multiple of 32 points");
@@ -650,43 +674,34 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     int w_diag = 17, w_off = 24;
     if (const char* e = std::getenv("SGP_SWEEP_WEIGHTS")) { int a_ = 0, b_ = 0; if (std::sscanf(e, "%d,%d", &a_, &b_) == 2 && a_ > 0 && b_ > 0) { w_diag = a_; w_off = b_; } }
     const long long total_cost = chunks * ((long long)nblk * w_diag + (long long)(ntiles - nblk) * w_off);
-    const int ncta = (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, chunks * ntiles));
+    const int ncta = (int)std::min<long long>(std::min(ctx->num_sms, 256), std::max<long long>(1, chunks * ntiles));   // <= block size: see the segment count in run_segment
     const int grid = ncta;
     const int nslots = ncta + ntiles;
 
-    size_t need_work = (size_t)nslots * TM * TM + (size_t)nslots * TM + 2 * 1024;
+    size_t need_work = (size_t)nslots * TM * TM + (size_t)nslots * TM + (size_t)nslots * 2 + 2;
     int rc = sgp_ensure(ctx, &ctx->work_dev, &ctx->work_cap, need_work); if (rc) return rc;
-    rc = sgp_ensure(ctx, &ctx->zrec_dev, &ctx->zrec_cap, (size_t)Mpad * (16 + 1)); if (rc) return rc;
     size_t need_stats = (size_t)M * M + (size_t)M + 8;
     rc = sgp_ensure(ctx, &ctx->stats_dev, &ctx->stats_cap, need_stats); if (rc) return rc;
     ctx->Dout = 1;
 
     SweepParams p{};
-    p.X = X; p.y = y; p.w = w; p.N = N; p.chunks = chunks; p.M = M; p.D = D; p.ntiles = ntiles; p.nblk = nblk; p.ncta = ncta;
+    p.X = X; p.y = y; p.yv = yv; p.w = w; p.N = N; p.chunks = chunks; p.M = M; p.D = D; p.ntiles = ntiles; p.nblk = nblk; p.ncta = ncta;
     p.total_cost = total_cost; p.w_diag = w_diag; p.w_off = w_off; p.dbg = (nslots <= 8192) ? ctx->sweep_dbg_dev : nullptr;
     if (p.dbg) { SGP_CUDA(ctx, cudaMemsetAsync(p.dbg, 0xff, (size_t)nslots * 4 * sizeof(long long), ctx->stream)); ctx->sweep_dbg_slots = nslots; }
     const double sq = std::sqrt(SGP_EXP_SCALE);
     for (int d = 0; d < SGP_MAX_D; ++d) { p.inv_ell_s[d] = d < D ? sq / ctx->ell[d] : 0.0; p.center[d] = d < D ? ctx->center[d] : 0.0; }
-    double* zt = ctx->zrec_dev; double* zb = ctx->zrec_dev + (size_t)Mpad * 16;
-    p.zt = zt; p.zb = zb; p.exptab = ctx->exptab_dev;
-    p.partial = ctx->work_dev; p.psi1_partial = ctx->work_dev + (size_t)nslots * TM * TM;
-    double* scal_partial = p.psi1_partial + (size_t)nslots * TM;
-    double* psi2 = ctx->stats_dev; double* psi1 = psi2 + (size_t)M * M; double* scal = psi1 + M;
+    p.log_var_s = SGP_EXP_SCALE * std::log(ctx->variance); p.variance = ctx->variance;
+    p.Z = ctx->Z_dev; p.exptab = ctx->exptab_dev;
+    p.partial = ctx->work_dev; p.psi1_partial = p.partial + (size_t)nslots * TM * TM; p.scal_partial = p.psi1_partial + (size_t)nslots * TM;
+    p.psi2 = ctx->stats_dev; p.psi1 = p.psi2 + (size_t)M * M; p.scal = p.psi1 + M;
 
     int launches = 0;
-    zprep_kernel<<<(Mpad + 127) / 128, 128, 0, ctx->stream>>>(ctx->Z_dev, zt, zb, M, Mpad, D, dpad, p, std::log(ctx->variance)); ++launches;
     if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     if (TM == 128) rc = launch_d<128, NB, 256>(ctx, p, w != nullptr, grid, dpad);
     else rc = launch_d<64, NB, 256>(ctx, p, w != nullptr, grid, dpad);
     if (rc) return rc;
     ++launches;
     if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (TM == 128) reduce_kernel<128><<<ntiles, 256, 0, ctx->stream>>>(p.partial, p.psi1_partial, psi2, psi1, M, chunks, total_cost, ncta, w_diag, w_off);
-    else reduce_kernel<64><<<ntiles, 256, 0, ctx->stream>>>(p.partial, p.psi1_partial, psi2, psi1, M, chunks, total_cost, ncta, w_diag, w_off);
-    ++launches;
-    int sb = (int)std::min<long long>(1024, (N + 255) / 256); if (sb < 1) sb = 1;
-    scalar_sums_kernel<<<sb, 256, 0, ctx->stream>>>(y, yv, w, N, scal_partial); ++launches;
-    scalar_finish_kernel<<<1, 32, 0, ctx->stream>>>(scal_partial, sb, ctx->variance, N, scal); ++launches;
     SGP_CUDA(ctx, cudaGetLastError());
     ctx->last_launches = launches;
     ctx->have_stats = true;
