@@ -40,6 +40,19 @@ def fp64_peak():
     return FP64_SPEC_TFLOPS, "spec (no measurement file)"
 
 
+def traffic(which):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of sweep_kernel from the committed `ncu --set full` captures
+    (profiles/r01_traffic.json: kin40k shape as benchmarked; synthetic scaled per point from the N=400000 capture)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if which == "kin40k":
+        return d.get("kin40k_bytes_per_launch")
+    per_pt = d.get("synthetic_bytes_per_point")
+    return None if per_pt is None else per_pt * SYN["N"]
+
+
 class ClockSampler:
     def __init__(self, dev):
         self.dev = dev; self.samples = []; self.reasons = set(); self.stop = False; self.max_mhz = None
@@ -196,15 +209,20 @@ def main():
     info = ctx.last_sweep_info()
     value = world * cfg["N"] / (ms_step * 1e-3)
 
-    # e2e through the C ABI with host buffers (pinned by the library's own staging is not assumed: plain host arrays)
+    # e2e through the C ABI with HOST buffers in pinned memory (sgp_pinned_alloc): per step the H2D copy of X / y
+    # (sgp_set_data) and the D2H read of Psi0 / Psi1 / Psi2 / sum_y2 (sgp_sweep_psi) are inside the timed region
+    from gaussianprocessnode_b200 import pinned_empty
+    Xp = pinned_empty(X.shape); Xp[...] = X
+    yp = pinned_empty(y.shape); yp[...] = y
+    psi1p = pinned_empty((cfg["M"],)); psi2p = pinned_empty((cfg["M"], cfg["M"]), order="F")
     for _ in range(3):
-        ctx.set_data(X, y); ctx.sweep_psi()
+        ctx.set_data(Xp, yp); ctx.sweep_psi(out=(psi1p, psi2p))
     barrier()
     n_e2e = max(10, min(args.steps, 50))
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        ctx.set_data(X, y)
-        out = ctx.sweep_psi()
+        ctx.set_data(Xp, yp)
+        out = ctx.sweep_psi(out=(psi1p, psi2p))
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / n_e2e)
     h2d = X.nbytes + y.nbytes
@@ -224,8 +242,8 @@ def main():
                    "parallelism": "N sharded over %d GPU(s)" % world, "wall_s_timed_region": t_wall},
         "e2e": {"value": e2e_val, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(info["launches"] * args.steps),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "sweep_kernel<128,32,8> grid=%d block=%d smem=%d" % (info["grid"], info["block"], info["smem_bytes"]),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic("kin40k"),
+                     "kernel": "sweep_kernel<128,32,8,256> (one cooperative launch per sweep) grid=%d block=%d smem=%d" % (info["grid"], info["block"], info["smem_bytes"]),
                      "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_main, "peak_source": peak_src,
                      "note": "kin40k shape is 2.6 GFLOP: launch/latency-bound (66 us at peak); see synthetic_10M for the throughput-bound case"},
         "clocks": clk.summary(),
@@ -260,7 +278,7 @@ def main():
             "value": world * n_pad / (ms_s * 1e-3), "unit": "points/s", "ms_per_step": ms_s, "steps": args.syn_steps,
             "psi2_tflops_all_gpus": world * fl / (ms_s * 1e-3) * 1e-12,
             "roofline": {"bound": "tensor", "achieved": fl / (ms_m * 1e-3) * 1e-12, "peak": peak, "unit": "TFLOP/s",
-                         "frac": fl / (ms_m * 1e-3) * 1e-12 / peak, "traffic": None, "ms_per_launch": ms_m,
+                         "frac": fl / (ms_m * 1e-3) * 1e-12 / peak, "traffic": traffic("synthetic"), "ms_per_launch": ms_m,
                          "algorithmic_flops_per_launch": fl, "kernel": "sweep_kernel<128,32,8> grid=%d" % info2["grid"],
                          "peak_source": peak_src},
             "clocks": clk2.summary()}
@@ -268,10 +286,10 @@ def main():
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1:
-        rate, secs = cpu_port_rate(KIN, 4000, native=True)
+        rate, secs = cpu_port_rate(KIN, KIN["N"], native=True, reps=5)
         line["cpu_baseline"] = {"value": rate, "unit": "points/s", "cores": 1, "kind": "port",
-                                "sample": "4000 of the 10000 kin40k-shape points (%.1f s); C port of the reference's per-point "
-                                          "rule + prod schedule (oracle/sweep_port.c), Julia not installed" % secs}
+                                "sample": "all 10000 kin40k-shape points, best of 5 passes (%.1f s each); C port of the reference's "
+                                          "per-point rule + prod schedule (oracle/sweep_port.c), Julia not installed" % secs}
         try:
             from oracle import batched
             Xs, ys = synth(KIN, KIN["N"], 7)

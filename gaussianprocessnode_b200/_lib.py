@@ -18,6 +18,8 @@ SIGNATURES = {
     "sgp_destroy": (None, [ctypes.c_void_p]),
     "sgp_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "sgp_version": (ctypes.c_char_p, []),
+    "sgp_pinned_alloc": (ctypes.c_int, [ctypes.c_size_t, c_void_pp]),
+    "sgp_pinned_free": (None, [ctypes.c_void_p]),
     "sgp_set_kernel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_double_p]),
     "sgp_set_inducing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p]),
     "sgp_set_data": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),

@@ -89,6 +89,13 @@ extern "C" {
 
 const char* sgp_version(void) { return "libsgp 0.1 sm_100a"; }
 
+int sgp_pinned_alloc(size_t bytes, void** ptr) {
+    if (!ptr || bytes == 0) return SGP_ERR_ARG;
+    *ptr = nullptr;
+    return cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) == cudaSuccess ? SGP_OK : SGP_ERR_CUDA;
+}
+void sgp_pinned_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
 const char* sgp_last_error(const sgp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int sgp_create(sgp_ctx** out, int device_id) {
@@ -184,15 +191,20 @@ int sgp_set_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, c
     int rc = alloc_data(ctx, N > 0 ? N : 32); if (rc) return rc;
     const int D = ctx->D;
     const size_t cap = (size_t)ctx->Ncap;
-    SGP_CUDA(ctx, cudaMemsetAsync(ctx->X_dev, 0, cap * D * sizeof(double), ctx->stream));
-    SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, cap * sizeof(double), ctx->stream));
-    SGP_CUDA(ctx, cudaMemsetAsync(ctx->yv_dev, 0, cap * sizeof(double), ctx->stream));
-    SGP_CUDA(ctx, cudaMemsetAsync(ctx->w_dev, 0, cap * sizeof(double), ctx->stream));
-    if (N > 0) {
-        SGP_CUDA(ctx, cudaMemcpyAsync(ctx->X_dev, X, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        if (ybar) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->y_dev, ybar, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        if (yvar) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->yv_dev, yvar, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        if (wts) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->w_dev, wts, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // the sweep stages whole chunks of 32 points: rows [N, cap) must hold finite values (they generate exact zeros)
+    const size_t n = (size_t)N, tail = cap - n;
+    if (tail) SGP_CUDA(ctx, cudaMemsetAsync(ctx->X_dev + n * D, 0, tail * D * sizeof(double), ctx->stream));
+    if (n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->X_dev, X, n * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (ybar && n) {
+        SGP_CUDA(ctx, cudaMemcpyAsync(ctx->y_dev, ybar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (tail) SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev + n, 0, tail * sizeof(double), ctx->stream));
+    } else {
+        SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, cap * sizeof(double), ctx->stream));
+    }
+    if (yvar && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->yv_dev, yvar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (wts && n) {
+        SGP_CUDA(ctx, cudaMemcpyAsync(ctx->w_dev, wts, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (tail) SGP_CUDA(ctx, cudaMemsetAsync(ctx->w_dev + n, 0, tail * sizeof(double), ctx->stream));
     }
     SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->N = N; ctx->have_yv = yvar != nullptr; ctx->have_w = wts != nullptr; ctx->have_stats = false;

@@ -27,6 +27,30 @@ def _f64(a, shape=None):
     return a
 
 
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            _lib.load().sgp_pinned_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, order="C"):
+    """Float64 NumPy array in page-locked host memory (sgp_pinned_alloc): H2D / D2H copies of such arrays run at full PCIe
+    speed.  The memory is released when the array (and every view of it) is garbage-collected."""
+    n = int(np.prod(shape))
+    ptr = ctypes.c_void_p()
+    rc = _lib.load().sgp_pinned_alloc(max(n, 1) * 8, ctypes.byref(ptr))
+    if rc != 0:
+        raise SGPError(rc, "sgp_pinned_alloc failed")
+    buf = (ctypes.c_double * max(n, 1)).from_address(ptr.value)
+    buf._owner = _PinnedOwner(ptr)          # keeps the allocation alive as long as the ctypes buffer is referenced
+    return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order=order)
+
+
 class SGPContext:
     """Owns one ``sgp_ctx``.  Layout notes: the C ABI takes Julia's column-major D x N; a C-contiguous NumPy array of
     shape (N, D) is the same memory, so inputs here are (N, D) / (M, D) row-per-point arrays.  M x M results come back
@@ -88,14 +112,19 @@ class SGPContext:
         self.N = int(N)
 
     # ---- sweep ----
-    def sweep_psi(self, fetch=True):
+    def sweep_psi(self, fetch=True, out=None):
+        """`out` = (psi1, psi2) preallocated arrays (e.g. pinned_empty) to receive the results."""
         M = self.M
         if not fetch:
             self._ck(self.lib.sgp_sweep_psi(self.h, None, None, None, None))
             return None
         psi0, sy2 = ctypes.c_double(), ctypes.c_double()
-        psi1 = np.empty(M)
-        psi2 = np.empty((M, M), order="F")
+        if out is not None:
+            psi1, psi2 = out
+            assert psi1.size == M and psi2.shape == (M, M) and psi2.flags.f_contiguous and psi1.dtype == psi2.dtype == np.float64
+        else:
+            psi1 = np.empty(M)
+            psi2 = np.empty((M, M), order="F")
         self._ck(self.lib.sgp_sweep_psi(self.h, ctypes.byref(psi0), _p(psi1), _p(psi2), ctypes.byref(sy2)))
         return psi0.value, psi1, psi2, sy2.value
 

@@ -19,6 +19,7 @@
 #ifndef SGP_H
 #define SGP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -49,6 +50,12 @@ void sgp_destroy(sgp_ctx* ctx);
 const char* sgp_last_error(const sgp_ctx* ctx);
 /* library build string: "libsgp <version> sm_100a" */
 const char* sgp_version(void);
+
+/* Page-locked host memory for the arrays that cross the boundary every sweep (X, ybar, the Psi outputs): copies from / to
+ * such buffers run at full PCIe speed and without a staging copy.  Any other host memory is accepted everywhere too.
+ * (Julia: wrap with unsafe_wrap(Array, Ptr{Float64}(p), dims); free after the last use.) */
+int sgp_pinned_alloc(size_t bytes, void** ptr);
+void sgp_pinned_free(void* ptr);
 
 /* ---- model state (what UniSGPMeta / MultiSGPMeta carry: helper_functions/gp_helperfunction.jl:33-73) ------ */
 /* kernel(theta) of the meta, already transformed by the host (softplus etc.): variance sigma^2, lengthscale[D]. */

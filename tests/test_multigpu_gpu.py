@@ -1,0 +1,54 @@
+"""Sharded sweep over two GPUs through the C ABI: N is cut into two slices, one process / sgp_ctx per GPU, the packed
+statistics are all-reduced with NCCL inside sgp_sweep_psi; every rank must hold the single-GPU result (tolerance: the
+summation order differs, relative Frobenius <= 1e-12).  Skipped on boxes with one GPU."""
+import os
+import socket
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from gaussianprocessnode_b200 import SGPContext, shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # host plumbing only: carries the NCCL unique id
+    uid = [SGPContext.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    rng = np.random.default_rng(11)
+    N, D, M = 50_001, 8, 300
+    X = rng.normal(size=(N, D)); y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=N); yv = rng.uniform(0, 0.1, N)
+    Z = X[:M].copy(); ell = np.full(D, 2.0)
+    ctx = SGPContext(rank); ctx.set_kernel(1.2, ell); ctx.set_inducing(Z)
+    sw = shard.ShardedSweep(ctx, world, rank, uid[0])
+    sw.set_data(X, y, yv)
+    p0, p1, p2, sy = sw.sweep_psi()
+    ctx.close()
+    single = SGPContext(rank); single.set_kernel(1.2, ell); single.set_inducing(Z); single.set_data(X, y, yv)
+    f0, f1, f2, fy = single.sweep_psi(); single.close()
+    out[rank] = (float(np.linalg.norm(p2 - f2) / np.linalg.norm(f2)), float(np.linalg.norm(p1 - f1) / np.linalg.norm(f1)),
+                 float(abs(p0 - f0) / abs(f0)), float(abs(sy - fy) / abs(fy)))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_sweep_matches_single_gpu():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        res = dict(out)
+    assert set(res) == {0, 1}
+    for r in res.values():
+        assert max(r) <= 1e-12, res
