@@ -139,7 +139,7 @@ struct SmemPtrs {
 
 // One segment: tile (I, J), chunks [c_begin, c_begin + nchunks) of the N range.  `g` = chunks this CTA has already
 // pushed through the pipeline (selects stage / record / tile buffers and the mbarrier parity).
-template <int TM, int NB, int DPAD, int NT, bool WEIGHTED, bool DIAG>
+template <int TM, int NB, int DPAD, int NT, int KIND, bool WEIGHTED, bool DIAG>
 __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs& sm, const int I, const int J, const long long c_begin,
                                             const int nchunks, const unsigned g, const int slot) {
     using S = Smem<TM, NB, DPAD>;
@@ -154,7 +154,9 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     constexpr int KQ = (DPAD + 3) / 4;               // DMMA k-quarters of the dot product x~ . z~
     constexpr int NPB = 4 / RB;                      // 8-point blocks per generator unit
     constexpr int KSPAN = KS / RB;                   // k-steps one generator unit is spread over
-    constexpr int NST = KQ + 8;                      // stages of a generator unit
+    constexpr int NMAT = (KIND == SGP_KERNEL_SE) ? 0 : 3;   // extra stages of the Matern kernels: r^2 -> sqrt -> exponent
+    constexpr int NST = KQ + 8 + NMAT;               // stages of a generator unit
+    constexpr int E0 = KQ + 1 + NMAT;                // first stage of the exp
     static_assert(RB == 1 || RB == 2 || RB == 4, "generator mapping");
     static_assert(NB == 32, "generator schedule");
 
@@ -212,7 +214,7 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
             sm.zrec[r * ZR + d] = v;
             a = fma(v, v, a);
         }
-        sm.zbias[r] = (gm < p.M) ? (p.log_var_s - 0.5 * a) : -1.0e300;
+        sm.zbias[r] = (gm < p.M) ? ((KIND == SGP_KERNEL_SE ? p.log_var_s : 0.0) - 0.5 * a) : -1.0e300;
     }
     if (tid == 0)
         for (int c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
@@ -243,7 +245,7 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) psi1_acc[rb][0] = psi1_acc[rb][1] = 0.0;
 
-    struct Unit { double t[8], q[8], xa[NPB][KQ]; int n[8]; };
+    struct Unit { double t[8], q[8], u[NMAT ? 8 : 1], xa[NPB][KQ]; int n[8]; };
     auto gen_stage = [&](auto st_tag, Unit& u, const double* __restrict__ rn, double* __restrict__ Kn, const int ui) {
         constexpr int st = decltype(st_tag)::value;
         const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
@@ -266,10 +268,21 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
         } else if constexpr (st <= KQ) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) dmma884_nv(u.t[2 * q], u.t[2 * q + 1], u.xa[q / RB][st - 1], zf[q % RB][st - 1]);
-        } else if constexpr (st == KQ + 1) {
+        } else if constexpr (NMAT > 0 && st == KQ + 1) {
+            // Matern: the accumulated exponent is -(s/2) r^2 (r = |(x - z)/ell|);  u^2 = nu' r^2, nu' = 3 or 5
+            const double f = (KIND == SGP_KERNEL_MATERN32 ? -6.0 : -10.0) / SGP_EXP_SCALE;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u.q[c] = fmax(u.t[c] * f, 0.0);
+        } else if constexpr (NMAT > 0 && st == KQ + 2) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u.u[c] = sqrt(u.q[c]);
+        } else if constexpr (NMAT > 0 && st == KQ + 3) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u.t[c] = fma(u.u[c], -SGP_EXP_SCALE, p.log_var_s);     // s (ln sigma^2 - u)
+        } else if constexpr (st == E0) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) u.q[c] = u.t[c] + MAGIC;
-        } else if constexpr (st == KQ + 2) {
+        } else if constexpr (st == E0 + 1) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 // t < -2.0e6 (result below exp(-677): flushed to zero) <=> sign set and magnitude above: compare the high
@@ -279,16 +292,16 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
                 u.n[c] = tiny ? (int)0x80000000 : nn;
                 u.q[c] = u.q[c] - MAGIC;
             }
-        } else if constexpr (st == KQ + 3) {
+        } else if constexpr (st == E0 + 2) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) u.t[c] = u.t[c] - u.q[c];          // r
-        } else if constexpr (st == KQ + 4) {
+        } else if constexpr (st == E0 + 3) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) u.q[c] = fma(u.t[c], C3, C2);
-        } else if constexpr (st == KQ + 5) {
+        } else if constexpr (st == E0 + 4) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) u.q[c] = fma(u.q[c], u.t[c], C1);
-        } else if constexpr (st == KQ + 6) {
+        } else if constexpr (st == E0 + 5) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) u.q[c] = u.q[c] * u.t[c];
         } else {
@@ -301,6 +314,8 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
                 const int hi = __double2hiint(res[c]) + ((u.n[c] >> 11) << 20);
                 res[c] = __hiloint2double(hi, __double2loint(res[c]));
                 if (u.n[c] == (int)0x80000000) res[c] = 0.0;
+                if (KIND == SGP_KERNEL_MATERN32) res[c] = fma(res[c], u.u[c], res[c]);                               // (1 + u) e^-u
+                if (KIND == SGP_KERNEL_MATERN52) res[c] *= fma(u.u[c], fma(u.u[c], 1.0 / 3.0, 1.0), 1.0);           // (1 + u + u^2/3) e^-u
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -587,7 +602,7 @@ __device__ __forceinline__ void reduce_items(const SweepParams& p, double* __res
     }
 }
 
-template <int TM, int NB, int DPAD, int NT, bool WEIGHTED>
+template <int TM, int NB, int DPAD, int NT, int KIND, bool WEIGHTED>
 __global__ void __launch_bounds__(NT, 1) sweep_kernel(const __grid_constant__ SweepParams p) {
     using S = Smem<TM, NB, DPAD>;
     extern __shared__ __align__(128) double smem[];
@@ -616,8 +631,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const __grid_constant__ Sw
         seg_range(p0, p1, pre, wt, p.chunks, lo, hi);
         if (lo < hi) {
             const int n = (int)(hi - lo);
-            if (diag) run_segment<TM, NB, DPAD, NT, WEIGHTED, true>(p, sm, I, J, lo, n, g, bcta + t);
-            else run_segment<TM, NB, DPAD, NT, WEIGHTED, false>(p, sm, I, J, lo, n, g, bcta + t);
+            if (diag) run_segment<TM, NB, DPAD, NT, KIND, WEIGHTED, true>(p, sm, I, J, lo, n, g, bcta + t);
+            else run_segment<TM, NB, DPAD, NT, KIND, WEIGHTED, false>(p, sm, I, J, lo, n, g, bcta + t);
             g += (unsigned)n;
         }
         pre += (long long)wt * p.chunks;
@@ -629,10 +644,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const __grid_constant__ Sw
     reduce_items<TM, NT>(p, sm.Kt, reinterpret_cast<int*>(sm.stage));
 }
 
-template <int TM, int NB, int DPAD, int NT>
+template <int TM, int NB, int DPAD, int NT, int KIND>
 int launch_t(sgp_ctx* ctx, const SweepParams& p, bool weighted, int grid) {
     using S = Smem<TM, NB, DPAD>;
-    auto kern = weighted ? sweep_kernel<TM, NB, DPAD, NT, true> : sweep_kernel<TM, NB, DPAD, NT, false>;
+    auto kern = weighted ? sweep_kernel<TM, NB, DPAD, NT, KIND, true> : sweep_kernel<TM, NB, DPAD, NT, KIND, false>;
     SGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
     void* args[] = {const_cast<SweepParams*>(&p)};
     SGP_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NT), args, S::bytes, ctx->stream));
@@ -641,13 +656,21 @@ int launch_t(sgp_ctx* ctx, const SweepParams& p, bool weighted, int grid) {
     return SGP_OK;
 }
 
-template <int TM, int NB, int NT>
+template <int TM, int NB, int NT, int KIND>
 int launch_d(sgp_ctx* ctx, const SweepParams& p, bool weighted, int grid, int dpad) {
     switch (dpad) {
-        case 2: return launch_t<TM, NB, 2, NT>(ctx, p, weighted, grid);
-        case 4: return launch_t<TM, NB, 4, NT>(ctx, p, weighted, grid);
-        case 8: return launch_t<TM, NB, 8, NT>(ctx, p, weighted, grid);
-        default: return launch_t<TM, NB, 16, NT>(ctx, p, weighted, grid);
+        case 4: return launch_t<TM, NB, 4, NT, KIND>(ctx, p, weighted, grid);
+        case 8: return launch_t<TM, NB, 8, NT, KIND>(ctx, p, weighted, grid);
+        default: return launch_t<TM, NB, 16, NT, KIND>(ctx, p, weighted, grid);
+    }
+}
+
+template <int TM, int NB, int NT>
+int launch_k(sgp_ctx* ctx, const SweepParams& p, bool weighted, int grid, int dpad, int kind) {
+    switch (kind) {
+        case SGP_KERNEL_SE: return launch_d<TM, NB, NT, SGP_KERNEL_SE>(ctx, p, weighted, grid, dpad);
+        case SGP_KERNEL_MATERN32: return launch_d<TM, NB, NT, SGP_KERNEL_MATERN32>(ctx, p, weighted, grid, dpad);
+        default: return launch_d<TM, NB, NT, SGP_KERNEL_MATERN52>(ctx, p, weighted, grid, dpad);
     }
 }
 
@@ -659,10 +682,9 @@ int sgp_sweep_chunk() { return 32; }
 int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const double* yv, const double* w, int64_t N, int64_t Ncap,
                      bool time_main) {
     if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: set_kernel and set_inducing first");
-    if (ctx->kind != SGP_KERNEL_SE) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "fused sweep: SE-ARD only in this build (Matern: next)");
     constexpr int NB = 32;
     const int M = ctx->M, D = ctx->D;
-    const int dpad = D <= 2 ? 2 : D <= 4 ? 4 : D <= 8 ? 8 : 16;
+    const int dpad = D <= 4 ? 4 : D <= 8 ? 8 : 16;
     const int TM = (M > 192) ? 128 : 64;
     const int nblk = (M + TM - 1) / TM;
     const int ntiles = nblk * (nblk + 1) / 2;
@@ -697,8 +719,8 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
 
     int launches = 0;
     if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (TM == 128) rc = launch_d<128, NB, 256>(ctx, p, w != nullptr, grid, dpad);
-    else rc = launch_d<64, NB, 256>(ctx, p, w != nullptr, grid, dpad);
+    if (TM == 128) rc = launch_k<128, NB, 256>(ctx, p, w != nullptr, grid, dpad, ctx->kind);
+    else rc = launch_k<64, NB, 256>(ctx, p, w != nullptr, grid, dpad, ctx->kind);
     if (rc) return rc;
     ++launches;
     if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));

@@ -101,6 +101,22 @@ def test_far_from_origin_inputs(ctx):
     _check(ctx, X, y, Z, 2.0, np.array([1.0, 2.0, 0.5]), tol=1e-9)
 
 
+@pytest.mark.parametrize("kind", [kernels.MATERN32, kernels.MATERN52])
+@pytest.mark.parametrize("N,D,M", [(2000, 8, 300), (333, 2, 64), (1000, 12, 130)])
+def test_matern_kernels_in_the_fused_sweep(ctx, kind, N, D, M):
+    # KernelFunctions convention r = |(x - z) ./ ell| (the reference only ever imports Matern52Kernel; extension):
+    # Matern-3/2 (1 + sqrt3 r) exp(-sqrt3 r), Matern-5/2 (1 + sqrt5 r + 5 r^2 / 3) exp(-sqrt5 r)
+    rng = np.random.default_rng(17 + N + kind)
+    X = rng.normal(size=(N, D)); Z = np.vstack([X[:M // 2], rng.normal(size=(M - M // 2, D))])   # r = 0 exactly for half of Z
+    y = rng.normal(size=N); w = rng.uniform(0.2, 2.0, N)
+    ell = 0.8 + rng.random(D) * 2.0
+    for wts in (None, w):
+        ctx.set_kernel(1.4, ell, D=D, kind=kind); ctx.set_inducing(Z); ctx.set_data(X, y, None, wts)
+        psi0, psi1, psi2, sy2 = ctx.sweep_psi()
+        o0, o1, o2, oy = batched.psi_stats_point(X, y, Z, 1.4, ell, kind=kind, weights=wts)
+        assert abs(psi0 - o0) <= TOL * abs(o0) and fro(psi1, o1) <= TOL and fro(psi2, o2) <= TOL, (fro(psi1, o1), fro(psi2, o2))
+
+
 def test_far_points_underflow_to_zero(ctx):
     X = np.array([[0.0], [1.0e3], [-5.0e4]]); Z = np.array([[0.0], [1.0]]); y = np.ones(3)
     _check(ctx, X, y, Z, 1.0, np.array([1.0]))
