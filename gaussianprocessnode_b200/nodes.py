@@ -295,3 +295,184 @@ def rule_out(q_in, q_v, q_w, q_theta, meta: UniSGPMeta):
     if X.shape[0] == 1 and x.ndim <= 1:
         return NormalMeanPrecision(float(m[0]), w)
     return [NormalMeanPrecision(float(v), w) for v in m]
+
+
+# ======================================================================================================================
+# Uncertain inputs: UniSGP with q(x) Gaussian (GPnode/UniSGPnode.jl:125-140) and the MultiSGP node
+# (GPnode/MultiSGPnode.jl, helper_functions/gp_helperfunction.jl:55-73)
+# ======================================================================================================================
+def _method_of(meta):
+    """meta.method: a libsgp method id or (id, p) for Gauss-Hermite of order p (the reference passes a ReactiveMP
+    approximation object: srcubature(), ghcubature(p), GenUnscented())."""
+    return meta.method if isinstance(meta.method, tuple) else (meta.method, 21)
+
+
+def rule_v_uncertain(q_out, q_in, q_w, q_theta, meta: UniSGPMeta):
+    """@rule UniSGP(:v, Marginalisation) (q_out, q_in::UnivariateGaussianDistributionsFamily, ...) -- UniSGPnode.jl:125-140.
+    Enqueues (m_n, v_n, E[y_n]); ``prod_uncertain`` materialises the sum on the N-th fold."""
+    _configure(meta, mean(q_theta))
+    m, v = mean_var(q_in)
+    mu_y, _ = mean_var(q_out)
+    meta._x.append((np.atleast_1d(np.asarray(m, dtype=np.float64)), np.atleast_2d(np.asarray(v, dtype=np.float64))))
+    meta._y.append(float(mu_y))
+    return BufferUniSGP((float(mean(q_w)), "uncertain"), meta)
+
+
+def prod_uncertain(left, right: BufferUniSGP):
+    """The N-th fold of the uncertain-input messages: one sgp_sweep_psi_uncertain over the N queued inputs.  Each of the
+    reference's per-node messages carries Psi2_n + 1e-8 I (UniSGPnode.jl:135), so the sum carries N * 1e-8 I."""
+    meta = right.meta
+    meta.counter += 1
+    if meta.counter != meta.N:
+        return left
+    ctx = _ctx(meta)
+    w = right.qv[0]
+    mid, p = _method_of(meta)
+    means = np.stack([x[0] for x in meta._x[:meta.N]]); covs = np.stack([x[1] for x in meta._x[:meta.N]])
+    y = np.array(meta._y[:meta.N])
+    meta._x.clear(); meta._y.clear(); meta._yv.clear()
+    psi0, psi1, psi2, _ = ctx.sweep_psi_uncertain(mid, means, covs, R=y[:, None], D_out=1, p=p)
+    psi1 = np.asarray(psi1).reshape(-1)
+    psi2 = psi2 + meta.N * 1e-8 * np.eye(psi2.shape[0])
+    meta.Psi0[...] = psi0; meta.Psi1_trans[:, 0] = psi1; meta.Psi2[...] = psi2
+    if isinstance(left, MvNormalWeightedMeanPrecision):
+        xi0, Lam0 = left.xi, left.Lam
+    else:
+        m0, S0 = mean_cov(left)
+        Lam0 = np.linalg.inv(S0); xi0 = Lam0 @ m0
+    meta.counter = 0
+    return MvNormalWeightedMeanPrecision(xi0 + w * psi1, Lam0 + w * psi2)
+
+
+@dataclass
+class MultiSGPMeta:
+    """helper_functions/gp_helperfunction.jl:55-64 -- same fields, same order (GPCache is scratch only and has no
+    counterpart) -- plus N (nodes sharing the meta), the library handle and the staging buffers."""
+    method: Any
+    Xu: np.ndarray
+    Psi0: np.ndarray
+    Psi1_trans: np.ndarray
+    Psi2: np.ndarray
+    Kuu_inverse: Any
+    kernel: Callable
+    N: int = 0
+    ctx: Optional[SGPContext] = None
+    _m: List = field(default_factory=list)
+    _P: List = field(default_factory=list)
+    _muy: List = field(default_factory=list)
+    _Sy: List = field(default_factory=list)
+    _count: int = 0
+    _theta_key: Any = None
+    _stats: Any = None
+
+
+def _multi_enqueue(meta, q_out, q_in):
+    m, P = mean_cov(q_in)
+    if isinstance(q_out, PointMass):
+        mu_y, S_y = np.asarray(q_out.value, dtype=np.float64), None
+    else:
+        mu_y, S_y = mean_cov(q_out)
+    meta._m.append(np.asarray(m, dtype=np.float64)); meta._P.append(np.asarray(P, dtype=np.float64))
+    meta._muy.append(np.asarray(mu_y, dtype=np.float64)); meta._Sy.append(S_y)
+    meta._count += 1
+    return meta._count == meta.N
+
+
+def _multi_flush(meta, want_psi1_n=False):
+    """One sgp_sweep_psi_uncertain over the N queued nodes: Psi0, P_Y = sum_n Psi1_n mu_y_n' (M x D), Psi2 (and Psi1_n)."""
+    ctx = _ctx(meta)
+    mid, p = _method_of(meta)
+    means = np.stack(meta._m[:meta.N]); covs = np.stack(meta._P[:meta.N]); Y = np.stack(meta._muy[:meta.N])
+    Sy = sum((np.zeros((Y.shape[1], Y.shape[1])) if s is None else s) for s in meta._Sy[:meta.N])
+    meta._m.clear(); meta._P.clear(); meta._muy.clear(); meta._Sy.clear(); meta._count = 0
+    psi0, PY, psi2, p1n = ctx.sweep_psi_uncertain(mid, means, covs, R=Y, D_out=Y.shape[1], p=p, want_psi1_n=want_psi1_n)
+    PY = np.asarray(PY).reshape(psi2.shape[0], Y.shape[1])
+    meta.Psi0[...] = psi0; meta.Psi2[...] = psi2
+    meta._stats = dict(psi0=psi0, PY=PY, psi2=psi2, Y=Y, Sy=Sy, psi1_n=p1n)
+    return meta._stats
+
+
+def multi_rule_v(q_out, q_in, q_w, q_theta, meta: MultiSGPMeta):
+    """@rule MultiSGP(:v, Marginalisation) -- MultiSGPnode.jl:290-308 (q_out Gaussian), :310-328 (PointMass).
+    Neutral (xi = 0, Lambda = 0) for the first N-1 nodes; on the N-th the sum of the N per-node messages:
+    Lambda = kron(W_bar, sum_n Psi2_n),  xi = vec(sum_n Psi1_n (W_bar mu_y_n)')  (output-major blocks of M)."""
+    _configure(meta, mean(q_theta))
+    W = np.asarray(mean(q_w), dtype=np.float64)
+    M = np.asarray(meta.Xu).shape[0]; D = W.shape[0]
+    if not _multi_enqueue(meta, q_out, q_in):
+        return MvNormalWeightedMeanPrecision(np.zeros(D * M), np.zeros((D * M, D * M)))
+    s = _multi_flush(meta)
+    return MvNormalWeightedMeanPrecision((s["PY"] @ W).ravel(order="F"), np.kron(W, s["psi2"]))
+
+
+def _kuu_inverse(meta):
+    """meta.Kuu_inverse = cholinv(Kuu + jitter I) (host side in the reference: Pendulum_Wishart_2d.ipynb:2542-2543)."""
+    if meta.Kuu_inverse is None or getattr(meta, "_kuu_key", None) != meta._theta_key:
+        ctx = _ctx(meta)
+        ctx.kuu_factor(getattr(meta, "kuu_jitter", 1e-12), fetch=False)
+        M = np.asarray(meta.Xu).shape[0]
+        meta.Kuu_inverse = ctx.kuu_solve(np.eye(M))
+        meta._kuu_key = meta._theta_key
+    return meta.Kuu_inverse
+
+
+def multi_rule_w(q_out, q_in, q_v, q_theta, meta: MultiSGPMeta):
+    """@rule MultiSGP(:w, Marginalisation) -- MultiSGPnode.jl:367-405, 407-444.  The reference returns
+    WishartFast(D+2, Psi_4,n) per node; their product has nu = N (D+2) - (N-1)(D+1) = N + D + 1 and inverse scale
+    sum_n Psi_4,n.  Neutral element WishartFast(D+1, 0) for the first N-1 nodes."""
+    _configure(meta, mean(q_theta))
+    mu_v, Sigma_v = mean_cov(q_v)
+    M = np.asarray(meta.Xu).shape[0]; D = mu_v.size // M
+    if not _multi_enqueue(meta, q_out, q_in):
+        return WishartFast(D + 1.0, np.zeros((D, D)))
+    N = meta.N
+    s = _multi_flush(meta)
+    Kinv = _kuu_inverse(meta)
+    Rv = Sigma_v + np.outer(mu_v, mu_v)
+    V = mu_v.reshape(D, M).T                                            # column d = mu_v^(d)
+    Psi4 = np.array([[np.sum(Rv[i * M:(i + 1) * M, j * M:(j + 1) * M] * s["psi2"].T) for j in range(D)] for i in range(D)])
+    A = s["PY"].T @ V                                                   # sum_n mu_y_n E_n',  E_n = V' Psi1_n
+    Ry = s["Y"].T @ s["Y"] + s["Sy"]
+    I1 = s["psi0"] - np.sum(Kinv * s["psi2"])                           # sum_n (Psi0_n - tr(Kuu^-1 Psi2_n))
+    return WishartFast(N + D + 1.0, Psi4 + Ry - (A + A.T) + I1 * np.eye(D))
+
+
+def multi_average_energy(q_out, q_in, q_v, q_w, q_theta, meta: MultiSGPMeta):
+    """@average_energy MultiSGP -- MultiSGPnode.jl:544-571, 574-602, 604-631: 0 for the first N-1 nodes, sum_n U_n on the
+    N-th.  q_w: Wishart (E[W] = nu S, E[ln|W|] = psi_D(nu/2) + D ln 2 + ln|S|) or PointMass."""
+    _configure(meta, mean(q_theta))
+    mu_v, Sigma_v = mean_cov(q_v)
+    M = np.asarray(meta.Xu).shape[0]; D = mu_v.size // M
+    if not _multi_enqueue(meta, q_out, q_in):
+        return 0.0
+    N = meta.N
+    s = _multi_flush(meta)
+    Kinv = _kuu_inverse(meta)
+    if isinstance(q_w, PointMass):
+        W = np.asarray(q_w.value, dtype=np.float64); ElogW = float(np.linalg.slogdet(W)[1])
+    else:
+        W = q_w.nu * q_w.S
+        ElogW = float(sum(digamma(0.5 * (q_w.nu - i)) for i in range(D)) + D * np.log(2.0) + np.linalg.slogdet(q_w.S)[1])
+    Rv = Sigma_v + np.outer(mu_v, mu_v)
+    V = mu_v.reshape(D, M).T
+    sumRvblk_W = sum(Rv[i * M:(i + 1) * M, j * M:(j + 1) * M] * W[i, j] for i in range(D) for j in range(D))
+    Ry = s["Y"].T @ s["Y"] + s["Sy"]
+    return float(N * (0.5 * D * LOG2PI - 0.5 * ElogW) + 0.5 * np.trace(W @ Ry)
+                 + 0.5 * np.trace(W) * (s["psi0"] - np.sum(Kinv * s["psi2"]))
+                 - np.trace(W @ V.T @ s["PY"]) + 0.5 * np.sum(s["psi2"] * sumRvblk_W))
+
+
+def multi_rule_out(q_ins, q_v, q_w, q_theta, meta: MultiSGPMeta):
+    """@rule MultiSGP(:out, Marginalisation) -- MultiSGPnode.jl:90-104, 106-120 -- for a whole set of input marginals at
+    once: MvNormalMeanPrecision([Psi1_n' mu_v^(d)]_d, W_bar) per node."""
+    _configure(meta, mean(q_theta))
+    ctx = _ctx(meta)
+    mid, p = _method_of(meta)
+    mc = [mean_cov(q) for q in q_ins]
+    means = np.stack([np.asarray(m, dtype=np.float64) for m, _ in mc]); covs = np.stack([np.asarray(P, dtype=np.float64) for _, P in mc])
+    mu_v = np.asarray(mean(q_v), dtype=np.float64)
+    W = np.asarray(mean(q_w), dtype=np.float64)
+    M = np.asarray(meta.Xu).shape[0]; D = mu_v.size // M
+    _, _, _, p1n = ctx.sweep_psi_uncertain(mid, means, covs, p=p, want_psi1_n=True)
+    E = p1n @ mu_v.reshape(D, M).T                                      # N x D
+    return [MvNormalMeanPrecision(E[n], W) for n in range(E.shape[0])]
