@@ -117,6 +117,36 @@ def test_matern_kernels_in_the_fused_sweep(ctx, kind, N, D, M):
         assert abs(psi0 - o0) <= TOL * abs(o0) and fro(psi1, o1) <= TOL and fro(psi2, o2) <= TOL, (fro(psi1, o1), fro(psi2, o2))
 
 
+@pytest.mark.parametrize("N,D,M", [(3000, 4, 1500), (1500, 8, 2500)])
+def test_many_tiles_per_cta(ctx, N, D, M):
+    # M = 1500: 78 tiles on 148 CTAs; M = 2500: 210 tiles, i.e. more tiles than CTAs -- a CTA walks through several tiles
+    rng = np.random.default_rng(M)
+    X = rng.normal(size=(N, D)); Z = rng.normal(size=(M, D)) * 1.5; y = rng.normal(size=N)
+    _check(ctx, X, y, Z, 0.9, np.full(D, 1.8))
+
+
+def test_pinned_buffers_and_segment_clocks(ctx):
+    from gaussianprocessnode_b200 import pinned_empty
+    rng = np.random.default_rng(21)
+    N, D, M = 5000, 8, 256
+    X = pinned_empty((N, D)); X[...] = rng.normal(size=(N, D))
+    y = pinned_empty((N,)); y[...] = rng.normal(size=N)
+    Z = np.array(X[:M])
+    psi1 = pinned_empty((M,)); psi2 = pinned_empty((M, M), order="F")
+    ctx.set_kernel(1.0, np.full(D, 2.0)); ctx.set_inducing(Z); ctx.set_data(X, y)
+    ctx.sweep_debug_clocks()                                   # switches the per-segment clock recording on
+    p0, p1, p2, sy = ctx.sweep_psi(out=(psi1, psi2))
+    assert p1 is psi1 and p2 is psi2
+    o0, o1, o2, oy = batched.psi_stats_point(np.array(X), np.array(y), Z, 1.0, np.full(D, 2.0))
+    assert fro(psi2, o2) <= TOL and fro(psi1, o1) <= TOL
+    rec = ctx.sweep_debug_clocks()
+    rec = rec[rec[:, 0] >= 0]
+    ntiles = 3                                                 # M = 256 -> 2 x 2 blocks of 128 -> 3 lower-triangle tiles
+    assert len(rec) >= ntiles and rec[:, 1].min() > 0
+    chunks = (N + 31) // 32
+    assert rec[:, 0].sum() == chunks * ntiles                  # every (tile, chunk) pair is processed exactly once
+
+
 def test_far_points_underflow_to_zero(ctx):
     X = np.array([[0.0], [1.0e3], [-5.0e4]]); Z = np.array([[0.0], [1.0]]); y = np.ones(3)
     _check(ctx, X, y, Z, 1.0, np.array([1.0]))
