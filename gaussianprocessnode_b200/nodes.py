@@ -476,3 +476,35 @@ def multi_rule_out(q_ins, q_v, q_w, q_theta, meta: MultiSGPMeta):
     _, _, _, p1n = ctx.sweep_psi_uncertain(mid, means, covs, p=p, want_psi1_n=True)
     E = p1n @ mu_v.reshape(D, M).T                                      # N x D
     return [MvNormalMeanPrecision(E[n], W) for n in range(E.shape[0])]
+
+
+# ======================================================================================================================
+# Driver-side helpers of helper_functions/gp_helperfunction.jl:133-158 (host code; no GPU work)
+# ======================================================================================================================
+def create_blockmatrix(A, d, M):
+    """gp_helperfunction.jl:133-135: d x d grid of M x M views."""
+    return [[A[i * M:(i + 1) * M, j * M:(j + 1) * M] for j in range(d)] for i in range(d)]
+
+
+def split2batch(data, batch_size):
+    """gp_helperfunction.jl:137-142: consecutive mini-batches, the last one ragged."""
+    x, y = data
+    n = len(x)
+    return ([x[i:min(i + batch_size, n)] for i in range(0, n, batch_size)],
+            [y[i:min(i + batch_size, n)] for i in range(0, len(y), batch_size)])
+
+
+def SMSE(y_true, y_approx):
+    """gp_helperfunction.jl:145-149: mean squared error over var(y_true), Julia's var = n-1 normalisation."""
+    y_true = np.asarray(y_true, dtype=np.float64); y_approx = np.asarray(y_approx, dtype=np.float64)
+    return float(np.sum((y_true - y_approx) ** 2) / y_true.size / np.var(y_true, ddof=1))
+
+
+def num_error(ytrue, y):
+    """gp_helperfunction.jl:152-154."""
+    return float(np.sum(np.abs(np.asarray(y, dtype=np.float64) - np.asarray(ytrue, dtype=np.float64))))
+
+
+def error_rate(ytrue, y):
+    """gp_helperfunction.jl:156-158."""
+    return num_error(ytrue, y) / len(ytrue)

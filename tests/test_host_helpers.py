@@ -1,0 +1,38 @@
+"""Driver-side helpers mirrored from helper_functions/gp_helperfunction.jl (CPU only) against the golden chains."""
+import numpy as np
+
+from gaussianprocessnode_b200 import nodes as nd
+from oracle import batched, kernels
+
+
+def test_split2batch_matches_the_reference_slicing():
+    x = list(range(10)); y = list(range(100, 110))
+    xb, yb = nd.split2batch((x, y), 4)
+    assert xb == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]] and yb == [[100, 101, 102, 103], [104, 105, 106, 107], [108, 109]]
+    xb, _ = nd.split2batch((np.arange(10000), np.arange(10000)), 500)      # regression_kin40k.ipynb: 20 batches of 500
+    assert len(xb) == 20 and all(len(b) == 500 for b in xb)
+
+
+def test_smse_reproduces_the_kin40k_notebook_number(kin40k):
+    sp = kernels.softplus(kin40k["theta_raw"])
+    Z = kin40k["xtrain"][kin40k["xu_ids"]]
+    pred = batched.predict_mean(kin40k["xtest"], Z, sp[0], sp[1:], kin40k["mu_v"])
+    assert abs(nd.SMSE(kin40k["ytest"], pred) - 0.08343114079545057) < 1e-12       # regression_kin40k.ipynb:315
+    assert abs(nd.SMSE(kin40k["ytest"], pred) - batched.smse(kin40k["ytest"], pred)) < 1e-15
+
+
+def test_error_rate_reproduces_the_banana_notebook_number(banana):
+    sp = kernels.softplus(banana["theta_raw"])
+    x, lab = banana["x"], banana["label"]
+    Z = x[:4000][banana["xu_ids"]]
+    xt, yt = x[4000:5300], (lab[4000:5300] > 0).astype(float)                       # -1 -> 0 (classification_banana.ipynb:66-73)
+    m = batched.predict_mean(xt, Z, sp[0], sp[1:], banana["mu_v"])
+    yhat = (m > 0).astype(float)
+    assert nd.num_error(yt, yhat) == 125.0                                           # classification_banana.ipynb:316-317
+    assert abs(nd.error_rate(yt, yhat) - 0.09615384615384616) < 1e-15
+
+
+def test_create_blockmatrix_views():
+    A = np.arange(36.0).reshape(6, 6)
+    blk = nd.create_blockmatrix(A, 2, 3)
+    assert np.array_equal(blk[1][0], A[3:6, 0:3]) and np.shares_memory(blk[0][1], A)
