@@ -5,3 +5,4 @@ binding of that ABI (``_lib`` / ``sgp``) and the host-side mirror of the referen
 from .sgp import SGPContext, SGPError, pinned_empty, SE, MATERN32, MATERN52, SRCUBATURE, GENUT, GAUSSHERMITE, CLOSED_FORM_SE  # noqa: F401
 from . import nodes  # noqa: F401
 from . import shard  # noqa: F401
+from . import theta  # noqa: F401

@@ -1,0 +1,240 @@
+// The theta step's collapsed objective and its exact gradient.
+//
+// Replaces `neg_log_backwardmess_fast` + `ForwardDiff.gradient!` (helper_functions/derivative_helper.jl:23-39, 55-67; called
+// once per mini-batch in experiments/regression_kin40k.ipynb:214-222), where a per-point loop does `Lu \ k_n`, `Uv * k_n`
+// in dual-number arithmetic:
+//     F(theta) = sum_n [ w/2 k_nn - w/2 |L_u^-1 k_n|^2 + w/2 |U_v k_n|^2 - w y_n v' k_n ]
+//              = w/2 [ Psi0 - <K_uu^-1, Psi2> + <R_v, Psi2> ] - w v' Psi1,          R_v = U_v' U_v
+// The value comes from the statistics of the fused sweep.  The gradient is analytic (what forward-mode AD evaluates, in closed
+// form): with A = R_v - K_uu^-1, B = K_uu^-1 Psi2 K_uu^-1, and d k(x,z) / d ell_d = h(r) (x_d - z_d)^2 / ell_d^3
+// (h = k for SE, sigma^2 3 e^{-sqrt3 r} for Matern-3/2, sigma^2 5/3 (1 + sqrt5 r) e^{-sqrt5 r} for Matern-5/2),
+//     dF/d ell_d = [ sum_n sum_m h_nm c_nmd (w (A k_n)_m - w y_n v_m) + w/2 sum_mm' B_mm' h_mm' c_mm'd ] / ell_d^3
+//     dF/d sigma^2 = [ w/2 Psi0 - w/2 <K_uu^-1, Psi2> + w <R_v, Psi2> - w v' Psi1 - w/2 jitter tr B ] / sigma^2
+// A k_n for a chunk of points is one DMMA GEMM against the materialised K_uf chunk; the contraction is an FP64-ALU-bound
+// elementwise pass with fixed-order partial sums (deterministic).  All M x M algebra reuses dense.cu.
+#include "sgp_internal.cuh"
+#include <cmath>
+#include <algorithm>
+#include <vector>
+
+int sgp_gemm(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+             double beta, double* C, int ldc, int lower_only);
+
+namespace {
+
+struct KParams {
+    int kind, D, M;
+    double variance;
+    double ell_inv[SGP_MAX_D];
+};
+
+__device__ __forceinline__ double r2_of(const double* __restrict__ x, const double* __restrict__ z, const KParams& kp, double* c) {
+    double r2 = 0.0;
+    for (int d = 0; d < kp.D; ++d) {
+        const double t = x[d] - z[d];
+        c[d] = t * t;                                             // (x_d - z_d)^2, unscaled
+        r2 = fma(c[d], kp.ell_inv[d] * kp.ell_inv[d], r2);
+    }
+    return r2;
+}
+__device__ __forceinline__ double k_of(const KParams& kp, double r2) {
+    if (kp.kind == SGP_KERNEL_SE) return kp.variance * exp(-0.5 * r2);
+    const double s = sqrt((kp.kind == SGP_KERNEL_MATERN32 ? 3.0 : 5.0) * r2);
+    return kp.kind == SGP_KERNEL_MATERN32 ? kp.variance * (1.0 + s) * exp(-s) : kp.variance * (1.0 + s + s * s / 3.0) * exp(-s);
+}
+// d k / d ell_d = h * (x_d - z_d)^2 / ell_d^3
+__device__ __forceinline__ double h_of(const KParams& kp, double r2) {
+    if (kp.kind == SGP_KERNEL_SE) return kp.variance * exp(-0.5 * r2);
+    if (kp.kind == SGP_KERNEL_MATERN32) return kp.variance * 3.0 * exp(-sqrt(3.0 * r2));
+    const double s = sqrt(5.0 * r2);
+    return kp.variance * (5.0 / 3.0) * (1.0 + s) * exp(-s);
+}
+
+// K[m + j*M] = k(z_m, x_{n0+j})
+__global__ void kuf_chunk_kernel(const double* __restrict__ X, const double* __restrict__ Z, double* __restrict__ K, long long n0, int nc, KParams kp) {
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e >= (size_t)kp.M * nc) return;
+    const int m = (int)(e % kp.M); const long long j = (long long)(e / kp.M);
+    double c[SGP_MAX_D];
+    K[e] = k_of(kp, r2_of(X + (n0 + j) * kp.D, Z + (size_t)m * kp.D, kp, c));
+}
+
+// partial[block][d] = sum over the block's (m, j) of h_mj c_mjd (w G_mj - w y_j v_m)
+__global__ void __launch_bounds__(256) grad_contract_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ Z,
+                                                            const double* __restrict__ G, const double* __restrict__ v, double w, long long n0,
+                                                            int nc, KParams kp, double* __restrict__ partial) {
+    double acc[SGP_MAX_D];
+#pragma unroll
+    for (int d = 0; d < SGP_MAX_D; ++d) acc[d] = 0.0;
+    const size_t total = (size_t)kp.M * nc;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(e % kp.M); const long long j = (long long)(e / kp.M);
+        double c[SGP_MAX_D];
+        const double r2 = r2_of(X + (n0 + j) * kp.D, Z + (size_t)m * kp.D, kp, c);
+        const double f = h_of(kp, r2) * (w * G[e] - w * y[n0 + j] * v[m]);
+#pragma unroll
+        for (int d = 0; d < SGP_MAX_D; ++d)
+            if (d < kp.D) acc[d] = fma(f, c[d], acc[d]);
+    }
+    __shared__ double s[8][SGP_MAX_D];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < SGP_MAX_D; ++d) {
+        double a = acc[d];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) s[wp][d] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < SGP_MAX_D) {
+        double a = 0.0;
+        for (int q = 0; q < 8; ++q) a += s[q][threadIdx.x];
+        partial[(size_t)blockIdx.x * SGP_MAX_D + threadIdx.x] = a;
+    }
+}
+
+// partial[block][d] = sum over the block's (m, m') of B_mm' h_mm' c_mm'd   (K_uu part of the gradient)
+__global__ void __launch_bounds__(256) kuu_contract_kernel(const double* __restrict__ Z, const double* __restrict__ B, KParams kp, double* __restrict__ partial) {
+    double acc[SGP_MAX_D];
+#pragma unroll
+    for (int d = 0; d < SGP_MAX_D; ++d) acc[d] = 0.0;
+    const size_t total = (size_t)kp.M * kp.M;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(e % kp.M), m2 = (int)(e / kp.M);
+        double c[SGP_MAX_D];
+        const double r2 = r2_of(Z + (size_t)m * kp.D, Z + (size_t)m2 * kp.D, kp, c);
+        const double f = h_of(kp, r2) * B[e];
+#pragma unroll
+        for (int d = 0; d < SGP_MAX_D; ++d)
+            if (d < kp.D) acc[d] = fma(f, c[d], acc[d]);
+    }
+    __shared__ double s[8][SGP_MAX_D];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < SGP_MAX_D; ++d) {
+        double a = acc[d];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) s[wp][d] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < SGP_MAX_D) {
+        double a = 0.0;
+        for (int q = 0; q < 8; ++q) a += s[q][threadIdx.x];
+        partial[(size_t)blockIdx.x * SGP_MAX_D + threadIdx.x] = a;
+    }
+}
+
+// total[d] += scale * sum_b partial[b][d]   (one thread per d, fixed order)
+__global__ void finish_kernel(const double* __restrict__ partial, int nblocks, double scale, double* __restrict__ total) {
+    const int d = threadIdx.x;
+    if (d >= SGP_MAX_D) return;
+    double a = 0.0;
+    for (int b = 0; b < nblocks; ++b) a += partial[(size_t)b * SGP_MAX_D + d];
+    total[d] += scale * a;
+}
+
+__global__ void identity_kernel2(double* __restrict__ A, int M) {
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e < (size_t)M * M) A[e] = (e % M == e / M) ? 1.0 : 0.0;
+}
+__global__ void sub_kernel(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
+}
+// out[0] = sum_i a[i*sa] * (b ? b[i*sb] : 1)   single block, fixed order
+__global__ void dot_kernel2(const double* __restrict__ a, size_t sa, const double* __restrict__ b, size_t sb, size_t n, double* __restrict__ out) {
+    __shared__ double s[256];
+    double v = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += 256) v = fma(a[i * sa], b ? b[i * sb] : 1.0, v);
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+
+inline unsigned nb(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const double* Uv, double w, double jitter, double* value,
+                                   double* dvariance, double* dlengthscale) {
+    if (!ctx) return SGP_ERR_ARG;
+    if (!ctx->have_kernel || !ctx->have_Z || ctx->N <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: set_kernel, set_inducing and set_data first");
+    if (!mu_v || !Uv) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: mu_v and Uv are inputs");
+    if (ctx->have_w) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "theta_objective: per-point weights are not part of the reference objective");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const int M = ctx->M, D = ctx->D;
+    const size_t MM = (size_t)M * M;
+    const int64_t N = ctx->N;
+    const bool want_grad = dvariance != nullptr || dlengthscale != nullptr;
+
+    // local statistics of this rank's points (the objective is a sum over n: its D + 2 scalars are all-reduced at the end)
+    int rc = sgp_sweep_launch(ctx, ctx->X_dev, ctx->y_dev, nullptr, nullptr, N, ctx->Ncap, false); if (rc) return rc;
+    rc = sgp_kuu_factor(ctx, jitter, nullptr); if (rc) return rc;
+
+    const int nc_max = (int)std::min<int64_t>(N, std::max<int64_t>(1024, (int64_t)(16u << 20) / M));     // K and G chunks: 2 x 128 MB at most
+    const int cblocks = 4 * ctx->num_sms;
+    // scratch: [Kinv | Rv | A | B | T] (M x M each) | v (M) | res (64) | total (SGP_MAX_D) | K chunk | G chunk | block partials
+    size_t need = 5 * MM + (size_t)M + 64 + SGP_MAX_D + (want_grad ? 2 * (size_t)M * nc_max + (size_t)cblocks * SGP_MAX_D : 0);
+    rc = sgp_ensure(ctx, &ctx->theta_dev, &ctx->theta_cap, need); if (rc) return rc;
+    double* Kinv = ctx->theta_dev; double* Rv = Kinv + MM; double* A = Rv + MM; double* B = A + MM; double* T = B + MM;
+    double* vdev = T + MM; double* res = vdev + M; double* total = res + 64; double* Kc = total + SGP_MAX_D;
+    double* Gc = Kc + (size_t)M * nc_max; double* partial = Gc + (size_t)M * nc_max;
+    double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM; double* scal = psi1 + M;
+
+    // K_uu^-1
+    identity_kernel2<<<nb(MM), 256, 0, ctx->stream>>>(Kinv, M);
+    rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, Kinv, M, M, false); if (rc) return rc;
+    rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, Kinv, M, M, true); if (rc) return rc;
+    // R_v = Uv' Uv (T holds Uv), A = R_v - K_uu^-1
+    SGP_CUDA(ctx, cudaMemcpyAsync(T, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(vdev, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, T, M, T, M, 0.0, Rv, M, 0); if (rc) return rc;
+    sub_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, Rv, Kinv, MM);
+    // scalars: <Kinv, Psi2>, <Rv, Psi2>, v' Psi1
+    dot_kernel2<<<1, 256, 0, ctx->stream>>>(Kinv, 1, psi2, 1, MM, res + 0);
+    dot_kernel2<<<1, 256, 0, ctx->stream>>>(Rv, 1, psi2, 1, MM, res + 1);
+    dot_kernel2<<<1, 256, 0, ctx->stream>>>(vdev, 1, psi1, 1, (size_t)M, res + 2);
+    SGP_CUDA(ctx, cudaMemsetAsync(total, 0, SGP_MAX_D * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaMemsetAsync(res + 3, 0, sizeof(double), ctx->stream));
+
+    if (want_grad) {
+        KParams kp{}; kp.kind = ctx->kind; kp.D = D; kp.M = M; kp.variance = ctx->variance;
+        for (int d = 0; d < D; ++d) kp.ell_inv[d] = 1.0 / ctx->ell[d];
+        // B = Kinv Psi2 Kinv (T free again), tr B, K_uu part of the lengthscale gradient
+        rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, Kinv, M, psi2, M, 0.0, T, M, 0); if (rc) return rc;
+        rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, T, M, Kinv, M, 0.0, B, M, 0); if (rc) return rc;
+        dot_kernel2<<<1, 256, 0, ctx->stream>>>(B, (size_t)M + 1, nullptr, 0, (size_t)M, res + 3);
+        kuu_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->Z_dev, B, kp, partial);
+        finish_kernel<<<1, 32, 0, ctx->stream>>>(partial, cblocks, 0.5 * w, total);
+        // data part, chunk by chunk: K chunk -> G = A K -> contraction
+        for (int64_t n0 = 0; n0 < N; n0 += nc_max) {
+            const int nc = (int)std::min<int64_t>(nc_max, N - n0);
+            kuf_chunk_kernel<<<nb((size_t)M * nc), 256, 0, ctx->stream>>>(ctx->X_dev, ctx->Z_dev, Kc, n0, nc, kp);
+            rc = sgp_gemm(ctx, 0, 0, M, nc, M, 1.0, A, M, Kc, M, 0.0, Gc, M, 0); if (rc) return rc;
+            grad_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, vdev, w, n0, nc, kp, partial);
+            finish_kernel<<<1, 32, 0, ctx->stream>>>(partial, cblocks, 1.0, total);
+        }
+    }
+    SGP_CUDA(ctx, cudaGetLastError());
+    // [value, dvariance, dlengthscale[D]] as one small buffer so that a communicator can sum it over ranks
+    double h[4], sc[4], tot[SGP_MAX_D];
+    SGP_CUDA(ctx, cudaMemcpyAsync(h, res, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(sc, scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(tot, total, SGP_MAX_D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double out[2 + SGP_MAX_D];
+    out[0] = 0.5 * w * (sc[0] - h[0] + h[1]) - w * h[2];
+    out[1] = (0.5 * w * sc[0] - 0.5 * w * h[0] + w * h[1] - w * h[2] - 0.5 * w * jitter * h[3]) / ctx->variance;
+    for (int d = 0; d < D; ++d) out[2 + d] = tot[d] / (ctx->ell[d] * ctx->ell[d] * ctx->ell[d]);
+    if (ctx->comm) {
+        SGP_CUDA(ctx, cudaMemcpyAsync(res + 8, out, (2 + D) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        rc = sgp_comm_allreduce(ctx, res + 8, (size_t)(2 + D)); if (rc) return rc;
+        SGP_CUDA(ctx, cudaMemcpyAsync(out, res + 8, (2 + D) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (value) *value = out[0];
+    if (dvariance) *dvariance = out[1];
+    if (dlengthscale) for (int d = 0; d < D; ++d) dlengthscale[d] = out[2 + d];
+    ctx->have_stats = true;
+    return SGP_OK;
+}

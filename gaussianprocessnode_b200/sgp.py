@@ -199,6 +199,16 @@ class SGPContext:
         self._ck(self.lib.sgp_predict_mean(self.h, Xt.shape[0], _p(Xt), _p(mu_v), _p(out)))
         return out
 
+    def theta_objective(self, mu_v, Uv, w, jitter=0.0, grad=True):
+        """(F, dF/dvariance, dF/dlengthscale[D]) of the theta step on the resident data (sgp_theta_objective)."""
+        M = self.M
+        mu_v = _f64(mu_v, (M,))
+        Uv = np.asfortranarray(np.asarray(Uv, dtype=np.float64).reshape(M, M))
+        val = ctypes.c_double(); dv = ctypes.c_double(); dl = np.zeros(self.D)
+        self._ck(self.lib.sgp_theta_objective(self.h, _p(mu_v), _p(Uv), float(w), float(jitter), ctypes.byref(val),
+                                              ctypes.byref(dv) if grad else None, _p(dl) if grad else None))
+        return (val.value, dv.value, dl) if grad else val.value
+
     # ---- multi-GPU ----
     @staticmethod
     def comm_unique_id():

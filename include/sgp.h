@@ -111,6 +111,17 @@ int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI
 /* `@rule UniSGP(:out)` over a test set (GPnode/UniSGPnode.jl:96-104; regression_kin40k.ipynb:289-304): out = K_*u mu_v */
 int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* mu_v, double* out);
 
+/* ---- the theta step ---------------------------------------------------------- */
+/* Collapsed objective of the hyper-parameter step and its exact gradient on the resident data, at the kernel parameters
+ * currently set: replaces `neg_log_backwardmess_fast` + `ForwardDiff.gradient!`
+ * (helper_functions/derivative_helper.jl:23-39, 55-67; experiments/regression_kin40k.ipynb:214-222):
+ *   F = sum_n [ w/2 k_nn - w/2 |L_u^-1 k_n|^2 + w/2 |Uv k_n|^2 - w y_n mu_v' k_n ],   K_uu = L_u L_u' (+ jitter I)
+ * value = F, dvariance = dF/d sigma^2, dlengthscale[D] = dF/d ell_d (analytic; the host applies its own chain rule for the
+ * raw parameters, e.g. softplus').  mu_v (M) and Uv (M x M upper, column-major) are inputs.  Any output may be NULL; without
+ * gradient outputs only the value is computed.  With a communicator attached the D + 2 scalars are summed over ranks. */
+int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const double* Uv, double w, double jitter, double* value,
+                        double* dvariance, double* dlengthscale);
+
 /* ---- multi-GPU: N is sharded over ranks, one ctx per rank/GPU --------------------------------------------- */
 /* NCCL unique id (128 bytes) created on rank 0 and handed to the other ranks by the host. */
 int sgp_comm_unique_id(char id[128]);
