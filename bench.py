@@ -284,6 +284,33 @@ def main():
             "clocks": clk2.summary()}
         del Xd, yd
 
+    # ------------------------------------------------------------------ theta step, N = 1 only
+    if world == 1:
+        try:
+            cfg = KIN
+            nb_ = 500                                   # the reference calls the gradient once per mini-batch of 500
+            Xb, yb = synth(cfg, nb_, 11); Zb = inducing(cfg); ellb = np.full(cfg["D"], cfg["ell"])
+            rngb = np.random.default_rng(5)
+            vb = rngb.standard_normal(cfg["M"]); Cb = rngb.standard_normal((cfg["M"], cfg["M"])) * 0.05
+            Uvb = np.linalg.cholesky(Cb @ Cb.T + 0.1 * np.eye(cfg["M"])).T
+            ctx.set_kernel(cfg["variance"], ellb); ctx.set_inducing(Zb); ctx.set_data(Xb, yb)
+            for _ in range(3):
+                ctx.theta_objective(vb, Uvb, 1.0e4, 1e-8)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                ctx.theta_objective(vb, Uvb, 1.0e4, 1e-8)
+            dt = (time.perf_counter() - t0) / 10
+            from oracle import theta as otheta
+            t0 = time.perf_counter(); otheta.neg_log_backwardmess_fast(cfg["variance"], ellb, yb, Xb, vb, Uvb, 1.0e4, Zb, 0, 1e-8)
+            dt_cpu = time.perf_counter() - t0
+            line["theta_step"] = {"workload": "objective + exact gradient of the theta step, one kin40k mini-batch: N=500, D=8, M=512 (host buffers in, "
+                                              "D+2 scalars out; sgp_theta_objective)", "ms_per_call": dt * 1e3,
+                                  "cpu_value_only_ms": dt_cpu * 1e3,
+                                  "cpu_kind": "oracle restatement of neg_log_backwardmess_fast (value only, 1 thread; the reference adds ForwardDiff: "
+                                              "3 chunked dual-number passes for 9 parameters)"}
+        except Exception as e:  # pragma: no cover
+            line["theta_step"] = {"error": str(e)}
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1:
         rate, secs = cpu_port_rate(KIN, KIN["N"], native=True, reps=5)
