@@ -131,7 +131,8 @@ void sgp_destroy(sgp_ctx* ctx) {
     if (ctx->own_data) { cudaFree(ctx->X_dev); cudaFree(ctx->y_dev); cudaFree(ctx->yv_dev); cudaFree(ctx->w_dev); }
     cudaFree(ctx->Z_dev); cudaFree(ctx->stats_dev); cudaFree(ctx->work_dev); cudaFree(ctx->zrec_dev); cudaFree(ctx->exptab_dev);
     cudaFree(ctx->dense_dev); cudaFree(ctx->info_dev); cudaFree(ctx->KuuL_dev); cudaFree(ctx->sp_X_dev); cudaFree(ctx->sp_w_dev);
-    cudaFree(ctx->sp_y_dev); cudaFree(ctx->sweep_dbg_dev); cudaFree(ctx->theta_dev);
+    cudaFree(ctx->sp_y_dev); cudaFree(ctx->sweep_dbg_dev); cudaFree(ctx->theta_dev); cudaFree(ctx->Kinv_dev); cudaFree(ctx->kuu_dinv_dev);
+    cudaFree(ctx->dinv_dev);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -349,13 +350,25 @@ int sgp_kuu_factor(sgp_ctx* ctx, double jitter, double* L) {
     const int M = ctx->M;
     if (ctx->KuuL_M != M) {
         if (ctx->KuuL_dev) SGP_CUDA(ctx, cudaFree(ctx->KuuL_dev));
-        ctx->KuuL_dev = nullptr;
+        if (ctx->Kinv_dev) SGP_CUDA(ctx, cudaFree(ctx->Kinv_dev));
+        ctx->KuuL_dev = nullptr; ctx->Kinv_dev = nullptr;
         SGP_CUDA(ctx, cudaMalloc((void**)&ctx->KuuL_dev, (size_t)M * M * sizeof(double)));
+        SGP_CUDA(ctx, cudaMalloc((void**)&ctx->Kinv_dev, (size_t)M * M * sizeof(double)));
         ctx->KuuL_M = M;
     }
     ctx->have_kuu = false;
     int rc = sgp_kuu_build(ctx, ctx->KuuL_dev, jitter); if (rc) return rc;
     rc = sgp_potrf_lower(ctx, ctx->KuuL_dev, M); if (rc) return rc;
+    // keep the diagonal-block inverses (the next factorisation overwrites ctx->dinv_dev) and K_uu^-1 = L^-T L^-1, which the
+    // :w rule / energy / theta step contract with Psi2
+    const size_t nd = (size_t)((M + 63) / 64) * 64 * 64;
+    rc = sgp_ensure(ctx, &ctx->kuu_dinv_dev, &ctx->kuu_dinv_cap, nd); if (rc) return rc;
+    SGP_CUDA(ctx, cudaMemcpyAsync(ctx->kuu_dinv_dev, ctx->dinv_dev, nd * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+        const size_t MM = (size_t)M * M;
+        double* d = ctx->dense_dev + 64;                     // scratch: X = L^-1, Tmp
+        rc = sgp_trtri_lower(ctx, ctx->KuuL_dev, d, d + MM, ctx->Kinv_dev, M); if (rc) return rc;
+    }
     ctx->have_kuu = true;
     if (L) {
         SGP_CUDA(ctx, cudaMemcpyAsync(L, ctx->KuuL_dev, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -372,11 +385,12 @@ int sgp_kuu_solve(sgp_ctx* ctx, int nrhs, double* B) {
     const int M = ctx->M;
     double* tmp = nullptr;
     size_t bytes = (size_t)M * nrhs * sizeof(double);
-    SGP_CUDA(ctx, cudaMalloc((void**)&tmp, bytes));
+    SGP_CUDA(ctx, cudaMalloc((void**)&tmp, bytes + (size_t)64 * nrhs * sizeof(double)));
+    double* panel = tmp + (size_t)M * nrhs;
     int rc = SGP_OK;
     if (cudaMemcpyAsync(tmp, B, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
-    if (!rc) rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, tmp, M, nrhs, false);
-    if (!rc) rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, tmp, M, nrhs, true);
+    if (!rc) rc = sgp_trsm_lower_dinv(ctx, ctx->KuuL_dev, ctx->kuu_dinv_dev, tmp, panel, M, nrhs, false);
+    if (!rc) rc = sgp_trsm_lower_dinv(ctx, ctx->KuuL_dev, ctx->kuu_dinv_dev, tmp, panel, M, nrhs, true);
     if (!rc && cudaMemcpyAsync(B, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = SGP_ERR_CUDA;
     cudaFree(tmp);
@@ -399,9 +413,7 @@ int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, doub
     axpby_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(Lam, Lam, 1.0, psi2, w, MM);        // Lambda = Lambda0 + w Psi2
     axpby_kernel<<<nblocks(M), 256, 0, ctx->stream>>>(xi, xi, 1.0, psi1, w, M);            // xi = xi0 + w Psi1
     int rc = sgp_potrf_lower(ctx, Lam, M); if (rc) return rc;                               // Lambda = L L'
-    identity_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(X, M);
-    rc = sgp_trsm_lower(ctx, Lam, X, M, M, false); if (rc) return rc;                       // X = L^-1
-    rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, X, M, X, M, 0.0, Sig, M, 0); if (rc) return rc;  // Sigma = X' X
+    rc = sgp_trtri_lower(ctx, Lam, X, T, Sig, M); if (rc) return rc;                        // X = L^-1, Sigma = X' X
     rc = sgp_gemm(ctx, 0, 0, M, 1, M, 1.0, Sig, M, xi, M, 0.0, mu, M, 0); if (rc) return rc; // mu = Sigma xi
     if (Sigma_v) SGP_CUDA(ctx, cudaMemcpyAsync(Sigma_v, Sig, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (mu_v) SGP_CUDA(ctx, cudaMemcpyAsync(mu_v, mu, M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -428,14 +440,12 @@ int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI
     double* d = ctx->dense_dev + 64;
     double *A = d, *U = d + MM, *C = d + 2 * MM, *mu = d + 4 * MM, *res = mu + M;
     double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM; double* scal = psi1 + M;
-    SGP_CUDA(ctx, cudaMemcpyAsync(A, psi2, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     SGP_CUDA(ctx, cudaMemcpyAsync(U, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     SGP_CUDA(ctx, cudaMemcpyAsync(mu, mu_v, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, A, M, M, false); if (rc) return rc;       // L^-1 Psi2
-    rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, A, M, M, true); if (rc) return rc;            // K_uu^-1 Psi2
-    dot_kernel<<<1, 256, 0, ctx->stream>>>(A, (size_t)M + 1, nullptr, 0, (size_t)M, res);              // trace
+    int rc = SGP_OK;
+    rc = sgp_dot(ctx, ctx->Kinv_dev, 1, psi2, 1, MM, res); if (rc) return rc;                            // tr(K_uu^-1 Psi2) = <K_uu^-1, Psi2>
     rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, U, M, psi2, M, 0.0, C, M, 0); if (rc) return rc; // Uv Psi2
-    dot_kernel<<<1, 256, 0, ctx->stream>>>(C, 1, U, 1, MM, res + 1);                                   // <Uv Psi2, Uv>
+    rc = sgp_dot(ctx, C, 1, U, 1, MM, res + 1); if (rc) return rc;                                       // <Uv Psi2, Uv>
     dot_kernel<<<1, 256, 0, ctx->stream>>>(mu, 1, psi1, 1, (size_t)M, res + 2);                        // mu' Psi1
     double h[3], sc[4];
     SGP_CUDA(ctx, cudaMemcpyAsync(h, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

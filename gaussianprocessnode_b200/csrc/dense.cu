@@ -11,6 +11,7 @@
 // MultiSGP), i.e. latency-bound: the kernels are organised as few launches per 64-wide panel, not as a FLOP race.
 #include "sgp_internal.cuh"
 #include <cmath>
+#include <algorithm>
 
 namespace {
 
@@ -97,65 +98,8 @@ int gemm(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha, cons
     return SGP_OK;
 }
 
-// ---- Cholesky -----------------------------------------------------------------------------------------------------
-// Diagonal block (nb <= 64) factorised by one CTA in shared memory; info = first non-positive pivot (1-based) or 0.
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, int lda, int nb, int offset, int* info) {
-    __shared__ double S[PB][PB + 1];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < nb * nb; e += 256) { int r = e % nb, c = e / nb; S[r][c] = A[(size_t)r + (size_t)c * lda]; }
-    __syncthreads();
-    for (int j = 0; j < nb; ++j) {
-        double d = S[j][j];
-        if (!(d > 0.0)) {   // also catches NaN
-            if (tid == 0 && *info == 0) *info = offset + j + 1;
-            return;
-        }
-        double sd = sqrt(d);
-        __syncthreads();
-        if (tid == 0) S[j][j] = sd;
-        for (int r = j + 1 + tid; r < nb; r += 256) S[r][j] /= sd;
-        __syncthreads();
-        // trailing update of the remaining columns: S[r][c] -= S[r][j] * S[c][j]  (c > j, r >= c)
-        int rem = nb - j - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            int r = j + 1 + e % rem, c = j + 1 + e / rem;
-            if (r >= c) S[r][c] = fma(-S[r][j], S[c][j], S[r][c]);
-        }
-        __syncthreads();
-    }
-    for (int e = tid; e < nb * nb; e += 256) {
-        int r = e % nb, c = e / nb;
-        A[(size_t)r + (size_t)c * lda] = (r >= c) ? S[r][c] : 0.0;    // explicit zeros above the diagonal
-    }
-}
+// (the Cholesky itself lives in dense_coop.cu: one cooperative kernel per factorisation)
 
-// Panel below the diagonal block: X L_kk' = A  (row-wise forward substitution), one thread per row.
-__global__ void __launch_bounds__(64) potrf_panel_kernel(const double* Lkk, double* P, int lda, int nb, int rows, const int* info) {
-    if (*info != 0) return;
-    __shared__ double L[PB][PB + 1];
-    for (int e = threadIdx.x; e < nb * nb; e += 64) { int r = e % nb, c = e / nb; L[r][c] = Lkk[(size_t)r + (size_t)c * lda]; }
-    __syncthreads();
-    int r = blockIdx.x * 64 + threadIdx.x;
-    if (r >= rows) return;
-    double x[PB];
-#pragma unroll 1
-    for (int j = 0; j < nb; ++j) {
-        double v = P[(size_t)r + (size_t)j * lda];
-        for (int l = 0; l < j; ++l) v = fma(-x[l], L[j][l], v);
-        x[j] = v / L[j][j];
-    }
-    for (int j = 0; j < nb; ++j) P[(size_t)r + (size_t)j * lda] = x[j];
-}
-
-__global__ void zero_upper_kernel(double* A, int M) {
-    size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (e >= (size_t)M * M) return;
-    int r = (int)(e % M), c = (int)(e / M);
-    if (r < c) A[e] = 0.0;
-}
-
-// ---- triangular solves with many right-hand sides ---------------------------------------------------------------
-// Diagonal block solve: one thread per right-hand-side column.  trans = 0: L x = b (forward); 1: L' x = b (backward).
 __global__ void __launch_bounds__(64) trsm_diag_kernel(const double* Lkk, int ldl, double* B, int ldb, int nb, int nrhs, int trans) {
     __shared__ double L[PB][PB + 1];
     for (int e = threadIdx.x; e < nb * nb; e += 64) { int r = e % nb, c = e / nb; L[r][c] = Lkk[(size_t)r + (size_t)c * ldl]; }
@@ -197,39 +141,44 @@ __global__ void kuu_kernel(const double* __restrict__ Z, double* __restrict__ K,
     K[e] = v;
 }
 
+
+
+// out[0] = sum_i a[i*sa] * (b ? b[i*sb] : 1): block partials in a fixed order -> deterministic
+__global__ void __launch_bounds__(256) dot_partial_kernel(const double* __restrict__ a, size_t sa, const double* __restrict__ b, size_t sb, size_t n,
+                                                          double* __restrict__ partial) {
+    __shared__ double s[256];
+    double v0 = 0.0, v1 = 0.0;
+    const size_t per = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+    size_t i = lo + threadIdx.x;
+    for (; i + 256 < hi; i += 512) {
+        v0 = fma(a[i * sa], b ? b[i * sb] : 1.0, v0);
+        v1 = fma(a[(i + 256) * sa], b ? b[(i + 256) * sb] : 1.0, v1);
+    }
+    if (i < hi) v0 = fma(a[i * sa], b ? b[i * sb] : 1.0, v0);
+    s[threadIdx.x] = v0 + v1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+__global__ void dot_finish_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+    if (threadIdx.x == 0) { double v = 0.0; for (int i = 0; i < nb; ++i) v += partial[i]; out[0] = v; }
+}
+
 }  // namespace
+
+int sgp_dot(sgp_ctx* ctx, const double* a, size_t sa, const double* b, size_t sb, size_t n, double* out) {
+    const int nb = (int)std::min<size_t>(128, (n + 4095) / 4096);
+    double* partial = ctx->dense_dev + SGP_MAX_D;            // [SGP_MAX_D, 64) of the scratch header holds up to 32 block partials
+    const int nblk = nb > 32 ? 32 : (nb < 1 ? 1 : nb);
+    dot_partial_kernel<<<nblk, 256, 0, ctx->stream>>>(a, sa, b, sb, n, partial);
+    dot_finish_kernel<<<1, 32, 0, ctx->stream>>>(partial, nblk, out);
+    SGP_CUDA(ctx, cudaGetLastError());
+    return SGP_OK;
+}
 
 int sgp_gemm(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc, int lower_only) {
     return gemm(ctx, opA, opB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
-}
-
-// In-place lower Cholesky of the column-major M x M matrix A (upper triangle is zeroed).
-int sgp_potrf_lower(sgp_ctx* ctx, double* A, int M) {
-    SGP_CUDA(ctx, cudaMemsetAsync(ctx->info_dev, 0, sizeof(int), ctx->stream));
-    for (int k = 0; k < M; k += PB) {
-        int nb = M - k < PB ? M - k : PB;
-        double* Akk = A + (size_t)k + (size_t)k * M;
-        potrf_diag_kernel<<<1, 256, 0, ctx->stream>>>(Akk, M, nb, k, ctx->info_dev);
-        int rows = M - k - nb;
-        if (rows > 0) {
-            double* P = A + (size_t)(k + nb) + (size_t)k * M;
-            potrf_panel_kernel<<<(rows + 63) / 64, 64, 0, ctx->stream>>>(Akk, P, M, nb, rows, ctx->info_dev);
-            // trailing update (lower tiles only): A22 -= P P'
-            int rc = gemm(ctx, 0, 1, rows, rows, nb, -1.0, P, M, P, M, 1.0, A + (size_t)(k + nb) + (size_t)(k + nb) * M, M, 1);
-            if (rc) return rc;
-        }
-    }
-    zero_upper_kernel<<<(unsigned)(((size_t)M * M + 255) / 256), 256, 0, ctx->stream>>>(A, M);
-    int info = 0;
-    SGP_CUDA(ctx, cudaMemcpyAsync(&info, ctx->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (info != 0) {
-        char buf[128];
-        snprintf(buf, sizeof buf, "Cholesky: non-positive pivot at row %d of %d", info, M);
-        SGP_FAIL(ctx, SGP_ERR_NOT_PD, buf);
-    }
-    return SGP_OK;
 }
 
 // B (M x nrhs, ld M) <- L^{-1} B (trans = false) or L^{-T} B (trans = true); L lower, column-major, ld M.

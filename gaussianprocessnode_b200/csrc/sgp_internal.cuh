@@ -54,6 +54,9 @@ struct sgp_ctx {
 
     // K_uu factor
     double* KuuL_dev = nullptr; int KuuL_M = 0; bool have_kuu = false;
+    double* Kinv_dev = nullptr;                            // K_uu^-1 (full symmetric), refreshed by sgp_kuu_factor
+    double* kuu_dinv_dev = nullptr; size_t kuu_dinv_cap = 0; // inverses of the 64 x 64 diagonal blocks of KuuL
+    double* dinv_dev = nullptr; size_t dinv_cap = 0;       // ... of the factor produced by the last sgp_potrf_lower
 
     // uncertain-input scratch (sigma-point cloud)
     double *sp_X_dev = nullptr, *sp_w_dev = nullptr, *sp_y_dev = nullptr; size_t sp_cap = 0;
@@ -86,7 +89,11 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
 // dense.cu
 int sgp_potrf_lower(sgp_ctx* ctx, double* A, int M);                              // in place, column-major, lower
 int sgp_trsm_lower(sgp_ctx* ctx, const double* L, double* B, int M, int nrhs, bool trans);  // L X = B or L' X = B
+// dense_coop.cu
+int sgp_trsm_lower_dinv(sgp_ctx* ctx, const double* L, const double* dinv, double* B, double* tmp, int M, int nrhs, bool trans);
+int sgp_trtri_lower(sgp_ctx* ctx, const double* L, double* X, double* Tmp, double* S, int M);   // X = L^-1, S = X' X (optional)
 int sgp_kuu_build(sgp_ctx* ctx, double* K, double jitter);
+int sgp_dot(sgp_ctx* ctx, const double* a, size_t sa, const double* b, size_t sb, size_t n, double* out);   // deterministic
 // comm.cu
 int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count);
 void sgp_comm_destroy(sgp_ctx* ctx);

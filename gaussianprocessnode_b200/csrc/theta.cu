@@ -181,18 +181,16 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
     double* Gc = Kc + (size_t)M * nc_max; double* partial = Gc + (size_t)M * nc_max;
     double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM; double* scal = psi1 + M;
 
-    // K_uu^-1
-    identity_kernel2<<<nb(MM), 256, 0, ctx->stream>>>(Kinv, M);
-    rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, Kinv, M, M, false); if (rc) return rc;
-    rc = sgp_trsm_lower(ctx, ctx->KuuL_dev, Kinv, M, M, true); if (rc) return rc;
+    // K_uu^-1 (left by sgp_kuu_factor)
+    SGP_CUDA(ctx, cudaMemcpyAsync(Kinv, ctx->Kinv_dev, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     // R_v = Uv' Uv (T holds Uv), A = R_v - K_uu^-1
     SGP_CUDA(ctx, cudaMemcpyAsync(T, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     SGP_CUDA(ctx, cudaMemcpyAsync(vdev, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, T, M, T, M, 0.0, Rv, M, 0); if (rc) return rc;
     sub_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, Rv, Kinv, MM);
     // scalars: <Kinv, Psi2>, <Rv, Psi2>, v' Psi1
-    dot_kernel2<<<1, 256, 0, ctx->stream>>>(Kinv, 1, psi2, 1, MM, res + 0);
-    dot_kernel2<<<1, 256, 0, ctx->stream>>>(Rv, 1, psi2, 1, MM, res + 1);
+    rc = sgp_dot(ctx, Kinv, 1, psi2, 1, MM, res + 0); if (rc) return rc;
+    rc = sgp_dot(ctx, Rv, 1, psi2, 1, MM, res + 1); if (rc) return rc;
     dot_kernel2<<<1, 256, 0, ctx->stream>>>(vdev, 1, psi1, 1, (size_t)M, res + 2);
     SGP_CUDA(ctx, cudaMemsetAsync(total, 0, SGP_MAX_D * sizeof(double), ctx->stream));
     SGP_CUDA(ctx, cudaMemsetAsync(res + 3, 0, sizeof(double), ctx->stream));

@@ -174,13 +174,17 @@ class SGPContext:
         self._ck(self.lib.sgp_kuu_solve(self.h, B.shape[1], _p(B)))
         return B
 
-    def posterior_v(self, xi0, Lambda0, w, want_Uv=True):
+    def posterior_v(self, xi0, Lambda0, w, want_Uv=True, out=None):
+        """`out` = (mu, Sigma, Uv) preallocated Fortran-ordered arrays (e.g. pinned_empty) to receive the results."""
         M = self.M
         xi0 = _f64(xi0, (M,))
         Lam0 = np.asfortranarray(np.asarray(Lambda0, dtype=np.float64).reshape(M, M))
-        mu = np.empty(M)
-        Sigma = np.empty((M, M), order="F")
-        Uv = np.empty((M, M), order="F") if want_Uv else None
+        if out is not None:
+            mu, Sigma, Uv = out
+        else:
+            mu = np.empty(M)
+            Sigma = np.empty((M, M), order="F")
+            Uv = np.empty((M, M), order="F") if want_Uv else None
         self._ck(self.lib.sgp_posterior_v(self.h, _p(xi0), _p(Lam0), float(w), _p(mu), _p(Sigma), _p(Uv)))
         return mu, Sigma, Uv
 
