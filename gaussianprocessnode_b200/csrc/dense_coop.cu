@@ -99,8 +99,6 @@ __device__ void tile_store(const Acc& acc, double* __restrict__ C, int ldc, int 
 // sub-panels, each factorised with a thread per row (registers), followed by a rank-8 update of the trailing block.
 __device__ void factor_diag_block(double* __restrict__ A, int lda, int nb, int row0, double* __restrict__ Dinv, int* __restrict__ info, double* __restrict__ T) {
     constexpr int LD = TB + 1, SP = 8;
-    __shared__ double col[2][TB];
-    __shared__ double piv_s[2][2];
     __shared__ double rdiag[TB];
     const int tid = threadIdx.x;
     __syncthreads();
@@ -112,37 +110,34 @@ __device__ void factor_diag_block(double* __restrict__ A, int lda, int nb, int r
     }
     __syncthreads();
     for (int jb = 0; jb < TB; jb += SP) {
-        // (a) sub-panel: rows jb..63, columns jb..jb+7; thread r owns row r
-        const int r = tid;
-        double a[SP];
-        if (r < TB) {
+        // (a) sub-panel (rows jb..63, columns jb..jb+7) by warp 0 alone, warp-synchronously: lane owns rows lane and lane+32,
+        //     pivots and multipliers travel by shuffle -- no block barrier inside the 8 pivot steps
+        if (tid < 32) {
+            const int lane = tid, r0 = lane, r1 = lane + 32;
+            const bool hi = jb >= 32;                         // the sub-panel's diagonal rows live in the second half
+            double a0[SP], a1[SP];
 #pragma unroll
-            for (int t = 0; t < SP; ++t) a[t] = T[r * LD + jb + t];
-        }
+            for (int t = 0; t < SP; ++t) { a0[t] = T[r0 * LD + jb + t]; a1[t] = T[r1 * LD + jb + t]; }
 #pragma unroll
-        for (int jj = 0; jj < SP; ++jj) {
-            const int piv = jb + jj;
-            if (r == piv) {
-                double d = a[jj];
-                if (!(d > 0.0)) { if (piv < nb) atomicCAS(info, 0, row0 + piv + 1); d = 1.0; }
-                const double ri = rsqrt(d);
-                piv_s[jj & 1][0] = d * ri;                   // sqrt(d)
-                piv_s[jj & 1][1] = ri;
+            for (int jj = 0; jj < SP; ++jj) {
+                const int piv = jb + jj;
+                double d = __shfl_sync(0xffffffffu, hi ? a1[jj] : a0[jj], piv & 31);
+                if (!(d > 0.0)) { if (lane == 0 && piv < nb) atomicCAS(info, 0, row0 + piv + 1); d = 1.0; }
+                const double ri = rsqrt(d), sq = d * ri;
+                if (r0 > piv) a0[jj] *= ri; else if (r0 == piv) a0[jj] = sq;
+                if (r1 > piv) a1[jj] *= ri; else if (r1 == piv) a1[jj] = sq;
+#pragma unroll
+                for (int t = jj + 1; t < SP; ++t) {
+                    const double v = __shfl_sync(0xffffffffu, hi ? a1[jj] : a0[jj], (jb + t) & 31);     // L[jb+t][piv]
+                    if (r0 > piv) a0[t] = fma(-a0[jj], v, a0[t]);
+                    if (r1 > piv) a1[t] = fma(-a1[jj], v, a1[t]);
+                }
             }
-            __syncthreads();
-            if (r < TB && r >= piv) {
-                a[jj] = (r == piv) ? piv_s[jj & 1][0] : a[jj] * piv_s[jj & 1][1];
-                col[jj & 1][r] = a[jj];
-            }
-            __syncthreads();
-            if (r < TB && r > piv) {
 #pragma unroll
-                for (int t = jj + 1; t < SP; ++t) a[t] = fma(-a[jj], col[jj & 1][jb + t], a[t]);
+            for (int t = 0; t < SP; ++t) {
+                if (r0 >= jb) T[r0 * LD + jb + t] = a0[t];
+                if (r1 >= jb) T[r1 * LD + jb + t] = a1[t];
             }
-        }
-        if (r < TB && r >= jb) {
-#pragma unroll
-            for (int t = 0; t < SP; ++t) T[r * LD + jb + t] = a[t];
         }
         __syncthreads();
         // (b) trailing update: T[i][l] -= sum_t T[i][jb+t] T[l][jb+t] for jb+8 <= l <= i; thread = (row i, column group)
@@ -168,23 +163,26 @@ __device__ void factor_diag_block(double* __restrict__ A, int lda, int nb, int r
     }
     if (tid < TB) rdiag[tid] = 1.0 / T[tid * LD + tid];
     __syncthreads();
-    // inverse of the unit-padded 64 x 64 lower-triangular block: 4 lanes per column (rows i = q mod 4), axpy form
+    // inverse of the unit-padded 64 x 64 lower-triangular block: 4 lanes per column c (lane q owns rows i = q mod 4), axpy
+    // form over ALL 64 elimination steps with compile-time indices (steps l < c multiply zeros: no predicates, no divisions)
     {
         const int c = tid >> 2, q = tid & 3;
-        double x[TB / 4];                                   // rows q, q+4, ... (only rows >= c matter)
+        const int gbase = (tid & 31) & ~3;
+        const unsigned gmask = 0xfu << gbase;
+        double x[TB / 4];
 #pragma unroll
         for (int s = 0; s < TB / 4; ++s) x[s] = (4 * s + q == c) ? 1.0 : 0.0;
-        const unsigned gmask = 0xfu << ((tid & 31) & ~3);
-        for (int l = c; l < TB; ++l) {
-            // owner of row l finalises x_l and broadcasts it to its 4-lane group
-            double xl = 0.0;
 #pragma unroll
-            for (int s = 0; s < TB / 4; ++s) if (4 * s + q == l) { x[s] = x[s] * rdiag[l]; xl = x[s]; }
-            xl = __shfl_sync(gmask, xl, ((tid & 31) & ~3) | (l & 3));
+        for (int lb = 0; lb < TB / 4; ++lb) {
 #pragma unroll
-            for (int s = 0; s < TB / 4; ++s) {
-                const int i = 4 * s + q;
-                if (i > l) x[s] = fma(-T[i * LD + l], xl, x[s]);
+            for (int lq = 0; lq < 4; ++lq) {
+                const int l = 4 * lb + lq;
+                double xl = x[lb] * rdiag[l];
+                if (q == lq) x[lb] = xl;
+                xl = __shfl_sync(gmask, xl, gbase | lq);
+                if (q > lq) x[lb] = fma(-T[(4 * lb + q) * LD + l], xl, x[lb]);
+#pragma unroll
+                for (int s = lb + 1; s < TB / 4; ++s) x[s] = fma(-T[(4 * s + q) * LD + l], xl, x[s]);
             }
         }
 #pragma unroll

@@ -12,6 +12,7 @@
 #include "sgp_internal.cuh"
 #include <cmath>
 #include <vector>
+#include <algorithm>
 
 int sgp_gemm(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc, int lower_only);
@@ -262,6 +263,36 @@ __global__ void cf_finish_kernel(const double* __restrict__ partial, const doubl
     psi2[(size_t)b + (size_t)a * M] = v;
 }
 
+// Psi1 (M x D_out) = Psi1_n (M x N) R (N x D_out): the output is tiny and K = N is huge -> split N over blocks, one thread per
+// inducing row (coalesced), fixed-order finish (deterministic)
+template <int DO>
+__global__ void __launch_bounds__(128) psi1_split_kernel(const double* __restrict__ p1n, const double* __restrict__ R, double* __restrict__ partial,
+                                                         long long N, int M, int nsplit) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int split = blockIdx.y;
+    const long long n0 = N * split / nsplit, n1 = N * (split + 1) / nsplit;
+    double acc[DO];
+#pragma unroll
+    for (int d = 0; d < DO; ++d) acc[d] = 0.0;
+    if (m < M)
+        for (long long n = n0; n < n1; ++n) {
+            const double v = p1n[(size_t)m + (size_t)n * M];
+#pragma unroll
+            for (int d = 0; d < DO; ++d) acc[d] = fma(v, R[(size_t)n + (size_t)d * N], acc[d]);
+        }
+    if (m < M)
+#pragma unroll
+        for (int d = 0; d < DO; ++d) partial[((size_t)split * DO + d) * M + m] = acc[d];
+}
+__global__ void psi1_finish_kernel(const double* __restrict__ partial, double* __restrict__ psi1, int M, int DO, int nsplit) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M * DO) return;
+    const int m = e % M, d = e / M;
+    double v = 0.0;
+    for (int s = 0; s < nsplit; ++s) v += partial[((size_t)s * DO + d) * M + m];
+    psi1[(size_t)m + (size_t)d * M] = v;
+}
+
 __global__ void set_scal_kernel(double* scal, double psi0, double n) { scal[0] = psi0; scal[1] = 0.0; scal[2] = n; scal[3] = n; }
 __global__ void copy4_kernel(double* dst, const double* src) { if (threadIdx.x < 4) dst[threadIdx.x] = src[threadIdx.x]; }
 
@@ -396,8 +427,25 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
             UC(cudaMemcpyAsync(R_d, ones.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             UC(cudaStreamSynchronize(ctx->stream));
         }
-        rc = sgp_gemm(ctx, 0, 0, M, D_out, (int)N, 1.0, p1n_d, M, R_d, (int)N, 0.0, s_psi1, M, 0);
-        if (rc) { cleanup(); return rc; }
+        if (D_out <= 4) {
+            const int nsplit = (int)std::max<long long>(1, std::min<long long>(512, N / 64));
+            double* part = nullptr;
+            UC(cudaMalloc((void**)&part, (size_t)nsplit * D_out * M * sizeof(double)));
+            dim3 g((M + 127) / 128, nsplit);
+            switch (D_out) {
+                case 1: psi1_split_kernel<1><<<g, 128, 0, ctx->stream>>>(p1n_d, R_d, part, N, M, nsplit); break;
+                case 2: psi1_split_kernel<2><<<g, 128, 0, ctx->stream>>>(p1n_d, R_d, part, N, M, nsplit); break;
+                case 3: psi1_split_kernel<3><<<g, 128, 0, ctx->stream>>>(p1n_d, R_d, part, N, M, nsplit); break;
+                default: psi1_split_kernel<4><<<g, 128, 0, ctx->stream>>>(p1n_d, R_d, part, N, M, nsplit); break;
+            }
+            psi1_finish_kernel<<<nb((size_t)M * D_out), 256, 0, ctx->stream>>>(part, s_psi1, M, D_out, nsplit);
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(part);
+            if (e != cudaSuccess) { ctx->err = std::string("psi1 reduction: ") + cudaGetErrorString(e); cleanup(); return SGP_ERR_CUDA; }
+        } else {
+            rc = sgp_gemm(ctx, 0, 0, M, D_out, (int)N, 1.0, p1n_d, M, R_d, (int)N, 0.0, s_psi1, M, 0);
+            if (rc) { cleanup(); return rc; }
+        }
     }
     int info = 0;
     UC(cudaMemcpyAsync(&info, ctx->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
