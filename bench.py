@@ -308,6 +308,27 @@ def main():
                                   "cpu_value_only_ms": dt_cpu * 1e3,
                                   "cpu_kind": "oracle restatement of neg_log_backwardmess_fast (value only, 1 thread; the reference adds ForwardDiff: "
                                               "3 chunked dual-number passes for 9 parameters)"}
+            # one full mini-batch step of the kin40k driver (regression_kin40k.ipynb:196-228), device-resident streaming:
+            # upload 500 points -> sweep -> posterior on the resident prior (becomes the next prior) -> theta objective + gradient
+            ctx.kuu_factor(0.0, fetch=False)
+            ctx.prior_set_isotropic(50.0)
+            def mb_step():
+                ctx.set_data(Xb, yb); ctx.sweep_psi(fetch=False)
+                ctx.posterior_v_stream(1.0e4, carry=True)
+                return ctx.theta_objective(None, None, 1.0e4, 0.0)
+            for _ in range(3):
+                mb_step()
+            ctx.prior_set_isotropic(50.0)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                mb_step()
+            torch.cuda.synchronize()
+            dt_mb = (time.perf_counter() - t0) / 20
+            line["minibatch_step"] = {"workload": "kin40k driver mini-batch (500 points, M=512): H2D of the batch, sweep, posterior on the resident "
+                                                  "streaming prior, theta objective + gradient; only D+2 scalars return to the host",
+                                      "ms_per_minibatch": dt_mb * 1e3, "points_per_s": 500 / dt_mb,
+                                      "reference": "~400 points/s end to end (3h30 for 500 epochs x 10000 points, regression_kin40k.ipynb:239; "
+                                                   "author's Mac, includes RxInfer scheduling)"}
         except Exception as e:  # pragma: no cover
             line["theta_step"] = {"error": str(e)}
 

@@ -31,6 +31,9 @@ SIGNATURES = {
     "sgp_kuu_factor": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_double_p]),
     "sgp_kuu_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p]),
     "sgp_posterior_v": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
+    "sgp_prior_set": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p]),
+    "sgp_prior_set_isotropic": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
+    "sgp_posterior_v_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
     "sgp_w_terms": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sgp_predict_mean": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p]),
     "sgp_theta_objective": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_double, ctypes.c_double, c_double_p, c_double_p, c_double_p]),

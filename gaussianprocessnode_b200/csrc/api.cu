@@ -132,7 +132,7 @@ void sgp_destroy(sgp_ctx* ctx) {
     cudaFree(ctx->Z_dev); cudaFree(ctx->stats_dev); cudaFree(ctx->work_dev); cudaFree(ctx->zrec_dev); cudaFree(ctx->exptab_dev);
     cudaFree(ctx->dense_dev); cudaFree(ctx->info_dev); cudaFree(ctx->KuuL_dev); cudaFree(ctx->sp_X_dev); cudaFree(ctx->sp_w_dev);
     cudaFree(ctx->sp_y_dev); cudaFree(ctx->sweep_dbg_dev); cudaFree(ctx->theta_dev); cudaFree(ctx->Kinv_dev); cudaFree(ctx->kuu_dinv_dev);
-    cudaFree(ctx->dinv_dev);
+    cudaFree(ctx->dinv_dev); cudaFree(ctx->post_dev);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -398,35 +398,112 @@ int sgp_kuu_solve(sgp_ctx* ctx, int nrhs, double* B) {
     return rc;
 }
 
+// resident prior / posterior of v: post_dev = [Lambda_prior (MM) | xi_prior (M) | mu (M) | Sigma (MM) | Uv (MM, upper)]
+static int ensure_post(sgp_ctx* ctx) {
+    const size_t M = (size_t)ctx->M, need = 3 * M * M + 2 * M;
+    if (ctx->post_M != ctx->M) { ctx->have_prior = ctx->have_post = false; ctx->post_M = ctx->M; }
+    return sgp_ensure(ctx, &ctx->post_dev, &ctx->post_cap, need);
+}
+static double* post_LamP(sgp_ctx* ctx) { return ctx->post_dev; }
+static double* post_xiP(sgp_ctx* ctx) { return ctx->post_dev + (size_t)ctx->M * ctx->M; }
+static double* post_mu(sgp_ctx* ctx) { return post_xiP(ctx) + ctx->M; }
+static double* post_Sig(sgp_ctx* ctx) { return post_mu(ctx) + ctx->M; }
+static double* post_Uv(sgp_ctx* ctx) { return post_Sig(ctx) + (size_t)ctx->M * ctx->M; }
+
+__global__ void isotropic_kernel(double* __restrict__ A, int M, double diag) {
+    size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e < (size_t)M * M) A[e] = (e % M == e / M) ? diag : 0.0;
+}
+
+// The N-th prod on the resident prior: Lambda = Lambda_p + w Psi2, xi = xi_p + w Psi1 -> Sigma, mu, Uv (resident).
+// carry: the posterior's natural parameters become the resident prior (the streaming schedule of regression_kin40k.ipynb:200-213).
+static int posterior_core(sgp_ctx* ctx, double w, bool carry, bool want_uv) {
+    const int M = ctx->M; const size_t MM = (size_t)M * M;
+    double* d = ctx->dense_dev + 64;
+    double *Lam = d, *X = d + MM, *T = d + 3 * MM, *xi = d + 4 * MM;
+    double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM;
+    double *mu = post_mu(ctx), *Sig = post_Sig(ctx), *U = post_Uv(ctx);
+    axpby_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(Lam, post_LamP(ctx), 1.0, psi2, w, MM);      // Lambda = Lambda0 + w Psi2
+    axpby_kernel<<<nblocks(M), 256, 0, ctx->stream>>>(xi, post_xiP(ctx), 1.0, psi1, w, M);          // xi = xi0 + w Psi1
+    if (carry) {
+        SGP_CUDA(ctx, cudaMemcpyAsync(post_LamP(ctx), Lam, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        SGP_CUDA(ctx, cudaMemcpyAsync(post_xiP(ctx), xi, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    int rc = sgp_potrf_lower(ctx, Lam, M); if (rc) return rc;                               // Lambda = L L'
+    rc = sgp_trtri_lower(ctx, Lam, X, T, Sig, M); if (rc) return rc;                        // X = L^-1, Sigma = X' X
+    rc = sgp_gemm(ctx, 0, 0, M, 1, M, 1.0, Sig, M, xi, M, 0.0, mu, M, 0); if (rc) return rc; // mu = Sigma xi
+    ctx->have_post = true; ctx->have_post_uv = false;
+    if (want_uv) {
+        axpby_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(X, Sig, 1.0, nullptr, 0.0, MM);  // R_v = Sigma + mu mu' (X is free again)
+        add_outer_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(X, mu, M);
+        rc = sgp_potrf_lower(ctx, X, M); if (rc) return rc;
+        dim3 tg((M + 31) / 32, (M + 31) / 32), tb(32, 8);
+        transpose_kernel<<<tg, tb, 0, ctx->stream>>>(X, U, M);                              // Uv = L_R'
+        ctx->have_post_uv = true;
+    }
+    SGP_CUDA(ctx, cudaGetLastError());
+    return SGP_OK;
+}
+
+static int posterior_fetch(sgp_ctx* ctx, double* mu_v, double* Sigma_v, double* Uv) {
+    const size_t M = (size_t)ctx->M, MM = M * M;
+    if (Sigma_v) SGP_CUDA(ctx, cudaMemcpyAsync(Sigma_v, post_Sig(ctx), MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mu_v) SGP_CUDA(ctx, cudaMemcpyAsync(mu_v, post_mu(ctx), M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Uv) SGP_CUDA(ctx, cudaMemcpyAsync(Uv, post_Uv(ctx), MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SGP_OK;
+}
+
+}  // extern "C"
+const double* sgp_resident_mu(sgp_ctx* ctx) { return (ctx->have_post && ctx->post_M == ctx->M) ? post_mu(ctx) : nullptr; }
+const double* sgp_resident_uv(sgp_ctx* ctx) { return (ctx->have_post && ctx->have_post_uv && ctx->post_M == ctx->M) ? post_Uv(ctx) : nullptr; }
+extern "C" {
+
+int sgp_prior_set(sgp_ctx* ctx, const double* xi0, const double* Lambda0) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_Z || !xi0 || !Lambda0) SGP_FAIL(ctx, SGP_ERR_ARG, "prior_set: set_inducing first; xi0 and Lambda0 required");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    int rc = ensure_post(ctx); if (rc) return rc;
+    const size_t M = (size_t)ctx->M;
+    SGP_CUDA(ctx, cudaMemcpyAsync(post_LamP(ctx), Lambda0, M * M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(post_xiP(ctx), xi0, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_prior = true;
+    return SGP_OK;
+}
+
+int sgp_prior_set_isotropic(sgp_ctx* ctx, double variance) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_Z || !(variance > 0.0)) SGP_FAIL(ctx, SGP_ERR_ARG, "prior_set_isotropic: set_inducing first; variance > 0");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    int rc = ensure_post(ctx); if (rc) return rc;
+    const int M = ctx->M;
+    isotropic_kernel<<<nblocks((size_t)M * M), 256, 0, ctx->stream>>>(post_LamP(ctx), M, 1.0 / variance);
+    SGP_CUDA(ctx, cudaMemsetAsync(post_xiP(ctx), 0, (size_t)M * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaGetLastError());
+    ctx->have_prior = true;
+    return SGP_OK;
+}
+
+int sgp_posterior_v_stream(sgp_ctx* ctx, double w, int carry, double* mu_v, double* Sigma_v, double* Uv) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v_stream: run a sweep first");
+    if (ctx->Dout != 1) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "posterior_v_stream: scalar-output statistics only");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    int rc = ensure_post(ctx); if (rc) return rc;
+    if (!ctx->have_prior) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v_stream: sgp_prior_set / sgp_prior_set_isotropic first");
+    rc = posterior_core(ctx, w, carry != 0, true); if (rc) return rc;
+    return posterior_fetch(ctx, mu_v, Sigma_v, Uv);
+}
+
 int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, double w, double* mu_v, double* Sigma_v, double* Uv) {
     if (check(ctx)) return SGP_ERR_ARG;
     if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v: run a sweep first");
     if (ctx->Dout != 1) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "posterior_v: scalar-output statistics only (MultiSGP folds kron(W, Psi2) on the host)");
     if (!xi0 || !Lambda0) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v: prior natural parameters required");
-    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
-    const int M = ctx->M; const size_t MM = (size_t)M * M;
-    double* d = ctx->dense_dev + 64;
-    double *Lam = d, *X = d + MM, *Sig = d + 2 * MM, *T = d + 3 * MM, *xi = d + 4 * MM, *mu = xi + M;
-    double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM;
-    SGP_CUDA(ctx, cudaMemcpyAsync(Lam, Lambda0, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    SGP_CUDA(ctx, cudaMemcpyAsync(xi, xi0, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    axpby_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(Lam, Lam, 1.0, psi2, w, MM);        // Lambda = Lambda0 + w Psi2
-    axpby_kernel<<<nblocks(M), 256, 0, ctx->stream>>>(xi, xi, 1.0, psi1, w, M);            // xi = xi0 + w Psi1
-    int rc = sgp_potrf_lower(ctx, Lam, M); if (rc) return rc;                               // Lambda = L L'
-    rc = sgp_trtri_lower(ctx, Lam, X, T, Sig, M); if (rc) return rc;                        // X = L^-1, Sigma = X' X
-    rc = sgp_gemm(ctx, 0, 0, M, 1, M, 1.0, Sig, M, xi, M, 0.0, mu, M, 0); if (rc) return rc; // mu = Sigma xi
-    if (Sigma_v) SGP_CUDA(ctx, cudaMemcpyAsync(Sigma_v, Sig, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (mu_v) SGP_CUDA(ctx, cudaMemcpyAsync(mu_v, mu, M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (Uv) {
-        add_outer_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(Sig, mu, M);                 // R_v = Sigma + mu mu'
-        rc = sgp_potrf_lower(ctx, Sig, M); if (rc) return rc;
-        dim3 tg((M + 31) / 32, (M + 31) / 32), tb(32, 8);
-        transpose_kernel<<<tg, tb, 0, ctx->stream>>>(Sig, T, M);                            // Uv = L_R'
-        SGP_CUDA(ctx, cudaMemcpyAsync(Uv, T, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    SGP_CUDA(ctx, cudaGetLastError());
-    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SGP_OK;
+    int rc = sgp_prior_set(ctx, xi0, Lambda0); if (rc) return rc;
+    rc = posterior_core(ctx, w, false, Uv != nullptr); if (rc) return rc;
+    return posterior_fetch(ctx, mu_v, Sigma_v, Uv);
 }
 
 int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI1, double* sumI2) {
@@ -434,14 +511,19 @@ int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI
     if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: run a sweep first");
     if (!ctx->have_kuu) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: sgp_kuu_factor first");
     if (ctx->Dout != 1) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "w_terms: scalar-output statistics only");
-    if (!mu_v || !Uv) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: mu_v and Uv are inputs");
+    if ((mu_v == nullptr) != (Uv == nullptr)) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: pass both mu_v and Uv, or neither (resident posterior)");
+    if (!mu_v && !(ctx->have_post && ctx->have_post_uv && ctx->post_M == ctx->M)) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: no resident posterior (sgp_posterior_v first)");
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
     const int M = ctx->M; const size_t MM = (size_t)M * M;
     double* d = ctx->dense_dev + 64;
-    double *A = d, *U = d + MM, *C = d + 2 * MM, *mu = d + 4 * MM, *res = mu + M;
+    double *U = d + MM, *C = d + 2 * MM, *mu = d + 4 * MM, *res = mu + M;
     double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM; double* scal = psi1 + M;
-    SGP_CUDA(ctx, cudaMemcpyAsync(U, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    SGP_CUDA(ctx, cudaMemcpyAsync(mu, mu_v, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (mu_v) {
+        SGP_CUDA(ctx, cudaMemcpyAsync(U, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        SGP_CUDA(ctx, cudaMemcpyAsync(mu, mu_v, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        U = post_Uv(ctx); mu = post_mu(ctx);
+    }
     int rc = SGP_OK;
     rc = sgp_dot(ctx, ctx->Kinv_dev, 1, psi2, 1, MM, res); if (rc) return rc;                            // tr(K_uu^-1 Psi2) = <K_uu^-1, Psi2>
     rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, U, M, psi2, M, 0.0, C, M, 0); if (rc) return rc; // Uv Psi2

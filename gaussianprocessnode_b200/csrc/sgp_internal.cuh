@@ -61,6 +61,10 @@ struct sgp_ctx {
     // uncertain-input scratch (sigma-point cloud)
     double *sp_X_dev = nullptr, *sp_w_dev = nullptr, *sp_y_dev = nullptr; size_t sp_cap = 0;
 
+    // resident prior / posterior of v (api.cu: post_*): [Lambda_prior | xi_prior | mu | Sigma | Uv]
+    double* post_dev = nullptr; size_t post_cap = 0; int post_M = 0;
+    bool have_prior = false, have_post = false, have_post_uv = false;
+
     SgpComm* comm = nullptr;
 
     // last sweep launch record
@@ -93,6 +97,9 @@ int sgp_trsm_lower(sgp_ctx* ctx, const double* L, double* B, int M, int nrhs, bo
 int sgp_trsm_lower_dinv(sgp_ctx* ctx, const double* L, const double* dinv, double* B, double* tmp, int M, int nrhs, bool trans);
 int sgp_trtri_lower(sgp_ctx* ctx, const double* L, double* X, double* Tmp, double* S, int M);   // X = L^-1, S = X' X (optional)
 int sgp_kuu_build(sgp_ctx* ctx, double* K, double jitter);
+// api.cu: resident posterior (mu [M], Uv [M x M upper]) or nullptr when there is none
+const double* sgp_resident_mu(sgp_ctx* ctx);
+const double* sgp_resident_uv(sgp_ctx* ctx);
 int sgp_dot(sgp_ctx* ctx, const double* a, size_t sa, const double* b, size_t sb, size_t n, double* out);   // deterministic
 // comm.cu
 int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count);

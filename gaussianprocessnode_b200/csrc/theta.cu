@@ -159,7 +159,8 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
                                    double* dvariance, double* dlengthscale) {
     if (!ctx) return SGP_ERR_ARG;
     if (!ctx->have_kernel || !ctx->have_Z || ctx->N <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: set_kernel, set_inducing and set_data first");
-    if (!mu_v || !Uv) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: mu_v and Uv are inputs");
+    if ((mu_v == nullptr) != (Uv == nullptr)) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: pass both mu_v and Uv, or neither (resident posterior)");
+    if (!mu_v && !(sgp_resident_mu(ctx) && sgp_resident_uv(ctx))) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: no resident posterior (sgp_posterior_v first)");
     if (ctx->have_w) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "theta_objective: per-point weights are not part of the reference objective");
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
     const int M = ctx->M, D = ctx->D;
@@ -184,8 +185,13 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
     // K_uu^-1 (left by sgp_kuu_factor)
     SGP_CUDA(ctx, cudaMemcpyAsync(Kinv, ctx->Kinv_dev, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     // R_v = Uv' Uv (T holds Uv), A = R_v - K_uu^-1
-    SGP_CUDA(ctx, cudaMemcpyAsync(T, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    SGP_CUDA(ctx, cudaMemcpyAsync(vdev, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (mu_v) {
+        SGP_CUDA(ctx, cudaMemcpyAsync(T, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        SGP_CUDA(ctx, cudaMemcpyAsync(vdev, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        SGP_CUDA(ctx, cudaMemcpyAsync(T, sgp_resident_uv(ctx), MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        SGP_CUDA(ctx, cudaMemcpyAsync(vdev, sgp_resident_mu(ctx), (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, T, M, T, M, 0.0, Rv, M, 0); if (rc) return rc;
     sub_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, Rv, Kinv, MM);
     // scalars: <Kinv, Psi2>, <Rv, Psi2>, v' Psi1

@@ -188,10 +188,31 @@ class SGPContext:
         self._ck(self.lib.sgp_posterior_v(self.h, _p(xi0), _p(Lam0), float(w), _p(mu), _p(Sigma), _p(Uv)))
         return mu, Sigma, Uv
 
+    def prior_set(self, xi0, Lambda0):
+        M = self.M
+        self._ck(self.lib.sgp_prior_set(self.h, _p(_f64(xi0, (M,))), _p(np.asfortranarray(np.asarray(Lambda0, dtype=np.float64).reshape(M, M)))))
+
+    def prior_set_isotropic(self, variance):
+        self._ck(self.lib.sgp_prior_set_isotropic(self.h, float(variance)))
+
+    def posterior_v_stream(self, w, carry=True, fetch=False, out=None):
+        """Posterior from the RESIDENT prior and the last sweep; with `carry` it becomes the next prior.  fetch=False copies
+        nothing back (mu_v / Uv stay resident for w_terms(None, None) / theta_objective(None, None, ...))."""
+        M = self.M
+        if out is not None:
+            mu, Sigma, Uv = out
+        elif fetch:
+            mu, Sigma, Uv = np.empty(M), np.empty((M, M), order="F"), np.empty((M, M), order="F")
+        else:
+            mu = Sigma = Uv = None
+        self._ck(self.lib.sgp_posterior_v_stream(self.h, float(w), 1 if carry else 0, _p(mu), _p(Sigma), _p(Uv)))
+        return mu, Sigma, Uv
+
     def w_terms(self, mu_v, Uv):
         M = self.M
-        mu_v = _f64(mu_v, (M,))
-        Uv = np.asfortranarray(np.asarray(Uv, dtype=np.float64).reshape(M, M))
+        if mu_v is not None:
+            mu_v = _f64(mu_v, (M,))
+            Uv = np.asfortranarray(np.asarray(Uv, dtype=np.float64).reshape(M, M))
         a, b = ctypes.c_double(), ctypes.c_double()
         self._ck(self.lib.sgp_w_terms(self.h, _p(mu_v), _p(Uv), ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
@@ -206,8 +227,9 @@ class SGPContext:
     def theta_objective(self, mu_v, Uv, w, jitter=0.0, grad=True):
         """(F, dF/dvariance, dF/dlengthscale[D]) of the theta step on the resident data (sgp_theta_objective)."""
         M = self.M
-        mu_v = _f64(mu_v, (M,))
-        Uv = np.asfortranarray(np.asarray(Uv, dtype=np.float64).reshape(M, M))
+        if mu_v is not None:
+            mu_v = _f64(mu_v, (M,))
+            Uv = np.asfortranarray(np.asarray(Uv, dtype=np.float64).reshape(M, M))
         val = ctypes.c_double(); dv = ctypes.c_double(); dl = np.zeros(self.D)
         self._ck(self.lib.sgp_theta_objective(self.h, _p(mu_v), _p(Uv), float(w), float(jitter), ctypes.byref(val),
                                               ctypes.byref(dv) if grad else None, _p(dl) if grad else None))

@@ -104,9 +104,20 @@ int sgp_kuu_solve(sgp_ctx* ctx, int nrhs, double* B);
  * Outputs may be NULL. */
 int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, double w, double* mu_v, double* Sigma_v,
                     double* Uv);
+/* Streaming prior (experiments/regression_kin40k.ipynb:200-213: the posterior of mini-batch b is the prior of mini-batch b+1,
+ * restarted from N(0, 50 I) every epoch): the Gaussian on v stays RESIDENT on the device.
+ *   sgp_prior_set            load a prior (host natural parameters xi0 [M], Lambda0 [M x M])
+ *   sgp_prior_set_isotropic  N(0, variance I) without any host traffic
+ *   sgp_posterior_v_stream   the N-th prod on the resident prior and the last sweep; carry != 0: the posterior's natural
+ *                            parameters become the resident prior.  Outputs may be NULL (nothing is copied back); mu_v / Uv
+ *                            of the last posterior stay resident for sgp_w_terms / sgp_theta_objective (pass NULL there). */
+int sgp_prior_set(sgp_ctx* ctx, const double* xi0, const double* Lambda0);
+int sgp_prior_set_isotropic(sgp_ctx* ctx, double variance);
+int sgp_posterior_v_stream(sgp_ctx* ctx, double w, int carry, double* mu_v, double* Sigma_v, double* Uv);
 /* sum over n of the :w rule / energy ingredients (GPnode/UniSGPnode.jl:196-238, 337-387), from the last sweep:
  *   sumI1 = Psi0 - tr(K_uu^{-1} Psi2),  sumI2 = sum_y2 - 2 mu_v' Psi1 + <Uv' Uv, Psi2>.
- * mu_v / Uv are INPUTS (the previous sweep's posterior, as the VMP schedule has it); needs sgp_kuu_factor. */
+ * mu_v / Uv are INPUTS (the previous sweep's posterior, as the VMP schedule has it), or both NULL = the resident posterior of
+ * the last sgp_posterior_v[_stream]; needs sgp_kuu_factor. */
 int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI1, double* sumI2);
 /* `@rule UniSGP(:out)` over a test set (GPnode/UniSGPnode.jl:96-104; regression_kin40k.ipynb:289-304): out = K_*u mu_v */
 int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* mu_v, double* out);
@@ -117,7 +128,7 @@ int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* m
  * (helper_functions/derivative_helper.jl:23-39, 55-67; experiments/regression_kin40k.ipynb:214-222):
  *   F = sum_n [ w/2 k_nn - w/2 |L_u^-1 k_n|^2 + w/2 |Uv k_n|^2 - w y_n mu_v' k_n ],   K_uu = L_u L_u' (+ jitter I)
  * value = F, dvariance = dF/d sigma^2, dlengthscale[D] = dF/d ell_d (analytic; the host applies its own chain rule for the
- * raw parameters, e.g. softplus').  mu_v (M) and Uv (M x M upper, column-major) are inputs.  Any output may be NULL; without
+ * raw parameters, e.g. softplus').  mu_v (M) and Uv (M x M upper, column-major) are inputs (both NULL = resident posterior).  Any output may be NULL; without
  * gradient outputs only the value is computed.  With a communicator attached the D + 2 scalars are summed over ranks. */
 int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const double* Uv, double w, double jitter, double* value,
                         double* dvariance, double* dlengthscale);

@@ -106,3 +106,30 @@ def test_banana_golden_chain_on_gpu(ctx, banana):
     m = ctx.predict_mean(x[4000:5300], banana["mu_v"])
     yt = (banana["label"][4000:5300] > 0).astype(float)
     assert int(np.sum(np.abs((m > 0).astype(float) - yt))) == 125
+
+
+def test_streaming_prior_equals_one_full_sweep(ctx, kin40k):
+    # experiments/regression_kin40k.ipynb:196-228: 20 mini-batches of 500, the posterior of batch b is the prior of batch b+1,
+    # starting from N(0, 50 I).  For fixed theta that is the same posterior as ONE sweep over all 10000 points.
+    from gaussianprocessnode_b200 import nodes as nd
+    X, y = kin40k["xtrain"], kin40k["ytrain"]
+    sp = kernels.softplus(kin40k["theta_raw"])
+    M = 256
+    Z = X[kin40k["xu_ids"][:M]]
+    w = 1.0e4
+    ctx.set_kernel(sp[0], sp[1:]); ctx.set_inducing(Z)
+    ctx.prior_set_isotropic(50.0)
+    xb, yb = nd.split2batch((X, y), 500)
+    for b in range(len(xb)):
+        ctx.set_data(xb[b], yb[b]); ctx.sweep_psi(fetch=False)
+        ctx.posterior_v_stream(w, carry=True)                       # nothing crosses the bus
+    mu_s, Sig_s, Uv_s = ctx.posterior_v_stream(0.0, carry=False, fetch=True)     # w = 0: posterior == resident prior
+    ctx.set_data(X, y); ctx.sweep_psi(fetch=False)
+    mu_f, Sig_f, Uv_f = ctx.posterior_v(np.zeros(M), np.eye(M) / 50.0, w)
+    assert fro(mu_s, mu_f) < 1e-7 and fro(Sig_s, Sig_f) < 1e-7          # conditioning of Lambda (cond ~ 1e8: SURVEY.md 7)
+    # the resident posterior feeds the :w terms and the theta step without host copies
+    ctx.kuu_factor(1e-8, fetch=False)
+    a = ctx.w_terms(None, None); b_ = ctx.w_terms(mu_s, Uv_s)
+    assert abs(a[0] - b_[0]) <= 1e-12 * abs(b_[0]) and abs(a[1] - b_[1]) <= 1e-10 * abs(b_[1])
+    f1 = ctx.theta_objective(None, None, w, 1e-8); f2 = ctx.theta_objective(mu_s, Uv_s, w, 1e-8)
+    assert abs(f1[0] - f2[0]) <= 1e-10 * abs(f2[0]) and np.linalg.norm(f1[2] - f2[2]) <= 1e-9 * np.linalg.norm(f2[2])
