@@ -210,19 +210,18 @@ def main():
     value = world * cfg["N"] / (ms_step * 1e-3)
 
     # e2e through the C ABI with HOST buffers in pinned memory (sgp_pinned_alloc): per step the H2D copy of X / y
-    # (sgp_set_data) and the D2H read of Psi0 / Psi1 / Psi2 / sum_y2 (sgp_sweep_psi) are inside the timed region
+    # and the D2H read of Psi0 / Psi1 / Psi2 / sum_y2 (one sgp_sweep_psi_host call) are inside the timed region
     from gaussianprocessnode_b200 import pinned_empty
     Xp = pinned_empty(X.shape); Xp[...] = X
     yp = pinned_empty(y.shape); yp[...] = y
     psi1p = pinned_empty((cfg["M"],)); psi2p = pinned_empty((cfg["M"], cfg["M"]), order="F")
     for _ in range(3):
-        ctx.set_data(Xp, yp); ctx.sweep_psi(out=(psi1p, psi2p))
+        ctx.sweep_psi_host(Xp, yp, out=(psi1p, psi2p))
     barrier()
     n_e2e = max(10, min(args.steps, 50))
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        ctx.set_data(Xp, yp)
-        out = ctx.sweep_psi(out=(psi1p, psi2p))
+        out = ctx.sweep_psi_host(Xp, yp, out=(psi1p, psi2p))     # sgp_sweep_psi_host: H2D of X / y, sweep, D2H of the statistics
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / n_e2e)
     h2d = X.nbytes + y.nbytes

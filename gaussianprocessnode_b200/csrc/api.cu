@@ -183,7 +183,16 @@ static int alloc_data(sgp_ctx* ctx, int64_t N) {
     return SGP_OK;
 }
 
+static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts);
+
 int sgp_set_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts) {
+    int rc = upload_data(ctx, N, X, ybar, yvar, wts); if (rc) return rc;
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // the host buffers may be reused as soon as this returns
+    return SGP_OK;
+}
+
+// H2D copies enqueued on the ctx stream, no host synchronisation
+static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts) {
     if (check(ctx)) return SGP_ERR_ARG;
     if (!ctx->have_kernel) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data: set_kernel first (D is taken from it)");
     if (N < 0 || (N > 0 && !X)) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data: X required");
@@ -207,7 +216,6 @@ int sgp_set_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, c
         SGP_CUDA(ctx, cudaMemcpyAsync(ctx->w_dev, wts, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         if (tail) SGP_CUDA(ctx, cudaMemsetAsync(ctx->w_dev + n, 0, tail * sizeof(double), ctx->stream));
     }
-    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->N = N; ctx->have_yv = yvar != nullptr; ctx->have_w = wts != nullptr; ctx->have_stats = false;
     return SGP_OK;
 }
@@ -270,6 +278,13 @@ int sgp_sweep_psi(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
     int rc = sweep_resident(ctx, false); if (rc) return rc;
     return fetch_stats(ctx, psi0, psi1, psi2, sum_y2);
+}
+
+int sgp_sweep_psi_host(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts, double* psi0,
+                       double* psi1, double* psi2, double* sum_y2) {
+    int rc = upload_data(ctx, N, X, ybar, yvar, wts); if (rc) return rc;
+    rc = sweep_resident(ctx, false); if (rc) return rc;
+    return fetch_stats(ctx, psi0, psi1, psi2, sum_y2);       // the one host synchronisation of the step
 }
 
 int sgp_sweep_psi_uncertain(sgp_ctx* ctx, int method, int p, int64_t N, const double* mean, const double* cov, int D_out, const double* R,

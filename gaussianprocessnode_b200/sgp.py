@@ -128,6 +128,18 @@ class SGPContext:
         self._ck(self.lib.sgp_sweep_psi(self.h, ctypes.byref(psi0), _p(psi1), _p(psi2), ctypes.byref(sy2)))
         return psi0.value, psi1, psi2, sy2.value
 
+    def sweep_psi_host(self, X, ybar=None, yvar=None, wts=None, out=None):
+        """set_data + sweep_psi in one call (one host synchronisation); `out` = (psi1, psi2) preallocated arrays."""
+        X = _f64(X).reshape(-1, self.D)
+        N = X.shape[0]; M = self.M
+        ybar, yvar, wts = _f64(ybar, (N,)), _f64(yvar, (N,)), _f64(wts, (N,))
+        psi1, psi2 = out if out is not None else (np.empty(M), np.empty((M, M), order="F"))
+        psi0, sy2 = ctypes.c_double(), ctypes.c_double()
+        self._ck(self.lib.sgp_sweep_psi_host(self.h, N, _p(X), _p(ybar), _p(yvar), _p(wts), ctypes.byref(psi0), _p(psi1), _p(psi2),
+                                             ctypes.byref(sy2)))
+        self.N = N
+        return psi0.value, psi1, psi2, sy2.value
+
     def sweep_psi_uncertain(self, method, mean, cov, R=None, D_out=1, p=21, want_psi1_n=False):
         mean = _f64(mean).reshape(-1, self.D)
         N = mean.shape[0]

@@ -81,6 +81,11 @@ int sgp_set_data_dev(sgp_ctx* ctx, int64_t N, const double* X_dev, const double*
  * (sgp_comm_init) the statistics are all-reduced over ranks before they are returned. */
 int sgp_sweep_psi(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2);
 
+/* sgp_set_data + sgp_sweep_psi as ONE call with a single host synchronisation: the per-step call of a host whose data change
+ * every step (mini-batches).  The data stay resident afterwards exactly as after sgp_set_data. */
+int sgp_sweep_psi_host(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts,
+                       double* psi0, double* psi1, double* psi2, double* sum_y2);
+
 /* Uncertain inputs q(x_n) = N(mean_n, cov_n): replaces the cubature loop `approximate_kernel_expectation(!)`
  * (GPnode/UniSGPnode.jl:11-37, GPnode/MultiSGPnode.jl:11-35) inside `@rule UniSGP(:v)` (:125-140) and
  * `@rule MultiSGP(:v)/(:w)/(:out)` (GPnode/MultiSGPnode.jl:290-328, 367-444, 90-120), summed over the N nodes.

@@ -187,3 +187,14 @@ def test_synthetic_M1024_exact_on_a_slice_and_properties_at_scale(ctx):
     K = kernels.kernel_matrix(X, Z[cols], 1.0, ell)
     np.testing.assert_allclose(np.diag(full[2])[cols], np.sum(K * K, axis=0), rtol=1e-11)
     np.testing.assert_allclose(full[1][cols], K.T @ y, rtol=1e-9, atol=1e-7)
+
+
+def test_one_call_host_step_equals_set_data_plus_sweep(ctx):
+    rng = np.random.default_rng(31)
+    N, D, M = 3001, 8, 200
+    X = rng.normal(size=(N, D)); Z = rng.normal(size=(M, D)); y = rng.normal(size=N); yv = rng.uniform(0, 0.3, N)
+    ctx.set_kernel(1.1, np.full(D, 1.7)); ctx.set_inducing(Z)
+    a = ctx.sweep_psi_host(X, y, yv)
+    ctx.set_data(X, y, yv); b = ctx.sweep_psi()
+    assert a[0] == b[0] and a[3] == b[3] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(ctx.sweep_psi()[2], a[2])          # the data stay resident after the one-call step
