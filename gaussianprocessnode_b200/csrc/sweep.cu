@@ -46,9 +46,13 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     // one persistent CTA per SM; the (tile, chunk) sequence is cut into equally heavy contiguous slices.  Cost weights
     // of one chunk (measured per-chunk clocks, see profiles/): off-diagonal 2*TM generated rows + TM^2 MMA, diagonal TM
     // rows + the MMA blocks on or below the diagonal
-    int w_diag = 17, w_off = 24;
-    if (const char* e = std::getenv("SGP_SWEEP_WEIGHTS")) { int a_ = 0, b_ = 0; if (std::sscanf(e, "%d,%d", &a_, &b_) == 2 && a_ > 0 && b_ > 0) { w_diag = a_; w_off = b_; } }
-    const long long total_cost = chunks * ((long long)nblk * w_diag + (long long)(ntiles - nblk) * w_off);
+    int w_diag = 17, w_off = 24, w_fixed = 17;
+    if (const char* e = std::getenv("SGP_SWEEP_WEIGHTS")) {
+        int a_ = 0, b_ = 0, c_ = -1;
+        int got = std::sscanf(e, "%d,%d,%d", &a_, &b_, &c_);
+        if (got >= 2 && a_ > 0 && b_ > 0) { w_diag = a_; w_off = b_; if (got == 3 && c_ >= 0) w_fixed = c_; }
+    }
+    const long long total_cost = chunks * ((long long)nblk * w_diag + (long long)(ntiles - nblk) * w_off) + (long long)ntiles * w_fixed;
     const int ncta = (int)std::min<long long>(std::min(ctx->num_sms, 256), std::max<long long>(1, chunks * ntiles));   // <= block size: see the segment count in run_segment
     const int grid = ncta;
     const int nslots = ncta + ntiles;
@@ -61,7 +65,7 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
 
     SweepParams p{};
     p.X = X; p.y = y; p.yv = yv; p.w = w; p.N = N; p.chunks = chunks; p.M = M; p.D = D; p.ntiles = ntiles; p.nblk = nblk; p.ncta = ncta;
-    p.total_cost = total_cost; p.w_diag = w_diag; p.w_off = w_off; p.dbg = (nslots <= 8192) ? ctx->sweep_dbg_dev : nullptr;
+    p.total_cost = total_cost; p.w_diag = w_diag; p.w_off = w_off; p.w_fixed = w_fixed; p.dbg = (nslots <= 8192) ? ctx->sweep_dbg_dev : nullptr;
     if (p.dbg) { SGP_CUDA(ctx, cudaMemsetAsync(p.dbg, 0xff, (size_t)nslots * 4 * sizeof(long long), ctx->stream)); ctx->sweep_dbg_slots = nslots; }
     const double sq = std::sqrt(SGP_EXP_SCALE);
     for (int d = 0; d < SGP_MAX_D; ++d) { p.inv_ell_s[d] = d < D ? sq / ctx->ell[d] : 0.0; p.center[d] = d < D ? ctx->center[d] : 0.0; }

@@ -31,6 +31,7 @@ struct SweepParams {
     long long total_cost;                                // chunks * sum of tile weights
     int M, D, ntiles, nblk, ncta;
     int w_diag, w_off;                                   // cost weights of one chunk of a diagonal / off-diagonal tile
+    int w_fixed;                                         // cost of entering a tile (segment prologue), charged at each tile's start
     double inv_ell_s[SGP_MAX_D];                         // sqrt(s) / ell_d  (both operands carry sqrt(s))
     double center[SGP_MAX_D];
     double log_var_s;                                    // s * ln sigma^2
@@ -40,8 +41,8 @@ struct SweepParams {
 // ---- work partition (shared by the sweep and the reduce kernels, so that both see the same segments) -------------
 __host__ __device__ inline long long cta_pos(long long total_cost, int ncta, int b) { return total_cost / ncta * b + total_cost % ncta * b / ncta; }
 // chunk range [lo, hi) that the cost interval [p0, p1) covers inside a tile whose cost prefix is `pre`
-__host__ __device__ inline void seg_range(long long p0, long long p1, long long pre, int wt, long long chunks, long long& lo, long long& hi) {
-    long long d0 = p0 - pre, d1 = p1 - pre;
+__host__ __device__ inline void seg_range(long long p0, long long p1, long long pre, int wt, int wfix, long long chunks, long long& lo, long long& hi) {
+    long long d0 = p0 - pre - wfix, d1 = p1 - pre - wfix;      // the first wfix units of a tile's span are its entry cost
     lo = d0 <= 0 ? 0 : (d0 + wt - 1) / wt;
     hi = d1 <= 0 ? 0 : (d1 + wt - 1) / wt;
     if (lo > chunks) lo = chunks;
@@ -515,13 +516,13 @@ __device__ __forceinline__ void reduce_items(const SweepParams& p, double* __res
             long long pre = 0;
             I = 0; J = 0;
             for (int t = 0; t < tile; ++t) {
-                pre += (long long)(I == J ? p.w_diag : p.w_off) * p.chunks;
+                pre += (long long)(I == J ? p.w_diag : p.w_off) * p.chunks + p.w_fixed;
                 if (++J > I) { ++I; J = 0; }
             }
             int mine = 0;
             if (tid < p.ncta) {
                 long long lo, hi;
-                seg_range(cta_pos(p.total_cost, p.ncta, tid), cta_pos(p.total_cost, p.ncta, tid + 1), pre, I == J ? p.w_diag : p.w_off, p.chunks, lo, hi);
+                seg_range(cta_pos(p.total_cost, p.ncta, tid), cta_pos(p.total_cost, p.ncta, tid + 1), pre, I == J ? p.w_diag : p.w_off, p.w_fixed, p.chunks, lo, hi);
                 mine = lo < hi;
             }
             const unsigned ballot = __ballot_sync(0xffffffffu, mine);
@@ -606,14 +607,14 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const __grid_constant__ Sw
         const bool diag = (I == J);
         const int wt = diag ? p.w_diag : p.w_off;
         long long lo, hi;
-        seg_range(p0, p1, pre, wt, p.chunks, lo, hi);
+        seg_range(p0, p1, pre, wt, p.w_fixed, p.chunks, lo, hi);
         if (lo < hi) {
             const int n = (int)(hi - lo);
             if (diag) run_segment<TM, NB, DPAD, NT, KIND, WEIGHTED, true>(p, sm, I, J, lo, n, g, bcta + t);
             else run_segment<TM, NB, DPAD, NT, KIND, WEIGHTED, false>(p, sm, I, J, lo, n, g, bcta + t);
             g += (unsigned)n;
         }
-        pre += (long long)wt * p.chunks;
+        pre += (long long)wt * p.chunks + p.w_fixed;
         if (++J > I) { ++I; J = 0; }
     }
     // every partial tile of the sweep is in the workspace once all CTAs are here (cooperative launch: all CTAs resident)
