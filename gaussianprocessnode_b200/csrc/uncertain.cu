@@ -248,6 +248,82 @@ __global__ void __launch_bounds__(256) cf_psi2_kernel(const double* __restrict__
     if (active) partial[(size_t)split * M * M + a + (size_t)b * M] = acc;
 }
 
+// Closed-form Psi2, fast path (d <= 4): per-point packed record [s*B2 upper-packed with doubled off-diagonals | c2 | m],
+// s = -2048/ln2, so that the quadratic form IS the argument of the table-driven exp (sgp_internal.cuh: 7 FP64 instructions);
+// one thread per inducing pair (a >= b), points staged through shared memory, four points in flight per thread.
+// FP64-ALU-bound: d + d(d+1)/2 + d ... ~ 15 FP64 instructions per (pair, point) at d = 2.
+template <int DD>
+__global__ void __launch_bounds__(256) cf_psi2_fast_kernel(const double* __restrict__ rec2, const double* __restrict__ Z, const double* __restrict__ exptab,
+                                                           double* __restrict__ partial, long long N, int M, int nsplit) {
+    constexpr int NP = DD * (DD + 1) / 2, RS = NP + 1 + DD, PC = 128;
+    __shared__ double tab[SGP_EXP_TAB];
+    __shared__ double sh[PC * RS];
+    for (int i = threadIdx.x; i < SGP_EXP_TAB; i += 256) tab[i] = exptab[i];
+    const long long pair = blockIdx.x * 256LL + threadIdx.x;
+    const long long npairs = (long long)M * (M + 1) / 2;
+    int a = 0, b = 0;
+    const bool active = pair < npairs;
+    if (active) {
+        a = (int)((sqrt(8.0 * (double)pair + 1.0) - 1.0) * 0.5);
+        while ((long long)(a + 1) * (a + 2) / 2 <= pair) ++a;
+        while ((long long)a * (a + 1) / 2 > pair) --a;
+        b = (int)(pair - (long long)a * (a + 1) / 2);
+    }
+    double zb[DD];
+#pragma unroll
+    for (int i = 0; i < DD; ++i) zb[i] = active ? 0.5 * (Z[(size_t)a * DD + i] + Z[(size_t)b * DD + i]) : 0.0;
+    const int split = blockIdx.y;
+    const long long n0 = N * split / nsplit, n1 = N * (split + 1) / nsplit;
+    double acc = 0.0;
+    for (long long base = n0; base < n1; base += PC) {
+        const int cnt = (int)((n1 - base) < PC ? (n1 - base) : PC);
+        __syncthreads();
+        for (int e = threadIdx.x; e < PC * RS; e += 256) sh[e] = (e < cnt * RS) ? rec2[base * RS + e] : 0.0;   // padded points: c2 = 0
+        __syncthreads();
+#pragma unroll 1
+        for (int q0 = 0; q0 < PC; q0 += 4) {
+            if (q0 >= cnt) break;
+            double t[4], c2[4], k[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double* r = sh + (q0 + u) * RS;
+                double dm[DD];
+#pragma unroll
+                for (int i = 0; i < DD; ++i) dm[i] = r[NP + 1 + i] - zb[i];
+                double qf = 0.0;
+                int p = 0;
+#pragma unroll
+                for (int i = 0; i < DD; ++i) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = i; j < DD; ++j, ++p) s = fma(r[p], dm[j], s);
+                    qf = fma(dm[i], s, qf);
+                }
+                t[u] = qf; c2[u] = r[NP];
+            }
+            exp_scaled_v<4>(t, k, tab);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc = fma(c2[u], k[u], acc);
+        }
+    }
+    if (active) partial[(size_t)split * M * M + a + (size_t)b * M] = acc;
+}
+
+// rec (generic record of cf_prep_kernel) -> packed, pre-scaled Psi2 record
+__global__ void cf_pack_kernel(const double* __restrict__ rec, double* __restrict__ rec2, long long N, int d) {
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int RS = 2 * d * d + 2 + d, NP = d * (d + 1) / 2, RS2 = NP + 1 + d;
+    const double* r = rec + n * RS;
+    const double* B = r + d * d + 1;
+    double* o = rec2 + n * RS2;
+    int p = 0;
+    for (int i = 0; i < d; ++i)
+        for (int j = i; j < d; ++j, ++p) o[p] = -SGP_EXP_SCALE * (i == j ? B[i + j * d] : B[i + j * d] + B[j + i * d]);
+    o[NP] = B[d * d];
+    for (int i = 0; i < d; ++i) o[NP + 1 + i] = r[2 * d * d + 2 + i];
+}
+
 __global__ void cf_finish_kernel(const double* __restrict__ partial, const double* __restrict__ Z, const double* __restrict__ ell_inv,
                                  double* __restrict__ psi2, int M, int d, int nsplit) {
     size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -410,7 +486,22 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
         if (rc) { cudaFree(rec_d); cleanup(); return rc; }
         cudaMemsetAsync(ctx->work_dev, 0, (size_t)nsplit * MM * sizeof(double), ctx->stream);
         dim3 grid(nb((size_t)npairs), nsplit);
-        cf_psi2_kernel<<<grid, 256, 64 * RS * sizeof(double), ctx->stream>>>(rec_d, ctx->Z_dev, ctx->work_dev, N, M, d, nsplit);
+        if (d <= 4) {
+            double* rec2_d = nullptr;
+            const int RS2 = d * (d + 1) / 2 + 1 + d;
+            if (cudaMalloc((void**)&rec2_d, (size_t)N * RS2 * sizeof(double)) != cudaSuccess) { cudaFree(rec_d); cleanup(); SGP_FAIL(ctx, SGP_ERR_CUDA, "closed form: out of memory"); }
+            cf_pack_kernel<<<nb((size_t)N, 128), 128, 0, ctx->stream>>>(rec_d, rec2_d, N, d);
+            switch (d) {
+                case 1: cf_psi2_fast_kernel<1><<<grid, 256, 0, ctx->stream>>>(rec2_d, ctx->Z_dev, ctx->exptab_dev, ctx->work_dev, N, M, nsplit); break;
+                case 2: cf_psi2_fast_kernel<2><<<grid, 256, 0, ctx->stream>>>(rec2_d, ctx->Z_dev, ctx->exptab_dev, ctx->work_dev, N, M, nsplit); break;
+                case 3: cf_psi2_fast_kernel<3><<<grid, 256, 0, ctx->stream>>>(rec2_d, ctx->Z_dev, ctx->exptab_dev, ctx->work_dev, N, M, nsplit); break;
+                default: cf_psi2_fast_kernel<4><<<grid, 256, 0, ctx->stream>>>(rec2_d, ctx->Z_dev, ctx->exptab_dev, ctx->work_dev, N, M, nsplit); break;
+            }
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(rec2_d);
+        } else {
+            cf_psi2_kernel<<<grid, 256, 64 * RS * sizeof(double), ctx->stream>>>(rec_d, ctx->Z_dev, ctx->work_dev, N, M, d, nsplit);
+        }
         cf_finish_kernel<<<nb(MM), 256, 0, ctx->stream>>>(ctx->work_dev, ctx->Z_dev, ell_inv_d, s_psi2, M, d, nsplit);
         set_scal_kernel<<<1, 1, 0, ctx->stream>>>(s_scal, ctx->variance * (double)N, (double)N);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
