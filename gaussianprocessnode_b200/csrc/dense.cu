@@ -12,6 +12,7 @@
 #include "sgp_internal.cuh"
 #include <cmath>
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -176,9 +177,13 @@ int sgp_dot(sgp_ctx* ctx, const double* a, size_t sa, const double* b, size_t sb
     return SGP_OK;
 }
 
+int sgp_gemm2(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
+              double* C, int ldc, int lower_only);
+
 int sgp_gemm(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc, int lower_only) {
-    return gemm(ctx, opA, opB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
+    if (std::getenv("SGP_GEMM_V1")) return gemm(ctx, opA, opB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
+    return sgp_gemm2(ctx, opA, opB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
 }
 
 // B (M x nrhs, ld M) <- L^{-1} B (trans = false) or L^{-T} B (trans = true); L lower, column-major, ld M.

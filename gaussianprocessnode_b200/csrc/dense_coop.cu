@@ -325,6 +325,31 @@ __global__ void __launch_bounds__(CT, 1) trtri_coop_kernel(const double* __restr
     }
 }
 
+// General GEMM on the same tile routine: C[m x n] = beta C + alpha op(A) op(B), one CTA per 64 x 64 tile (grid-strided).
+struct Gemm2Args {
+    const double* A; const double* B; double* C;
+    int m, n, k, lda, ldb, ldc, opA, opB, lower_only;
+    double alpha, beta;
+};
+__global__ void __launch_bounds__(CT) gemm2_kernel(const Gemm2Args g) {
+    extern __shared__ double sm[];
+    double* As = sm; double* Bs = sm + TB * LDA_S;
+    const int tm = (g.m + TB - 1) / TB, tn = (g.n + TB - 1) / TB;
+    for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
+        const int ti = t % tm, tj = t / tm;
+        if (g.lower_only && tj > ti) continue;
+        const int rows = min(TB, g.m - ti * TB), cols = min(TB, g.n - tj * TB);
+        // A(r, k): opA == 0 -> A[(ti*64 + r) + k*lda], else A[k + (ti*64 + r)*lda];  B(k, c): opB == 0 -> B[k + (tj*64 + c)*ldb], else B[(tj*64 + c) + k*ldb]
+        const double* Ab = g.opA == 0 ? g.A + (size_t)ti * TB : g.A + (size_t)ti * TB * g.lda;
+        const double* Bb = g.opB == 0 ? g.B + (size_t)tj * TB * g.ldb : g.B + (size_t)tj * TB;
+        Acc acc; acc_zero(acc);
+        tile_mma(acc, Ab, g.opA == 0 ? 1 : (size_t)g.lda, g.opA == 0 ? (size_t)g.lda : 1, rows, Bb, g.opB == 0 ? 1 : (size_t)g.ldb,
+                 g.opB == 0 ? (size_t)g.ldb : 1, cols, g.k, As, Bs);
+        __syncthreads();
+        tile_store(acc, g.C + (size_t)ti * TB + (size_t)tj * TB * g.ldc, g.ldc, rows, cols, g.alpha, g.beta);
+    }
+}
+
 int coop_grid(sgp_ctx* ctx, const void* kern, int want) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CT, SMEM_DOUBLES * sizeof(double)) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -352,6 +377,17 @@ int sgp_potrf_lower(sgp_ctx* ctx, double* A, int M) {
         snprintf(buf, sizeof buf, "Cholesky: non-positive pivot at row %d of %d", info, M);
         SGP_FAIL(ctx, SGP_ERR_NOT_PD, buf);
     }
+    return SGP_OK;
+}
+
+int sgp_gemm2(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
+              double* C, int ldc, int lower_only) {
+    if (m <= 0 || n <= 0) return SGP_OK;
+    Gemm2Args g{A, B, C, m, n, k, lda, ldb, ldc, opA, opB, lower_only, alpha, beta};
+    const int tiles = ((m + TB - 1) / TB) * ((n + TB - 1) / TB);
+    const size_t smem = (size_t)(TB * LDA_S + KC * LDB_S) * sizeof(double);
+    gemm2_kernel<<<std::min(tiles, 4 * ctx->num_sms), CT, smem, ctx->stream>>>(g);
+    SGP_CUDA(ctx, cudaGetLastError());
     return SGP_OK;
 }
 

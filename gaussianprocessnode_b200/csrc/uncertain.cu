@@ -424,18 +424,28 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
     // device scratch: inputs
     double *mean_d = nullptr, *cov_d = nullptr, *R_d = nullptr, *p1n_d = nullptr, *misc_d = nullptr;
     int rc = SGP_OK;
-    auto cleanup = [&]() { cudaFree(mean_d); cudaFree(cov_d); cudaFree(R_d); cudaFree(p1n_d); cudaFree(misc_d); };
+    // all scratch of the call is carved from ONE context-owned arena that only ever grows: no cudaMalloc / cudaFree (and the
+    // implicit device synchronisations they bring) per call
+    const int RS_cf = 2 * d * d + 2 + d, RS2_cf = d * (d + 1) / 2 + 1 + d;
+    const int psi1_split = (int)std::max<long long>(1, std::min<long long>(512, N / 64));
+    size_t arena_need = (size_t)N * d + (size_t)N * d * d + 512 + (size_t)N * (size_t)std::max(D_out, 1) + (size_t)N
+                      + (need_p1n ? (size_t)N * M : 0) + (method == SGP_METHOD_CLOSED_FORM_SE ? (size_t)N * (RS_cf + RS2_cf) : 0)
+                      + (size_t)psi1_split * std::max(D_out, 1) * M + 64;
+    rc = sgp_ensure(ctx, &ctx->unc_dev, &ctx->unc_cap, arena_need); if (rc) return rc;
+    size_t arena_off = 0;
+    auto take = [&](size_t n) { double* p = ctx->unc_dev + arena_off; arena_off += (n + 1) & ~(size_t)1; return p; };
+    auto cleanup = [&]() {};
 #define UC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return SGP_ERR_CUDA; } } while (0)
-    UC(cudaMalloc((void**)&mean_d, (size_t)N * d * sizeof(double)));
-    UC(cudaMalloc((void**)&cov_d, (size_t)N * d * d * sizeof(double)));
-    UC(cudaMalloc((void**)&misc_d, (256 + SGP_MAX_D) * sizeof(double)));
+    mean_d = take((size_t)N * d);
+    cov_d = take((size_t)N * d * d);
+    misc_d = take(256 + SGP_MAX_D);
     UC(cudaMemcpyAsync(mean_d, mean, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     UC(cudaMemcpyAsync(cov_d, cov, (size_t)N * d * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (R) {
-        UC(cudaMalloc((void**)&R_d, (size_t)N * D_out * sizeof(double)));
+        R_d = take((size_t)N * D_out);
         UC(cudaMemcpyAsync(R_d, R, (size_t)N * D_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (need_p1n) UC(cudaMalloc((void**)&p1n_d, (size_t)N * M * sizeof(double)));
+    if (need_p1n) p1n_d = take((size_t)N * M);
     double hostmisc[256 + SGP_MAX_D] = {0};
     for (int i = 0; i < d; ++i) hostmisc[i] = 1.0 / ctx->ell[i];
     for (int i = 0; i < d; ++i) hostmisc[SGP_MAX_D + i] = ctx->ell[i];
@@ -455,7 +465,7 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
         const size_t NS = (size_t)N * S, cap = ((NS + 31) / 32) * 32;
         if (ctx->sp_cap < cap) {
             cudaFree(ctx->sp_X_dev); cudaFree(ctx->sp_w_dev); cudaFree(ctx->sp_y_dev); ctx->sp_X_dev = ctx->sp_w_dev = ctx->sp_y_dev = nullptr; ctx->sp_cap = 0;
-            UC(cudaMalloc((void**)&ctx->sp_X_dev, cap * d * sizeof(double)));
+            UC(cudaMalloc((void**)&ctx->sp_X_dev, cap * UD * sizeof(double)));   // sized for the largest input dimension: the buffer is reused across calls
             UC(cudaMalloc((void**)&ctx->sp_w_dev, cap * sizeof(double)));
             UC(cudaMalloc((void**)&ctx->sp_y_dev, cap * sizeof(double)));
             ctx->sp_cap = cap;
@@ -476,20 +486,20 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
     } else {
         const int RS = 2 * d * d + 2 + d;
         double* rec_d = nullptr;
-        UC(cudaMalloc((void**)&rec_d, (size_t)N * RS * sizeof(double)));
+        rec_d = take((size_t)N * RS);
         cf_prep_kernel<<<nb((size_t)N, 128), 128, 0, ctx->stream>>>(d, N, mean_d, cov_d, ell_d, ctx->variance, rec_d, ctx->info_dev);
         cf_psi1n_kernel<<<nb((size_t)N * M), 256, 0, ctx->stream>>>(rec_d, ctx->Z_dev, p1n_d, N, M, d);
         const long long npairs = (long long)M * (M + 1) / 2;
         int nsplit = (int)std::max<long long>(1, std::min<long long>(64, (4LL * ctx->num_sms * 256) / std::max<long long>(npairs, 1)));
         if (nsplit > N) nsplit = (int)N;
         rc = sgp_ensure(ctx, &ctx->work_dev, &ctx->work_cap, (size_t)nsplit * MM);
-        if (rc) { cudaFree(rec_d); cleanup(); return rc; }
+        if (rc) { cleanup(); return rc; }
         cudaMemsetAsync(ctx->work_dev, 0, (size_t)nsplit * MM * sizeof(double), ctx->stream);
         dim3 grid(nb((size_t)npairs), nsplit);
         if (d <= 4) {
             double* rec2_d = nullptr;
             const int RS2 = d * (d + 1) / 2 + 1 + d;
-            if (cudaMalloc((void**)&rec2_d, (size_t)N * RS2 * sizeof(double)) != cudaSuccess) { cudaFree(rec_d); cleanup(); SGP_FAIL(ctx, SGP_ERR_CUDA, "closed form: out of memory"); }
+            rec2_d = take((size_t)N * RS2);
             cf_pack_kernel<<<nb((size_t)N, 128), 128, 0, ctx->stream>>>(rec_d, rec2_d, N, d);
             switch (d) {
                 case 1: cf_psi2_fast_kernel<1><<<grid, 256, 0, ctx->stream>>>(rec2_d, ctx->Z_dev, ctx->exptab_dev, ctx->work_dev, N, M, nsplit); break;
@@ -497,15 +507,12 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
                 case 3: cf_psi2_fast_kernel<3><<<grid, 256, 0, ctx->stream>>>(rec2_d, ctx->Z_dev, ctx->exptab_dev, ctx->work_dev, N, M, nsplit); break;
                 default: cf_psi2_fast_kernel<4><<<grid, 256, 0, ctx->stream>>>(rec2_d, ctx->Z_dev, ctx->exptab_dev, ctx->work_dev, N, M, nsplit); break;
             }
-            cudaStreamSynchronize(ctx->stream);
-            cudaFree(rec2_d);
         } else {
             cf_psi2_kernel<<<grid, 256, 64 * RS * sizeof(double), ctx->stream>>>(rec_d, ctx->Z_dev, ctx->work_dev, N, M, d, nsplit);
         }
         cf_finish_kernel<<<nb(MM), 256, 0, ctx->stream>>>(ctx->work_dev, ctx->Z_dev, ell_inv_d, s_psi2, M, d, nsplit);
         set_scal_kernel<<<1, 1, 0, ctx->stream>>>(s_scal, ctx->variance * (double)N, (double)N);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        cudaFree(rec_d);
         if (e != cudaSuccess) { ctx->err = std::string("closed-form kernels: ") + cudaGetErrorString(e); cleanup(); return SGP_ERR_CUDA; }
         ctx->last_launches = 5;
     }
@@ -513,15 +520,14 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
     if (need_p1n) {
         // Psi1 (M x D_out) = Psi1_n (M x N) * R (N x D_out); R == NULL -> ones
         if (!R_d) {
-            UC(cudaMalloc((void**)&R_d, (size_t)N * sizeof(double)));
+            R_d = take((size_t)N);
             std::vector<double> ones((size_t)N, 1.0);
             UC(cudaMemcpyAsync(R_d, ones.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             UC(cudaStreamSynchronize(ctx->stream));
         }
         if (D_out <= 4) {
-            const int nsplit = (int)std::max<long long>(1, std::min<long long>(512, N / 64));
-            double* part = nullptr;
-            UC(cudaMalloc((void**)&part, (size_t)nsplit * D_out * M * sizeof(double)));
+            const int nsplit = psi1_split;
+            double* part = take((size_t)nsplit * D_out * M);
             dim3 g((M + 127) / 128, nsplit);
             switch (D_out) {
                 case 1: psi1_split_kernel<1><<<g, 128, 0, ctx->stream>>>(p1n_d, R_d, part, N, M, nsplit); break;
@@ -530,9 +536,6 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
                 default: psi1_split_kernel<4><<<g, 128, 0, ctx->stream>>>(p1n_d, R_d, part, N, M, nsplit); break;
             }
             psi1_finish_kernel<<<nb((size_t)M * D_out), 256, 0, ctx->stream>>>(part, s_psi1, M, D_out, nsplit);
-            cudaError_t e = cudaStreamSynchronize(ctx->stream);
-            cudaFree(part);
-            if (e != cudaSuccess) { ctx->err = std::string("psi1 reduction: ") + cudaGetErrorString(e); cleanup(); return SGP_ERR_CUDA; }
         } else {
             rc = sgp_gemm(ctx, 0, 0, M, D_out, (int)N, 1.0, p1n_d, M, R_d, (int)N, 0.0, s_psi1, M, 0);
             if (rc) { cleanup(); return rc; }
