@@ -46,7 +46,7 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     // one persistent CTA per SM; the (tile, chunk) sequence is cut into equally heavy contiguous slices.  Cost weights
     // of one chunk (measured per-chunk clocks, see profiles/): off-diagonal 2*TM generated rows + TM^2 MMA, diagonal TM
     // rows + the MMA blocks on or below the diagonal
-    int w_diag = 17, w_off = 24, w_fixed = 17;
+    int w_diag = 15, w_off = 24, w_fixed = 17;
     if (const char* e = std::getenv("SGP_SWEEP_WEIGHTS")) {
         int a_ = 0, b_ = 0, c_ = -1;
         int got = std::sscanf(e, "%d,%d,%d", &a_, &b_, &c_);

@@ -311,16 +311,18 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
 
     // MMA mapping.  Off-diagonal tile: WR x 4 warps, a WM x WN register tile each.  Diagonal tile: only the lower triangle
     // is needed (the reduce kernel mirrors it), i.e. 10 of the 16 SB x SB sub-blocks (SB = TM/4).  They are dealt out so
-    // that every scheduler (warps w and w+4) gets at most 3: slot 0 for every warp, slot 1 for warps 0 and 1 only.
+    // that every scheduler (warps w and w+4) gets exactly 2.5: slot 0 = one sub-block for every warp (the off-diagonal ones to
+    // warps 0-3, the diagonal ones to warps 4-7), slot 1 = HALF a sub-block (SB x SB/2) for warps 0-3: (2,0) left / right,
+    // (3,0) left / right.  40 DMMAs per k-step and scheduler instead of 64.
     constexpr int SB = TM / 4, SI = SB / 8;
     static_assert(!DIAG || NWARPS == 8, "diagonal sub-block schedule is written for 8 warps");
     const int wr = warp >> 2, wc = warp & 3;
     const int s0r = (0x32103321 >> (4 * warp)) & 0xf, s0c = (0x32102110 >> (4 * warp)) & 0xf;   // warps 7..0: rows 3,2,1,0,3,3,2,1
-    const int s1r = warp == 0 ? 2 : 3, s1c = 0;                                               // slot 1: (2,0) / (3,0)
-    const bool has1 = DIAG && warp < 2;
+    const int s1r = warp < 2 ? 2 : 3, s1c0 = (warp & 1) * (SB / 2);                           // slot 1: column half of (2,0) / (3,0)
+    const bool has1 = DIAG && warp < 4;
     const int a_off = (DIAG ? s0r * SB : wr * WM) + (lane >> 2);              // + 8*i
     const int b_off = (DIAG ? s0c * SB : TM + wc * WN) + (lane >> 2);         // + 8*j
-    const int a1_off = s1r * SB + (lane >> 2), b1_off = s1c * SB + (lane >> 2);
+    const int a1_off = s1r * SB + (lane >> 2), b1_off = s1c0 + (lane >> 2);
     const int kq = lane & 3;
     constexpr int AI = DIAG ? 2 * SI : MI, AJ = DIAG ? SI : NJ;      // accumulator blocks (diagonal: slot s = rows [s*SI, (s+1)*SI))
     double acc[AI][AJ][2];
@@ -345,6 +347,7 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     auto body = [&](auto gen_tag, const int c) {
         constexpr bool GEN = decltype(gen_tag)::value;
         constexpr int FI = DIAG ? SI : MI, FJ = DIAG ? SI : NJ;   // fragment blocks of the (slot-0) tile
+        constexpr int FJ1 = (FJ + 1) / 2;                        // slot 1 of a diagonal tile: half the columns
         constexpr int DPK = FI * FJ;                  // DMMAs per k-step (diagonal: of slot 0)
         constexpr int TOTAL = KSPAN * DPK;            // DMMAs one generator unit is interleaved with
         static_assert(TOTAL >= NST, "generator schedule");
@@ -368,20 +371,20 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
                     const double* row = Kc + ((ks0 + kk) * 4 + kq) * LD;
                     if (DIAG && kk > 0 && has1) {      // slot 1 of the previous k-step (a, b are free to be overwritten)
                         const double* prow_ = row - 4 * LD;
-                        double a1[FI], b1[FJ];
+                        double a1[FI], b1[FJ1];
 #pragma unroll
                         for (int ii = 0; ii < FI; ++ii) a1[ii] = prow_[a1_off + 8 * ii];
 #pragma unroll
-                        for (int jj = 0; jj < FJ; ++jj) b1[jj] = prow_[b1_off + 8 * jj];
+                        for (int jj = 0; jj < FJ1; ++jj) b1[jj] = prow_[b1_off + 8 * jj];
                         if (WEIGHTED) {
                             const double wn = rc[((ks0 + kk - 1) * 4 + kq) * REC + DPAD + 2];
 #pragma unroll
-                            for (int jj = 0; jj < FJ; ++jj) b1[jj] *= wn;
+                            for (int jj = 0; jj < FJ1; ++jj) b1[jj] *= wn;
                         }
 #pragma unroll
                         for (int ii = 0; ii < FI; ++ii)
 #pragma unroll
-                            for (int jj = 0; jj < FJ; ++jj) dmma884_nv(acc[(DIAG ? FI : 0) + ii][jj][0], acc[(DIAG ? FI : 0) + ii][jj][1], a1[ii], b1[jj]);
+                            for (int jj = 0; jj < FJ1; ++jj) dmma884_nv(acc[(DIAG ? FI : 0) + ii][jj][0], acc[(DIAG ? FI : 0) + ii][jj][1], a1[ii], b1[jj]);
                     }
 #pragma unroll
                     for (int ii = 0; ii < FI; ++ii) a[ii] = row[a_off + 8 * ii];
@@ -406,20 +409,20 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
             });
             if (has1) {      // slot 1 of the unit's last k-step
                 const double* row = Kc + ((ks0 + KSPAN - 1) * 4 + kq) * LD;
-                double a1[FI], b1[FJ];
+                double a1[FI], b1[FJ1];
 #pragma unroll
                 for (int ii = 0; ii < FI; ++ii) a1[ii] = row[a1_off + 8 * ii];
 #pragma unroll
-                for (int jj = 0; jj < FJ; ++jj) b1[jj] = row[b1_off + 8 * jj];
+                for (int jj = 0; jj < FJ1; ++jj) b1[jj] = row[b1_off + 8 * jj];
                 if (WEIGHTED) {
                     const double wn = rc[((ks0 + KSPAN - 1) * 4 + kq) * REC + DPAD + 2];
 #pragma unroll
-                    for (int jj = 0; jj < FJ; ++jj) b1[jj] *= wn;
+                    for (int jj = 0; jj < FJ1; ++jj) b1[jj] *= wn;
                 }
 #pragma unroll
                 for (int ii = 0; ii < FI; ++ii)
 #pragma unroll
-                    for (int jj = 0; jj < FJ; ++jj) dmma884_nv(acc[(DIAG ? FI : 0) + ii][jj][0], acc[(DIAG ? FI : 0) + ii][jj][1], a1[ii], b1[jj]);
+                    for (int jj = 0; jj < FJ1; ++jj) dmma884_nv(acc[(DIAG ? FI : 0) + ii][jj][0], acc[(DIAG ? FI : 0) + ii][jj][1], a1[ii], b1[jj]);
             }
         }
 #ifndef SGP_DBG_NOBAR
@@ -435,11 +438,11 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
             if (sl == 1 && !has1) break;
-            const int r0 = (sl ? s1r : s0r) * SB, c0 = (sl ? s1c : s0c) * SB;
+            const int r0 = (sl ? s1r : s0r) * SB, c0 = sl ? s1c0 : s0c * SB;
 #pragma unroll
             for (int i = 0; i < SI; ++i)
 #pragma unroll
-                for (int j = 0; j < SI; ++j) {
+                for (int j = 0; j < (sl ? (SI + 1) / 2 : SI); ++j) {
                     const int rr = r0 + 8 * i + (lane >> 2), cc = c0 + 8 * j + 2 * (lane & 3);
                     *reinterpret_cast<double2*>(out + rr * TM + cc) = make_double2(acc[sl * SI + i][j][0], acc[sl * SI + i][j][1]);
                 }
