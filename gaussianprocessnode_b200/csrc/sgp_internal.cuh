@@ -47,6 +47,8 @@ struct sgp_ctx {
     // scratch
     double* work_dev = nullptr;  size_t work_cap = 0;      // split-N partials
     double* zrec_dev = nullptr;  size_t zrec_cap = 0;      // prepared inducing rows
+    double* kbuf_dev = nullptr;  size_t kbuf_cap = 0;      // L2-resident K_uf panel of one slab (generate-once sweep)
+    unsigned* sweep_flags_dev = nullptr;                   // generation / consumption counters of the generate-once sweep
     double* exptab_dev = nullptr;
     double* dense_dev = nullptr; size_t dense_cap = 0;     // M x M scratch for factorisations
     int* info_dev = nullptr;

@@ -25,17 +25,93 @@
 // Roofline: FP64 DMMA pipe (measured 37.0 TFLOP/s on this pool's B200; cuBLAS DGEMM 35.5).  The generator's 16
 // instructions per value are paid from the same budget: (TI+TJ)*16 / (TI*TJ) = 25 % on top of the MMA work for a 128x128
 // off-diagonal tile.
-#include "sweep_kernel.cuh"
+#include "sweep4_kernel.cuh"
 
 using namespace sgp_sweep;
 
 int sgp_sweep_chunk() { return 32; }
+
+// ---- generate-once sweep (sweep4_kernel.cuh): every K_uf value is generated once per sweep into an L2-resident slab panel and
+// consumed by a TMA-fed DMMA SYRK.  Returns 1 when the shape is outside its range (nblk > CTAs): the caller falls back.
+static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const double* yv, const double* w, int64_t N, bool time_main) {
+    namespace s4 = sgp_sweep4;
+    constexpr int NB = 32;
+    const int M = ctx->M, D = ctx->D;
+    const int dpad = D <= 4 ? 4 : D <= 8 ? 8 : 16;
+    const int TM = (M > 192) ? 128 : 64;
+    const int nblk = (M + TM - 1) / TM;
+    const int ntiles = nblk * (nblk + 1) / 2;
+    const long long chunks = (N + NB - 1) / NB;
+    // slab: as many chunks as keep the panel (nblk x 32 x (TM + 4) doubles per chunk) inside the L2 budget
+    double slab_mb = 32.0;        // per panel; the ring holds three
+    if (const char* e = std::getenv("SGP_SWEEP_SLAB_MB")) { double v = std::atof(e); if (v > 0.0) slab_mb = v; }
+    const size_t chunk_doubles = (size_t)nblk * NB * (TM + 4);
+    long long max_slab = (long long)(slab_mb * 1048576.0 / (chunk_doubles * sizeof(double)));
+    if (max_slab < 8) max_slab = 8;
+    const int nslabs = (int)((chunks + max_slab - 1) / max_slab);
+    const long long slab_chunks = (chunks + nslabs - 1) / nslabs;
+    int w_diag = 5, w_off = 8, w_fixed = 64;          // per k-step (4 points) / per segment, from the per-segment clock fit (tools/profile_sweep.py)
+    if (const char* e = std::getenv("SGP_SWEEP4_WEIGHTS")) {
+        int a_ = 0, b_ = 0, c_ = -1;
+        int got = std::sscanf(e, "%d,%d,%d", &a_, &b_, &c_);
+        if (got >= 2 && a_ > 0 && b_ > 0) { w_diag = a_; w_off = b_; if (got == 3 && c_ >= 0) w_fixed = c_; }
+    }
+    const long long slab_units = slab_chunks * (NB / 4);
+    const long long total_cost = slab_units * ((long long)nblk * w_diag + (long long)(ntiles - nblk) * w_off) + (long long)ntiles * w_fixed;
+    const int ncta = (int)std::min<long long>(std::min(ctx->num_sms, 256), std::max<long long>(1, slab_chunks * ntiles));
+    if (nblk > ncta || ntiles / ncta + 2 > 60 || slab_units > 2000000000ll) return 1;
+    const int nslots = ncta + ntiles;
+
+    size_t need_work = (size_t)nslots * TM * TM + (size_t)ncta * TM + (size_t)ncta * 2 + 2;
+    int rc = sgp_ensure(ctx, &ctx->work_dev, &ctx->work_cap, need_work); if (rc) return rc;
+    const int nring = nslabs > 2 ? 3 : nslabs;
+    rc = sgp_ensure(ctx, &ctx->kbuf_dev, &ctx->kbuf_cap, (size_t)nring * slab_chunks * chunk_doubles); if (rc) return rc;
+    if (3 * (nblk + 1) > 1024) return 1;
+    if (!ctx->sweep_flags_dev) SGP_CUDA(ctx, cudaMalloc((void**)&ctx->sweep_flags_dev, 1024 * sizeof(unsigned)));
+    SGP_CUDA(ctx, cudaMemsetAsync(ctx->sweep_flags_dev, 0, (size_t)nring * (nblk + 1) * sizeof(unsigned), ctx->stream));
+    size_t need_stats = (size_t)M * M + (size_t)M + 8;
+    rc = sgp_ensure(ctx, &ctx->stats_dev, &ctx->stats_cap, need_stats); if (rc) return rc;
+    ctx->Dout = 1;
+
+    s4::Params p{};
+    p.X = X; p.y = y; p.yv = yv; p.w = w; p.N = N; p.chunks = chunks; p.slab_chunks = slab_chunks; p.slab_units = slab_units; p.nslabs = nslabs;
+    p.M = M; p.D = D; p.ntiles = ntiles; p.nblk = nblk; p.ncta = ncta;
+    p.total_cost = total_cost; p.w_diag = w_diag; p.w_off = w_off; p.w_fixed = w_fixed; p.dbg = (nslots + 2 * ncta <= 8192) ? ctx->sweep_dbg_dev : nullptr;
+    if (p.dbg) { SGP_CUDA(ctx, cudaMemsetAsync(p.dbg, 0xff, (size_t)(nslots + 2 * ncta) * 4 * sizeof(long long), ctx->stream)); ctx->sweep_dbg_slots = nslots + 2 * ncta; }
+    const double sq = std::sqrt(SGP_EXP_SCALE);
+    for (int d = 0; d < SGP_MAX_D; ++d) { p.inv_ell_s[d] = d < D ? sq / ctx->ell[d] : 0.0; p.center[d] = d < D ? ctx->center[d] : 0.0; }
+    p.log_var_s = SGP_EXP_SCALE * std::log(ctx->variance); p.variance = ctx->variance;
+    p.Z = ctx->Z_dev; p.exptab = ctx->exptab_dev; p.Kbuf = ctx->kbuf_dev; p.flags = ctx->sweep_flags_dev;
+    p.slab_doubles = (long long)(slab_chunks * chunk_doubles); p.nring = nring;
+    p.partial = ctx->work_dev; p.psi1_partial = p.partial + (size_t)nslots * TM * TM; p.scal_partial = p.psi1_partial + (size_t)ncta * TM;
+    p.psi2 = ctx->stats_dev; p.psi1 = p.psi2 + (size_t)M * M; p.scal = p.psi1 + M;
+
+    if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (ctx->kind == SGP_KERNEL_SE) rc = s4::launch4_se(ctx, p, w != nullptr, ncta, dpad, TM);
+    else if (ctx->kind == SGP_KERNEL_MATERN32) rc = s4::launch4_m32(ctx, p, w != nullptr, ncta, dpad, TM);
+    else rc = s4::launch4_m52(ctx, p, w != nullptr, ncta, dpad, TM);
+    if (rc) return rc;
+    if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    SGP_CUDA(ctx, cudaGetLastError());
+    ctx->last_launches = 1;
+    ctx->have_stats = true;
+    return SGP_OK;
+}
 
 // Runs the whole sweep on device-resident data; statistics land in ctx->stats_dev.
 int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const double* yv, const double* w, int64_t N, int64_t Ncap,
                      bool time_main) {
     if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: set_kernel and set_inducing first");
     constexpr int NB = 32;
+    {
+        const long long chunks_ = (N + NB - 1) / NB;
+        if (chunks_ * NB > Ncap) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: data buffers must be padded to a multiple of 32 points");
+        const char* impl = std::getenv("SGP_SWEEP_IMPL");
+        if (!(impl && impl[0] == '3')) {
+            int rc4 = sweep_launch4(ctx, X, y, yv, w, N, time_main);
+            if (rc4 <= 0) return rc4;      // 1 = shape outside the generate-once kernel's range: fall through
+        }
+    }
     const int M = ctx->M, D = ctx->D;
     const int dpad = D <= 4 ? 4 : D <= 8 ? 8 : 16;
     const int TM = (M > 192) ? 128 : 64;

@@ -141,10 +141,13 @@ def test_pinned_buffers_and_segment_clocks(ctx):
     assert fro(psi2, o2) <= TOL and fro(psi1, o1) <= TOL
     rec = ctx.sweep_debug_clocks()
     rec = rec[rec[:, 0] >= 0]
+    seg = rec[rec[:, 2] < 2]                                   # segment records {k-steps, clocks, is_diagonal, cta}; 2 / 3 = generator / waits
     ntiles = 3                                                 # M = 256 -> 2 x 2 blocks of 128 -> 3 lower-triangle tiles
-    assert len(rec) >= ntiles and rec[:, 1].min() > 0
+    assert len(seg) >= ntiles and seg[:, 1].min() > 0
     chunks = (N + 31) // 32
-    assert rec[:, 0].sum() == chunks * ntiles                  # every (tile, chunk) pair is processed exactly once
+    assert seg[:, 0].sum() == 8 * chunks * ntiles              # every (tile, k-step of 4 points) pair is processed exactly once
+    gen = rec[rec[:, 2] == 2]
+    assert gen[:, 0].sum() == chunks * 2                       # every (row block, chunk) of K_uf is generated exactly once
 
 
 def test_far_points_underflow_to_zero(ctx):

@@ -23,11 +23,28 @@ for _ in range(reps):
 if "--clocks" in sys.argv:
     r = ctx.sweep_debug_clocks()
     r = r[r[:, 0] >= 0]
+    if os.environ.get("SGP_SWEEP_IMPL", "4") != "3":
+        r = r.astype(float); r[r[:, 2] < 2, 0] /= 8.0        # the generate-once kernel records k-steps (1/8 chunk)
     for dg in (0, 1):
         q = r[r[:, 2] == dg]
         if len(q):
             print("diag=%d: %d segments, clocks/chunk mean %.0f (min %.0f max %.0f)" % (dg, len(q), (q[:, 1].sum() / q[:, 0].sum()),
                   (q[:, 1] / q[:, 0]).min(), (q[:, 1] / q[:, 0]).max()))
+    for dg, name in ((2, "generator (clocks per generated block-chunk)"), (3, "dependency waits (clocks per sweep)")):
+        q = r[r[:, 2] == dg]
+        if len(q):
+            print("%s: mean %.0f max %.0f; per-CTA total clocks mean %.3e max %.3e" % (name, q[:, 1].sum() / max(q[:, 0].sum(), 1),
+                  (q[:, 1] / np.maximum(q[:, 0], 1)).max(), q[:, 1].mean(), q[:, 1].max()))
+    r = r[r[:, 2] < 2]
+    for dg in (0, 1):       # least-squares  clocks = a * chunks + b  over the segments (per slab pass: b is per segment and slab)
+        q = r[r[:, 2] == dg].astype(float)
+        if len(q) > 2 and q[:, 0].std() > 0:
+            A = np.stack([q[:, 0], np.ones(len(q))], 1)
+            (a_, b_), *_ = np.linalg.lstsq(A, q[:, 1], rcond=None)
+            print("diag=%d fit: %.0f clocks per chunk + %.0f per segment (summed over slabs)" % (dg, a_, b_))
+    if "--dump" in sys.argv:
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savetxt("gpurun_out/segments_N%d_M%d.csv" % (N, M), r, fmt="%d", delimiter=",", header="chunks,clocks,diag,cta")
     per_cta = {}
     for ch, clk, dg, cta in r:
         per_cta[cta] = per_cta.get(cta, 0) + clk
