@@ -548,82 +548,96 @@ __host__ __device__ inline int gen_lo(int b, int ncta, int nblk) { return (int)(
 template <int TM, int NT>
 __device__ __forceinline__ void reduce_items4(const Params& p, double* __restrict__ S_, int* __restrict__ ibuf) {
     constexpr int SR = 4, STRIPES = TM / SR, NWARPS = NT / 32, LDS_ = TM + 1;
+    constexpr int NBATCH = 4;                        // stripes whose loads are in flight together (S_ holds NBATCH stripes)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nitems = p.ntiles * STRIPES;
     const int it0 = (int)((long long)nitems * blockIdx.x / gridDim.x), it1 = (int)((long long)nitems * (blockIdx.x + 1) / gridDim.x);
     int* slots = ibuf + NWARPS;
-    int cur_tile = -1, nseg = 0, I = 0, J = 0;
-    for (int it = it0; it < it1; ++it) {
-        const int tile = it / STRIPES, stripe = it - tile * STRIPES;
-        if (tile != cur_tile) {
-            cur_tile = tile;
-            long long pre = 0;
-            I = 0; J = 0;
-            for (int t = 0; t < tile; ++t) {
-                pre += (long long)(I == J ? p.w_diag : p.w_off) * p.slab_units + p.w_fixed;
-                if (++J > I) { ++I; J = 0; }
-            }
-            int mine = 0;
-            if (tid < p.ncta) {
-                long long lo, hi;
-                seg_range(cta_pos(p.total_cost, p.ncta, tid), cta_pos(p.total_cost, p.ncta, tid + 1), pre, I == J ? p.w_diag : p.w_off, p.w_fixed,
-                          p.slab_units, lo, hi);
-                mine = lo < hi;
-            }
-            const unsigned ballot = __ballot_sync(0xffffffffu, mine);
-            __syncthreads();
-            if (lane == 0) ibuf[warp] = (int)ballot;
-            nseg = __syncthreads_count(mine);
-            if (mine) {
-                int before = __popc(ballot & ((1u << lane) - 1u));
-                for (int wq = 0; wq < warp; ++wq) before += __popc((unsigned)ibuf[wq]);
-                slots[before] = tid + tile;
-            }
+    int it = it0;
+    while (it < it1) {
+        const int tile = it / STRIPES;
+        const int s_lo = it - tile * STRIPES, s_hi = min(STRIPES, s_lo + (it1 - it));      // this CTA's stripes of the tile
+        // the tile's workspace slots in CTA order: one candidate CTA per thread (ncta <= NT)
+        long long pre = 0;
+        int I = 0, J = 0;
+        for (int t = 0; t < tile; ++t) {
+            pre += (long long)(I == J ? p.w_diag : p.w_off) * p.slab_units + p.w_fixed;
+            if (++J > I) { ++I; J = 0; }
+        }
+        int mine = 0;
+        if (tid < p.ncta) {
+            long long lo, hi;
+            seg_range(cta_pos(p.total_cost, p.ncta, tid), cta_pos(p.total_cost, p.ncta, tid + 1), pre, I == J ? p.w_diag : p.w_off, p.w_fixed,
+                      p.slab_units, lo, hi);
+            mine = lo < hi;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, mine);
+        __syncthreads();                                     // the previous tile is done with ibuf / S_
+        if (lane == 0) ibuf[warp] = (int)ballot;
+        const int nseg = __syncthreads_count(mine);
+        if (mine) {
+            int before = __popc(ballot & ((1u << lane) - 1u));
+            for (int wq = 0; wq < warp; ++wq) before += __popc((unsigned)ibuf[wq]);
+            slots[before] = tid + tile;
         }
         __syncthreads();
         const bool diag = (I == J);
-        const int r0 = stripe * SR;
-        if (tid < SR * TM / 2) {
-            const int e = 2 * tid, rl = e / TM, c = e - rl * TM, r = r0 + rl;
-            double2 v = make_double2(0.0, 0.0);
-            if (!diag || c <= r) {
-                const double* src = p.partial + (size_t)r * TM + c;
+        for (int sb = s_lo; sb < s_hi; sb += NBATCH) {
+            const int nb = min(NBATCH, s_hi - sb);
+            if (tid < SR * TM / 2) {
+                const int e = 2 * tid, rl = e / TM, c = e - rl * TM;
+                double2 v[NBATCH];
+#pragma unroll
+                for (int q = 0; q < NBATCH; ++q) v[q] = make_double2(0.0, 0.0);
+                const double* src = p.partial + (size_t)(sb * SR + rl) * TM + c;
 #pragma unroll 8
                 for (int sq = 0; sq < nseg; ++sq) {
-                    const double2 x = __ldcg(reinterpret_cast<const double2*>(src + (size_t)slots[sq] * (TM * TM)));
-                    v.x += x.x; v.y += x.y;
+                    const double* ps = src + (size_t)slots[sq] * (TM * TM);
+#pragma unroll
+                    for (int q = 0; q < NBATCH; ++q)
+                        if (q < nb && (!diag || c <= (sb + q) * SR + rl)) {
+                            const double2 x = __ldcg(reinterpret_cast<const double2*>(ps + (size_t)q * SR * TM));
+                            v[q].x += x.x; v[q].y += x.y;
+                        }
+                }
+#pragma unroll
+                for (int q = 0; q < NBATCH; ++q) { S_[(q * SR + rl) * LDS_ + c] = v[q].x; S_[(q * SR + rl) * LDS_ + c + 1] = v[q].y; }
+            }
+            __syncthreads();
+            for (int q = 0; q < nb; ++q) {
+                const int r0 = (sb + q) * SR;
+                const double* Sq = S_ + (size_t)q * SR * LDS_;
+                for (int e = tid; e < SR * TM; e += NT) {
+                    {   // psi2[gi + gj*M]: SR consecutive rows = one 32-byte sector per column
+                        const int rl = e % SR, c = e / SR, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
+                        if (gi < p.M && gj < p.M && (!diag || c <= r)) p.psi2[(size_t)gi + (size_t)gj * p.M] = Sq[rl * LDS_ + c];
+                    }
+                    {   // mirror psi2[gj + gi*M]: consecutive threads -> consecutive columns
+                        const int rl = e / TM, c = e % TM, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
+                        if (gi < p.M && gj < p.M && (diag ? c < r : true)) p.psi2[(size_t)gj + (size_t)gi * p.M] = Sq[rl * LDS_ + c];
+                    }
+                }
+                if (diag && tid < SR) {
+                    const int r = r0 + tid, gi = I * TM + r;
+                    if (gi < p.M) {
+                        double v = 0.0;
+                        const int lo = gen_lo(I, p.ncta, p.nblk), hi = gen_lo(I + 1, p.ncta, p.nblk);
+                        for (int qq = lo; qq < hi; ++qq) v += __ldcg(p.psi1_partial + (size_t)qq * TM + r);
+                        p.psi1[gi] = v;
+                    }
                 }
             }
-            S_[rl * LDS_ + c] = v.x; S_[rl * LDS_ + c + 1] = v.y;
+            __syncthreads();                                 // S_ is reused by the next batch
         }
-        __syncthreads();
-        for (int e = tid; e < SR * TM; e += NT) {
-            {
-                const int rl = e % SR, c = e / SR, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
-                if (gi < p.M && gj < p.M && (!diag || c <= r)) p.psi2[(size_t)gi + (size_t)gj * p.M] = S_[rl * LDS_ + c];
-            }
-            {
-                const int rl = e / TM, c = e % TM, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
-                if (gi < p.M && gj < p.M && (diag ? c < r : true)) p.psi2[(size_t)gj + (size_t)gi * p.M] = S_[rl * LDS_ + c];
-            }
-        }
-        if (diag && tid < SR) {
-            const int r = r0 + tid, gi = I * TM + r;
-            if (gi < p.M) {
-                double v = 0.0;
-                const int lo = gen_lo(I, p.ncta, p.nblk), hi = gen_lo(I + 1, p.ncta, p.nblk);
-                for (int q = lo; q < hi; ++q) v += __ldcg(p.psi1_partial + (size_t)q * TM + r);
-                p.psi1[gi] = v;
-            }
-        }
-        if (tile == 0 && stripe == 0 && tid == 0) {
+        if (tile == 0 && s_lo == 0 && tid == 0) {
             double sw = 0.0, sy = 0.0;
             for (int q = 0; q < p.ncta; ++q) { sw += __ldcg(p.scal_partial + 2 * q); sy += __ldcg(p.scal_partial + 2 * q + 1); }
-            p.scal[0] = p.variance * sw;
-            p.scal[1] = sy;
+            p.scal[0] = p.variance * sw;   // Psi0 = sum_n w_n k(x_n, x_n)
+            p.scal[1] = sy;                // sum_n w_n (ybar^2 + yvar)
             p.scal[2] = sw;
             p.scal[3] = (double)p.N;
         }
+        it += s_hi - s_lo;
     }
 }
 
@@ -641,6 +655,8 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     sm.xfull = sm.empty + kKStages;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long t_k0 = 0, t_k1 = 0;
+    if (p.dbg) t_k0 = clock64();
     if (tid == 0) {
         for (int s = 0; s < kKStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NWARPS); }
         for (int s = 0; s < kXStages; ++s) mbar_init(&sm.xfull[s], 1);
@@ -655,8 +671,8 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
         int I = 0, J = 0, ns = 0;
         for (int t = 0; t < p.ntiles && pre < q1; ++t) {
             const int wt = (I == J) ? p.w_diag : p.w_off;
-            long long lo, hi;
-            seg_range(q0, q1, pre, wt, p.w_fixed, p.slab_units, lo, hi);
+            long long lo = 0, hi = 0;
+            if (pre + (long long)wt * p.slab_units + p.w_fixed > q0) seg_range(q0, q1, pre, wt, p.w_fixed, p.slab_units, lo, hi);
             if (lo < hi && ns < kMaxSeg) {
                 int* e = sm.segtab + 8 * ns++;
                 e[0] = I; e[1] = J; e[2] = bcta + t; e[3] = (int)lo; e[4] = (int)hi;
@@ -721,6 +737,7 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
         if (p.dbg) { t_gen += clock64() - t0; n_gen += scs * (gk + 1) / gcnt - scs * gk / gcnt; }
     };
 
+    if (p.dbg) t_k1 = clock64();
     generate(0);
     for (int s = 0; s < p.nslabs; ++s) {
         if (s + 1 < p.nslabs) generate(s + 1);        // one slab ahead: the consumers of slab s + 1 will not wait for it
@@ -766,6 +783,8 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
         d[8 * bcta + 0] = n_gen; d[8 * bcta + 1] = t_gen; d[8 * bcta + 2] = 2; d[8 * bcta + 3] = bcta;
         d[8 * bcta + 4] = 1; d[8 * bcta + 5] = t_wait; d[8 * bcta + 6] = 3; d[8 * bcta + 7] = bcta;
     }
+    long long t_k2 = 0, t_k3 = 0;
+    if (p.dbg) t_k2 = clock64();
     // Psi1 rows of this CTA's generator block: sum over the eight point positions (lane / 4); lanes 0..3 hold two rows each
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb)
@@ -779,7 +798,13 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
         }
     __threadfence();
     grid.sync();
-    reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 8 * (TM + 1)));
+    if (p.dbg) t_k3 = clock64();
+    reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)));
+    if (p.dbg && tid == 0) {   // timeline of this CTA: {setup clocks, slab-loop clocks, 4, cta}, {final barrier clocks, phase-2 clocks, 5, cta}
+        long long* d = p.dbg + 4 * (size_t)(p.ncta + p.ntiles) + 8 * (size_t)p.ncta;
+        d[8 * bcta + 0] = t_k1 - t_k0; d[8 * bcta + 1] = t_k2 - t_k1; d[8 * bcta + 2] = 4; d[8 * bcta + 3] = bcta;
+        d[8 * bcta + 4] = t_k3 - t_k2; d[8 * bcta + 5] = clock64() - t_k3; d[8 * bcta + 6] = 5; d[8 * bcta + 7] = bcta;
+    }
 }
 
 template <int TM, int NB, int DPAD, int NT, int KIND>

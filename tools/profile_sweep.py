@@ -35,6 +35,10 @@ if "--clocks" in sys.argv:
         if len(q):
             print("%s: mean %.0f max %.0f; per-CTA total clocks mean %.3e max %.3e" % (name, q[:, 1].sum() / max(q[:, 0].sum(), 1),
                   (q[:, 1] / np.maximum(q[:, 0], 1)).max(), q[:, 1].mean(), q[:, 1].max()))
+    q4, q5 = r[r[:, 2] == 4], r[r[:, 2] == 5]
+    if len(q4):
+        print("timeline (clocks, mean / max over CTAs): setup %.0f / %.0f, slab loop %.0f / %.0f, final barrier %.0f / %.0f, phase 2 %.0f / %.0f" % (
+              q4[:, 0].mean(), q4[:, 0].max(), q4[:, 1].mean(), q4[:, 1].max(), q5[:, 0].mean(), q5[:, 0].max(), q5[:, 1].mean(), q5[:, 1].max()))
     r = r[r[:, 2] < 2]
     for dg in (0, 1):       # least-squares  clocks = a * chunks + b  over the segments (per slab pass: b is per segment and slab)
         q = r[r[:, 2] == dg].astype(float)
