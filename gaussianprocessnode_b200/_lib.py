@@ -42,6 +42,7 @@ SIGNATURES = {
     "sgp_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "sgp_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
     "sgp_sweep_timed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p]),
+    "sgp_sweep_timed_flushed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_float_p, c_float_p]),
     "sgp_last_sweep_info": (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "sgp_sweep_debug_clocks": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, c_int_p]),
     "sgp_stats_dev": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_void_pp, c_void_pp]),

@@ -129,10 +129,10 @@ void sgp_destroy(sgp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     sgp_comm_destroy(ctx);
     if (ctx->own_data) { cudaFree(ctx->X_dev); cudaFree(ctx->y_dev); cudaFree(ctx->yv_dev); cudaFree(ctx->w_dev); }
-    cudaFree(ctx->Z_dev); cudaFree(ctx->stats_dev); cudaFree(ctx->work_dev); cudaFree(ctx->zrec_dev); cudaFree(ctx->exptab_dev);
+    cudaFree(ctx->Z_dev); if (!ctx->stats_external) cudaFree(ctx->stats_dev); cudaFree(ctx->work_dev); cudaFree(ctx->zrec_dev); cudaFree(ctx->exptab_dev);
     cudaFree(ctx->dense_dev); cudaFree(ctx->info_dev); cudaFree(ctx->KuuL_dev); cudaFree(ctx->sp_X_dev); cudaFree(ctx->sp_w_dev);
     cudaFree(ctx->sp_y_dev); cudaFree(ctx->sweep_dbg_dev); cudaFree(ctx->theta_dev); cudaFree(ctx->Kinv_dev); cudaFree(ctx->kuu_dinv_dev);
-    cudaFree(ctx->dinv_dev); cudaFree(ctx->post_dev); cudaFree(ctx->unc_dev); cudaFree(ctx->kbuf_dev); cudaFree(ctx->sweep_flags_dev);
+    cudaFree(ctx->dinv_dev); cudaFree(ctx->post_dev); cudaFree(ctx->unc_dev); cudaFree(ctx->kbuf_dev); cudaFree(ctx->sweep_flags_dev); cudaFree(ctx->flush_dev);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -262,10 +262,12 @@ static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, d
 
 static int sweep_resident(sgp_ctx* ctx, bool time_main) {
     if (ctx->N <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: no data (sgp_set_data)");
+    ctx->want_exchange = true;
     int rc = sgp_sweep_launch(ctx, ctx->X_dev, ctx->y_dev, ctx->have_yv ? ctx->yv_dev : nullptr, ctx->have_w ? ctx->w_dev : nullptr, ctx->N,
                               ctx->Ncap, time_main);
+    ctx->want_exchange = false;
     if (rc) return rc;
-    if (ctx->comm) {
+    if (ctx->comm && !ctx->last_sweep_exchanged) {       // (the generate-once kernel exchanges over peer memory inside its own launch)
         size_t cnt = (size_t)ctx->M * ctx->M + (size_t)ctx->M * ctx->Dout + 4;
         rc = sgp_comm_allreduce(ctx, ctx->stats_dev, cnt); if (rc) return rc;
         ctx->last_launches += 1;
@@ -314,6 +316,46 @@ int sgp_sweep_timed(sgp_ctx* ctx, int reps, float* ms_per_sweep, float* ms_main_
     float ms = 0.f; SGP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); main_sum += ms;
     float tot = 0.f; SGP_CUDA(ctx, cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[1]));
     if (ms_per_sweep) *ms_per_sweep = tot / reps;
+    if (ms_main_kernel) *ms_main_kernel = (float)(main_sum / reps);
+    ctx->last_main_ms = (float)(main_sum / reps);
+    return SGP_OK;
+}
+
+int sgp_sweep_timed_flushed(sgp_ctx* ctx, int reps, int flush_mb, float* ms_per_sweep, float* ms_main_kernel) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (reps < 1 || reps > 4096 || flush_mb < 0) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep_timed_flushed: 1 <= reps <= 4096, flush_mb >= 0");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const size_t fbytes = (size_t)flush_mb << 20;
+    if (fbytes > ctx->flush_cap) {
+        if (ctx->flush_dev) SGP_CUDA(ctx, cudaFree(ctx->flush_dev));
+        ctx->flush_dev = nullptr; ctx->flush_cap = 0;
+        SGP_CUDA(ctx, cudaMalloc(&ctx->flush_dev, fbytes));
+        ctx->flush_cap = fbytes;
+    }
+    // everything is enqueued without a host synchronisation: [flush] [e0] sweep (+ exchange) [e1] per repetition, so that the ranks of a
+    // multi-GPU job stay in lock step through the exchange itself instead of accumulating host-side launch skew
+    std::vector<cudaEvent_t> ev(4 * (size_t)reps, nullptr);
+    for (auto& e : ev) SGP_CUDA(ctx, cudaEventCreate(&e));
+    cudaEvent_t keep2 = ctx->ev[2], keep3 = ctx->ev[3];
+    int rc = SGP_OK;
+    for (int r = 0; r < reps && rc == SGP_OK; ++r) {
+        if (fbytes && cudaMemsetAsync(ctx->flush_dev, r & 0xff, fbytes, ctx->stream) != cudaSuccess) { rc = SGP_ERR_CUDA; break; }
+        if (cudaEventRecord(ev[4 * r], ctx->stream) != cudaSuccess) { rc = SGP_ERR_CUDA; break; }
+        ctx->ev[2] = ev[4 * r + 2]; ctx->ev[3] = ev[4 * r + 3];       // the launcher brackets the main kernel with ev[2] / ev[3]
+        rc = sweep_resident(ctx, true);
+        if (rc == SGP_OK && cudaEventRecord(ev[4 * r + 1], ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
+    }
+    ctx->ev[2] = keep2; ctx->ev[3] = keep3;
+    double tot = 0.0, main_sum = 0.0;
+    if (rc == SGP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
+    for (int r = 0; r < reps && rc == SGP_OK; ++r) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, ev[4 * r], ev[4 * r + 1]) != cudaSuccess || cudaEventElapsedTime(&b, ev[4 * r + 2], ev[4 * r + 3]) != cudaSuccess) rc = SGP_ERR_CUDA;
+        tot += a; main_sum += b;
+    }
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (rc != SGP_OK) { if (ctx->err.empty()) ctx->err = "sweep_timed_flushed: CUDA failure"; return rc; }
+    if (ms_per_sweep) *ms_per_sweep = (float)(tot / reps);
     if (ms_main_kernel) *ms_main_kernel = (float)(main_sum / reps);
     ctx->last_main_ms = (float)(main_sum / reps);
     return SGP_OK;

@@ -19,6 +19,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -33,6 +34,7 @@ NcclApi& api() {
     a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
     a.AllReduce = (decltype(a.AllReduce))dlsym(a.handle, "ncclAllReduce");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.handle, "ncclAllGather");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
     a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce;
     return a;
@@ -42,7 +44,80 @@ NcclApi& api() {
 struct SgpComm {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // fused peer-memory exchange (see SgpXchg): own region + the peers' regions mapped through CUDA IPC
+    bool p2p = false;
+    char* region = nullptr;
+    size_t cap_doubles = 0;
+    char* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned epoch = 0;
 };
+
+namespace {
+constexpr size_t kFlagBytes = 256;      // flags A [8] at 0, flags B [8] at 64
+
+// Collective over the communicator: allocate the exchange region, trade IPC handles through ncclAllGather, map the peers.
+// Any failure (ranks on different nodes, no peer access, ...) leaves p2p off on EVERY rank: the success flags are summed.
+void setup_p2p(sgp_ctx* ctx, SgpComm* c) {
+    NcclApi& a = api();
+    if (c->nranks < 2 || c->nranks > 8 || !a.AllGather) return;
+    if (const char* e = std::getenv("SGP_COMM_P2P")) if (e[0] == '0') return;
+    size_t maxM = 2048;
+    if (const char* e = std::getenv("SGP_COMM_P2P_MAXM")) { long v = std::atol(e); if (v >= 1) maxM = (size_t)v; }
+    const size_t cap = maxM * maxM + maxM + 64;
+    const size_t bytes = kFlagBytes + 2 * cap * sizeof(double);
+    bool ok = cudaMalloc((void**)&c->region, bytes) == cudaSuccess;
+    if (ok) ok = cudaMemset(c->region, 0, bytes) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok) ok = cudaIpcGetMemHandle(&mine, c->region) == cudaSuccess;
+    // handles (64 bytes each) + one success word per rank travel through NCCL
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    char* dev = nullptr;
+    std::vector<char> host(rec * c->nranks, 0);
+    bool ok_all = cudaMalloc((void**)&dev, rec * (c->nranks + 1)) == cudaSuccess;
+    if (ok_all) {
+        char mine_rec[sizeof(cudaIpcMemHandle_t) + 8];
+        memcpy(mine_rec, &mine, sizeof mine);
+        long long flag = ok ? 1 : 0;
+        memcpy(mine_rec + sizeof mine, &flag, 8);
+        ok_all = cudaMemcpyAsync(dev + rec * c->nranks, mine_rec, rec, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+        if (a.AllGather(dev + rec * c->nranks, dev, rec, /*ncclChar*/ 0, c->comm, ctx->stream) != 0) ok_all = false;
+        if (cudaMemcpyAsync(host.data(), dev, rec * c->nranks, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) ok_all = false;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok_all = false;
+    }
+    if (dev) cudaFree(dev);
+    int good = 0;
+    if (ok_all)
+        for (int q = 0; q < c->nranks; ++q) { long long f = 0; memcpy(&f, host.data() + rec * q + sizeof(cudaIpcMemHandle_t), 8); good += f == 1; }
+    bool mapped = ok_all && good == c->nranks;
+    if (mapped) {
+        for (int q = 0; q < c->nranks && mapped; ++q) {
+            if (q == c->rank) { c->peers[q] = c->region; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, host.data() + rec * q, sizeof h);
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mapped = false; }
+            c->peers[q] = (char*)ptr;
+        }
+    }
+    // second agreement round: every rank must have mapped every peer
+    int* dflag = nullptr;
+    int agreed = 0;
+    if (cudaMalloc((void**)&dflag, sizeof(int) * (c->nranks + 1)) == cudaSuccess) {
+        int v = mapped ? 1 : 0;
+        cudaMemcpyAsync(dflag + c->nranks, &v, sizeof v, cudaMemcpyHostToDevice, ctx->stream);
+        std::vector<int> all(c->nranks, 0);
+        if (a.AllGather(dflag + c->nranks, dflag, sizeof(int), 0, c->comm, ctx->stream) == 0 &&
+            cudaMemcpyAsync(all.data(), dflag, sizeof(int) * c->nranks, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+            cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+            for (int q = 0; q < c->nranks; ++q) agreed += all[q] == 1;
+        cudaFree(dflag);
+    }
+    if (agreed == c->nranks) { c->p2p = true; c->cap_doubles = cap; return; }
+    for (int q = 0; q < c->nranks; ++q) if (q != c->rank && c->peers[q]) { cudaIpcCloseMemHandle(c->peers[q]); c->peers[q] = nullptr; }
+    if (c->region) { cudaFree(c->region); c->region = nullptr; }
+}
+}  // namespace
 
 extern "C" int sgp_comm_unique_id(char id[128]) {
     if (!id) return SGP_ERR_ARG;
@@ -72,6 +147,7 @@ extern "C" int sgp_comm_init(sgp_ctx* ctx, int nranks, int rank, const char id[1
     }
     c->nranks = nranks; c->rank = rank;
     ctx->comm = c;
+    setup_p2p(ctx, c);
     return SGP_OK;
 }
 
@@ -86,9 +162,38 @@ int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count) {
     return SGP_OK;
 }
 
+bool sgp_comm_xchg(sgp_ctx* ctx, size_t need_doubles, SgpXchg* x) {
+    SgpComm* c = ctx->comm;
+    if (!c || !c->p2p || need_doubles > c->cap_doubles) return false;
+    x->nranks = c->nranks; x->rank = c->rank; x->epoch = ++c->epoch;
+    for (int q = 0; q < 8; ++q) x->peers[q] = c->peers[q];
+    x->xin_off = kFlagBytes; x->xout_off = kFlagBytes + c->cap_doubles * sizeof(double);
+    x->count = (long long)need_doubles;
+    return true;
+}
+
+int sgp_ensure_stats(sgp_ctx* ctx, size_t need) {
+    SgpComm* c = ctx->comm;
+    if (c && c->p2p && need <= c->cap_doubles) {
+        double* ext = reinterpret_cast<double*>(c->region + kFlagBytes + c->cap_doubles * sizeof(double));
+        if (ctx->stats_dev != ext) {
+            if (ctx->stats_dev && !ctx->stats_external) cudaFree(ctx->stats_dev);
+            ctx->stats_dev = ext; ctx->stats_cap = c->cap_doubles; ctx->stats_external = true; ctx->have_stats = false;
+        }
+        return SGP_OK;
+    }
+    if (ctx->stats_external) { ctx->stats_dev = nullptr; ctx->stats_cap = 0; ctx->stats_external = false; ctx->have_stats = false; }
+    return sgp_ensure(ctx, &ctx->stats_dev, &ctx->stats_cap, need);
+}
+
 void sgp_comm_destroy(sgp_ctx* ctx) {
     if (ctx && ctx->comm) {
         NcclApi& a = api();
+        SgpComm* c = ctx->comm;
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (ctx->stats_external) { ctx->stats_dev = nullptr; ctx->stats_cap = 0; ctx->stats_external = false; ctx->have_stats = false; }
+        for (int q = 0; q < 8; ++q) if (q != c->rank && c->peers[q]) cudaIpcCloseMemHandle(c->peers[q]);
+        if (c->region) cudaFree(c->region);
         if (a.ok && ctx->comm->comm) a.CommDestroy(ctx->comm->comm);
         delete ctx->comm;
         ctx->comm = nullptr;

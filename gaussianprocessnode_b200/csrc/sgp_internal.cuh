@@ -41,6 +41,7 @@ struct sgp_ctx {
     // statistics of the last sweep: stats_dev = [psi2 (M*M) | psi1 (M*Dout) | psi0 | sum_y2 | sum_w | n]
     double* stats_dev = nullptr;
     size_t stats_cap = 0;
+    bool stats_external = false;    // stats_dev lives in the peer-mapped exchange region of the communicator (comm.cu)
     int Dout = 1;
     bool have_stats = false;
 
@@ -48,6 +49,7 @@ struct sgp_ctx {
     double* work_dev = nullptr;  size_t work_cap = 0;      // split-N partials
     double* zrec_dev = nullptr;  size_t zrec_cap = 0;      // prepared inducing rows
     double* kbuf_dev = nullptr;  size_t kbuf_cap = 0;      // L2-resident K_uf panel of one slab (generate-once sweep)
+    void* flush_dev = nullptr; size_t flush_cap = 0;       // L2 flush buffer of sgp_sweep_timed_flushed
     unsigned* sweep_flags_dev = nullptr;                   // generation / consumption counters of the generate-once sweep
     double* exptab_dev = nullptr;
     double* dense_dev = nullptr; size_t dense_cap = 0;     // M x M scratch for factorisations
@@ -72,6 +74,8 @@ struct sgp_ctx {
 
     // last sweep launch record
     int last_launches = 0, last_grid = 0, last_block = 0, last_smem = 0;
+    bool want_exchange = false;           // set by the public sweep calls: theta / uncertain-input sweeps keep their statistics local
+    bool last_sweep_exchanged = false;    // the last sweep kernel already summed the statistics over the ranks
     float last_main_ms = 0.f;
     long long* sweep_dbg_dev = nullptr;   // optional per-segment clocks (sgp_sweep_debug_clocks)
     int sweep_dbg_slots = 0;
@@ -107,6 +111,17 @@ int sgp_dot(sgp_ctx* ctx, const double* a, size_t sa, const double* b, size_t sb
 // comm.cu
 int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count);
 void sgp_comm_destroy(sgp_ctx* ctx);
+// Peer-memory exchange fused into the sweep kernel (single node, <= 8 ranks): every rank owns a region
+// [flags A | flags B | xin (cap doubles) | xout (cap doubles)] that all peers map through CUDA IPC.
+struct SgpXchg {
+    int nranks = 1, rank = 0;
+    unsigned epoch = 0;            // barrier value of this sweep (flags are monotonic, never reset)
+    char* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // region of rank q as mapped here
+    size_t xin_off = 0, xout_off = 0;   // byte offsets inside a region; flags A at 0, flags B at 64
+    long long count = 0;           // doubles exchanged: M*M + M + 4
+};
+bool sgp_comm_xchg(sgp_ctx* ctx, size_t need_doubles, SgpXchg* x);     // fills x (and bumps the epoch) if the fused exchange is available
+int sgp_ensure_stats(sgp_ctx* ctx, size_t need_doubles);               // stats_dev: exchange region when available, else an own buffer
 
 // ---------------------------------------------------------------------------------------------------------------
 // device helpers

@@ -70,7 +70,7 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     if (!ctx->sweep_flags_dev) SGP_CUDA(ctx, cudaMalloc((void**)&ctx->sweep_flags_dev, 1024 * sizeof(unsigned)));
     SGP_CUDA(ctx, cudaMemsetAsync(ctx->sweep_flags_dev, 0, (size_t)nring * (nblk + 1) * sizeof(unsigned), ctx->stream));
     size_t need_stats = (size_t)M * M + (size_t)M + 8;
-    rc = sgp_ensure(ctx, &ctx->stats_dev, &ctx->stats_cap, need_stats); if (rc) return rc;
+    rc = sgp_ensure_stats(ctx, need_stats); if (rc) return rc;
     ctx->Dout = 1;
 
     s4::Params p{};
@@ -85,6 +85,13 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     p.slab_doubles = (long long)(slab_chunks * chunk_doubles); p.nring = nring;
     p.partial = ctx->work_dev; p.psi1_partial = p.partial + (size_t)nslots * TM * TM; p.scal_partial = p.psi1_partial + (size_t)ncta * TM;
     p.psi2 = ctx->stats_dev; p.psi1 = p.psi2 + (size_t)M * M; p.scal = p.psi1 + M;
+    // multi-GPU: phase 2 writes this rank's statistics into its exchange region and the kernel sums them over the ranks through peer
+    // memory (two-shot: every rank reduces 1/R of the buffer and stores the result into every rank's stats buffer)
+    ctx->last_sweep_exchanged = false;
+    if (ctx->want_exchange && sgp_comm_xchg(ctx, (size_t)M * M + M + 4, &p.xr)) {
+        p.psi2 = reinterpret_cast<double*>(p.xr.peers[p.xr.rank] + p.xr.xin_off); p.psi1 = p.psi2 + (size_t)M * M; p.scal = p.psi1 + M;
+        ctx->last_sweep_exchanged = true;
+    }
 
     if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     if (ctx->kind == SGP_KERNEL_SE) rc = s4::launch4_se(ctx, p, w != nullptr, ncta, dpad, TM);
@@ -112,6 +119,7 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
             if (rc4 <= 0) return rc4;      // 1 = shape outside the generate-once kernel's range: fall through
         }
     }
+    ctx->last_sweep_exchanged = false;
     const int M = ctx->M, D = ctx->D;
     const int dpad = D <= 4 ? 4 : D <= 8 ? 8 : 16;
     const int TM = (M > 192) ? 128 : 64;
@@ -136,7 +144,7 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     size_t need_work = (size_t)nslots * TM * TM + (size_t)nslots * TM + (size_t)nslots * 2 + 2;
     int rc = sgp_ensure(ctx, &ctx->work_dev, &ctx->work_cap, need_work); if (rc) return rc;
     size_t need_stats = (size_t)M * M + (size_t)M + 8;
-    rc = sgp_ensure(ctx, &ctx->stats_dev, &ctx->stats_cap, need_stats); if (rc) return rc;
+    rc = sgp_ensure_stats(ctx, need_stats); if (rc) return rc;
     ctx->Dout = 1;
 
     SweepParams p{};

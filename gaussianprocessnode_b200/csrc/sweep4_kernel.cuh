@@ -64,6 +64,7 @@ struct Params {
     double center[SGP_MAX_D];
     double log_var_s;
     double variance;
+    SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none)
 };
 
 __device__ __forceinline__ void mbar_wait_(unsigned long long* bar, unsigned parity) {
@@ -641,6 +642,67 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
     }
 }
 
+// ---- multi-GPU: sum of the statistics over the ranks through peer memory, inside the sweep kernel ------------------------------
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+// wait until rank q has signalled `epoch` in this rank's flag array (a peer that never arrives means a lost rank: trap after ~20 s)
+__device__ __forceinline__ void xchg_wait(const unsigned* flag, unsigned epoch) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        __nanosleep(64);
+        if (clock64() - t0 > 40000000000ll) __trap();
+    }
+}
+// Two-shot all-reduce over NVLink peer memory.  Every rank has written its statistics to its own xin.  Barrier A (flags), then rank r
+// sums elements [r, r+1) * count / R of all xin in rank order -- the same order on every rank: bitwise identical results -- and stores
+// the sums into every rank's xout (its stats buffer); barrier B.
+template <int NT>
+__device__ __forceinline__ void xchg_allreduce(const SgpXchg& x, cooperative_groups::grid_group& grid) {
+    const int tid = threadIdx.x, R = x.nranks;
+    __threadfence();
+    grid.sync();                                            // this rank's xin is complete (gpu scope) ...
+    unsigned* myflags = reinterpret_cast<unsigned*>(x.peers[x.rank]);
+    if (blockIdx.x == 0 && tid < R) {                       // ... and published system-wide by the signalling threads (release is cumulative)
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned*>(x.peers[tid]) + x.rank, x.epoch);
+    }
+    if (tid < R) xchg_wait(myflags + tid, x.epoch);         // every CTA polls the local flags: no second grid barrier
+    __syncthreads();
+    // this rank's share, in pairs of doubles; up to U pairs per thread with all their peer loads in flight together
+    constexpr int U = 2;
+    const long long pairs = (x.count + 1) / 2;              // (the buffers are padded: reading / writing one double past count is harmless)
+    const long long p0 = pairs * x.rank / R, p1 = pairs * (x.rank + 1) / R;
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long e = p0 + (long long)blockIdx.x * NT + tid; e < p1; e += U * stride) {
+        double2 v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < R && e + u * stride < p1) v[u][q] = __ldcv(reinterpret_cast<const double2*>(x.peers[q] + x.xin_off) + e + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (e + u * stride >= p1) break;
+            double2 sum = v[u][0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) if (q < R) { sum.x += v[u][q].x; sum.y += v[u][q].y; }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (q < R) reinterpret_cast<double2*>(x.peers[q] + x.xout_off)[e + u * stride] = sum;
+        }
+    }
+    __threadfence();
+    grid.sync();                                            // this rank's share is stored everywhere
+    if (blockIdx.x == 0 && tid < R) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned*>(x.peers[tid]) + 16 + x.rank, x.epoch);
+        xchg_wait(myflags + 16 + tid, x.epoch);             // the kernel ends only when every peer's share has landed here
+    }
+}
+
 template <int TM, int NB, int DPAD, int NT, int KIND, bool WEIGHTED>
 __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ Params p) {
     using S = Smem4<TM, NB, DPAD>;
@@ -800,7 +862,8 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     grid.sync();
     if (p.dbg) t_k3 = clock64();
     reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)));
-    if (p.dbg && tid == 0) {   // timeline of this CTA: {setup clocks, slab-loop clocks, 4, cta}, {final barrier clocks, phase-2 clocks, 5, cta}
+    if (p.xr.nranks > 1) xchg_allreduce<NT>(p.xr, grid);
+    if (p.dbg && tid == 0) {   // timeline of this CTA: {setup clocks, slab-loop clocks, 4, cta}, {final barrier clocks, phase-2 (+ exchange) clocks, 5, cta}
         long long* d = p.dbg + 4 * (size_t)(p.ncta + p.ntiles) + 8 * (size_t)p.ncta;
         d[8 * bcta + 0] = t_k1 - t_k0; d[8 * bcta + 1] = t_k2 - t_k1; d[8 * bcta + 2] = 4; d[8 * bcta + 3] = bcta;
         d[8 * bcta + 4] = t_k3 - t_k2; d[8 * bcta + 5] = clock64() - t_k3; d[8 * bcta + 6] = 5; d[8 * bcta + 7] = bcta;

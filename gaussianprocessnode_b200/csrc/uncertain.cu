@@ -457,7 +457,7 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
     UC(cudaMemsetAsync(ctx->info_dev, 0, sizeof(int), ctx->stream));
     const double* ell_inv_d = misc_d; const double* ell_d = misc_d + SGP_MAX_D; const double* gh_d = misc_d + 2 * SGP_MAX_D;
 
-    rc = sgp_ensure(ctx, &ctx->stats_dev, &ctx->stats_cap, MM + (size_t)M * (D_out > 1 ? D_out : 1) + 8);
+    rc = sgp_ensure_stats(ctx, MM + (size_t)M * (D_out > 1 ? D_out : 1) + 8);
     if (rc) { cleanup(); return rc; }
     double* s_psi2 = ctx->stats_dev; double* s_psi1 = s_psi2 + MM; double* s_scal = s_psi1 + (size_t)M * D_out;
 

@@ -147,6 +147,10 @@ int sgp_comm_init(sgp_ctx* ctx, int nranks, int rank, const char id[128]);
 /* Runs the sweep `reps` times on resident data without host copies and returns the mean device time of one sweep
  * (CUDA events on the ctx stream) and of its dominant kernel alone. */
 int sgp_sweep_timed(sgp_ctx* ctx, int reps, float* ms_per_sweep, float* ms_main_kernel);
+/* The same with an L2 flush (a `flush_mb` MB device buffer is rewritten on the ctx stream) before every repetition, all repetitions
+ * enqueued without a host synchronisation; the flush is outside the timed intervals (one event pair per repetition).  With a
+ * communicator attached the ranks stay in lock step through the exchange itself. */
+int sgp_sweep_timed_flushed(sgp_ctx* ctx, int reps, int flush_mb, float* ms_per_sweep, float* ms_main_kernel);
 /* number of kernels the last sweep launched, and the main kernel's launch geometry */
 int sgp_last_sweep_info(sgp_ctx* ctx, int* n_launches, int* grid, int* block, int* smem_bytes);
 /* per-segment clock counters of the fused sweep kernel (load-balance tuning).  The first call switches the

@@ -1,6 +1,9 @@
 """Sharded sweep over two GPUs through the C ABI: N is cut into two slices, one process / sgp_ctx per GPU, the packed
-statistics are all-reduced with NCCL inside sgp_sweep_psi; every rank must hold the single-GPU result (tolerance: the
-summation order differs, relative Frobenius <= 1e-12).  Skipped on boxes with one GPU."""
+statistics are summed over the ranks inside sgp_sweep_psi -- by the sweep kernel itself through NVLink peer memory (CUDA IPC,
+two-shot all-reduce in the kernel's tail), or by one NCCL all-reduce when SGP_COMM_P2P=0; every rank must hold the single-GPU
+result (tolerance: the summation order differs, relative Frobenius <= 1e-12) and all ranks the same bits.  Skipped on boxes
+with one GPU."""
+import hashlib
 import os
 import socket
 import numpy as np
@@ -14,7 +17,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, p2p):
+    os.environ["SGP_COMM_P2P"] = "1" if p2p else "0"
     import torch
     import torch.distributed as dist
     from gaussianprocessnode_b200 import SGPContext, shard
@@ -31,15 +35,20 @@ def _worker(rank, world, port, out):
     sw = shard.ShardedSweep(ctx, world, rank, uid[0])
     sw.set_data(X, y, yv)
     p0, p1, p2, sy = sw.sweep_psi()
+    q0, q1, q2, qy = sw.sweep_psi()                                  # a second sweep: the exchange epoch advances, same bits
+    same = bool(np.array_equal(p2, q2) and np.array_equal(p1, q1) and p0 == q0 and sy == qy)
+    digest = hashlib.sha256(p2.tobytes() + p1.tobytes()).hexdigest()
+    info = ctx.last_sweep_info()
     ctx.close()
     single = SGPContext(rank); single.set_kernel(1.2, ell); single.set_inducing(Z); single.set_data(X, y, yv)
     f0, f1, f2, fy = single.sweep_psi(); single.close()
     out[rank] = (float(np.linalg.norm(p2 - f2) / np.linalg.norm(f2)), float(np.linalg.norm(p1 - f1) / np.linalg.norm(f1)),
-                 float(abs(p0 - f0) / abs(f0)), float(abs(sy - fy) / abs(fy)))
+                 float(abs(p0 - f0) / abs(f0)), float(abs(sy - fy) / abs(fy)), same, digest, info["launches"])
     dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_sweep_matches_single_gpu():
+@pytest.mark.parametrize("p2p", [True, False])
+def test_two_gpu_sharded_sweep_matches_single_gpu(p2p):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -47,8 +56,11 @@ def test_two_gpu_sharded_sweep_matches_single_gpu():
     world = 2
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), out, p2p), nprocs=world, join=True)
         res = dict(out)
     assert set(res) == {0, 1}
     for r in res.values():
-        assert max(r) <= 1e-12, res
+        assert max(r[:4]) <= 1e-12, res
+        assert r[4], "repeated sweeps must give the same bits"
+        assert r[6] == (1 if p2p else 2), r                            # fused exchange: ONE launch per sweep; NCCL path: kernel + all-reduce
+    assert res[0][5] == res[1][5], "every rank must hold bitwise identical statistics"
