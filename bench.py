@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- VSGP data-sweep throughput on B200 (contract in the task statement).
 
-One "step" = one pass of the hot path over one batch: the fused K_uf-generate + DMMA-SYRK sweep producing Psi0/Psi1/Psi2
+One "step" = one pass of the hot path over one batch: the generate-once K_uf + DMMA-SYRK sweep producing Psi0/Psi1/Psi2
 for the kin40k-shape workload (N = 10000 points per GPU, D = 8, M = 512, SE-ARD, Float64).  `value` = data-points/s with
-inputs resident in HBM; `e2e` = the same through the C-ABI call with HOST buffers (sgp_set_data + sgp_sweep_psi: H2D
-of X / y and D2H of Psi1 / Psi2 inside the timed region).  With --gpus N every rank sweeps its own N-shard and the packed
-statistics are all-reduced once per step over NCCL ("weak": per-GPU work fixed).  The synthetic N = 10M / M = 1024
+inputs resident in HBM (K steps enqueued back to back, an L2 flush on the stream before each, one CUDA event pair per step);
+`e2e` = the same through the C-ABI call with HOST buffers (sgp_sweep_psi_host: H2D of X / y and D2H of Psi1 / Psi2 inside
+the timed region).  With --gpus N every rank sweeps its own N-shard and the statistics are summed over the ranks inside the
+sweep kernel through NVLink peer memory ("weak": per-GPU work fixed).  The synthetic N = 10M / M = 1024
 configuration, where the path is throughput-bound and the FP64 roofline is meaningful, is timed as well (strong scaling
 over ranks) and reported under "synthetic_10M".
 
@@ -42,8 +43,8 @@ def fp64_peak():
 
 def traffic(which):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of sweep_kernel from the committed `ncu --set full` captures
-    (profiles/r01_traffic.json: kin40k shape as benchmarked; synthetic scaled per point from the N=400000 capture)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    (profiles/r01g_traffic.json: kin40k shape as benchmarked; synthetic scaled per point from the N=400000 capture)."""
+    p = os.path.join(ROOT, "profiles", "r01g_traffic.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
@@ -238,7 +239,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(info["launches"] * args.steps),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic("kin40k"),
-                     "kernel": "sweep_kernel<128,32,8,256> (one cooperative launch per sweep) grid=%d block=%d smem=%d" % (info["grid"], info["block"], info["smem_bytes"]),
+                     "kernel": "sweep4_kernel<128,32,8,256> (generate-once sweep: one cooperative launch per sweep) grid=%d block=%d smem=%d" % (info["grid"], info["block"], info["smem_bytes"]),
                      "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_main, "peak_source": peak_src,
                      "note": "kin40k shape is 2.6 GFLOP: launch/latency-bound (66 us at peak); see synthetic_10M for the throughput-bound case"},
         "clocks": clk.summary(),
@@ -274,9 +275,22 @@ def main():
             "psi2_tflops_all_gpus": world * fl / (ms_s * 1e-3) * 1e-12,
             "roofline": {"bound": "tensor", "achieved": fl / (ms_m * 1e-3) * 1e-12, "peak": peak, "unit": "TFLOP/s",
                          "frac": fl / (ms_m * 1e-3) * 1e-12 / peak, "traffic": traffic("synthetic"), "ms_per_launch": ms_m,
-                         "algorithmic_flops_per_launch": fl, "kernel": "sweep_kernel<128,32,8> grid=%d" % info2["grid"],
+                         "algorithmic_flops_per_launch": fl, "kernel": "sweep4_kernel<128,32,8,256> grid=%d" % info2["grid"],
                          "peak_source": peak_src},
             "clocks": clk2.summary()}
+        # the same sweep with 32 MB panels (ring of 96 MB: fewer slab turnovers, but the K_uf panels no longer stay in L2 -- they are
+        # written back to and partly re-read from HBM); reported beside the default, not instead of it
+        try:
+            os.environ["SGP_SWEEP_SLAB_MB"] = "32"
+            for _ in range(2):
+                ctx.sweep_timed(1)
+            barrier()
+            ts2 = [ctx.sweep_timed(1)[1] for _ in range(args.syn_steps)]
+            ms2 = max_over_ranks(float(np.mean(ts2)))
+            line["synthetic_10M"]["slab_32MB_spilling"] = {"ms_per_launch": ms2, "tflops": fl / (ms2 * 1e-3) * 1e-12,
+                                                           "frac": fl / (ms2 * 1e-3) * 1e-12 / peak}
+        finally:
+            os.environ.pop("SGP_SWEEP_SLAB_MB", None)
         del Xd, yd
 
     # ------------------------------------------------------------------ theta step, N = 1 only

@@ -48,6 +48,7 @@ struct sgp_ctx {
     // scratch
     double* work_dev = nullptr;  size_t work_cap = 0;      // split-N partials
     double* zrec_dev = nullptr;  size_t zrec_cap = 0;      // prepared inducing rows
+    void* kbuf_window = nullptr; size_t kbuf_window_bytes = 0;   // L2 access-policy window currently set on the stream
     double* kbuf_dev = nullptr;  size_t kbuf_cap = 0;      // L2-resident K_uf panel of one slab (generate-once sweep)
     void* flush_dev = nullptr; size_t flush_cap = 0;       // L2 flush buffer of sgp_sweep_timed_flushed
     unsigned* sweep_flags_dev = nullptr;                   // generation / consumption counters of the generate-once sweep

@@ -1,4 +1,10 @@
-// Fused K_uf-tile generator + FP64 DMMA SYRK: the data sweep of the sparse variational GP node.
+// The data sweep of the sparse variational GP node: host-side launch logic of the two sweep kernels.
+//   sweep4_kernel.cuh  generate-once sweep (default): K_uf generated once per sweep into an L2-resident ring of slab panels,
+//                      consumed by a TMA-fed FP64 DMMA SYRK; see the notes at the top of that file and DESIGN.md section 4.1
+//   sweep_kernel.cuh   the first fused kernel (K_uf tiles regenerated in shared memory inside every Psi2 tile): SGP_SWEEP_IMPL=3,
+//                      and the fallback for shapes outside the first one's range.  Its notes follow.
+//
+// Fused K_uf-tile generator + FP64 DMMA SYRK.
 //
 // Replaces the reference's per-data-point schedule -- `kernelmatrix!(Psi1_trans, kernel(theta), Xu, [x_n])` followed by
 // the rank-1 `mul!(meta.Psi2, k, k', w, 0)` and the M x M add inside `prod` (GPnode/UniSGPnode.jl:144-173, 62-73;
@@ -43,7 +49,7 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     const int ntiles = nblk * (nblk + 1) / 2;
     const long long chunks = (N + NB - 1) / NB;
     // slab: as many chunks as keep the panel (nblk x 32 x (TM + 4) doubles per chunk) inside the L2 budget
-    double slab_mb = 32.0;        // per panel; the ring holds three
+    double slab_mb = 16.0;        // per panel; the ring holds three: 48 MB is what stays in the L2 (persisting window) without DRAM re-reads
     if (const char* e = std::getenv("SGP_SWEEP_SLAB_MB")) { double v = std::atof(e); if (v > 0.0) slab_mb = v; }
     const size_t chunk_doubles = (size_t)nblk * NB * (TM + 4);
     long long max_slab = (long long)(slab_mb * 1048576.0 / (chunk_doubles * sizeof(double)));
@@ -91,6 +97,27 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     if (ctx->want_exchange && sgp_comm_xchg(ctx, (size_t)M * M + M + 4, &p.xr)) {
         p.psi2 = reinterpret_cast<double*>(p.xr.peers[p.xr.rank] + p.xr.xin_off); p.psi1 = p.psi2 + (size_t)M * M; p.scal = p.psi1 + M;
         ctx->last_sweep_exchanged = true;
+    }
+
+    // the panel ring is the only buffer worth keeping in L2: mark it persisting, everything else streams through the rest of the cache
+    if (ctx->kbuf_window != (void*)ctx->kbuf_dev || ctx->kbuf_window_bytes != (size_t)nring * slab_chunks * chunk_doubles * sizeof(double)) {
+        const size_t ring_bytes = (size_t)nring * slab_chunks * chunk_doubles * sizeof(double);
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->dev);
+        const char* e = std::getenv("SGP_SWEEP_L2_PERSIST");
+        if (max_persist > 0 && max_window > 0 && !(e && e[0] == '0')) {
+            const size_t lim = std::min<size_t>((size_t)max_persist, ring_bytes);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim);
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = ctx->kbuf_dev;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(ring_bytes, (size_t)max_window);
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)lim / (double)av.accessPolicyWindow.num_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+        }
+        ctx->kbuf_window = ctx->kbuf_dev; ctx->kbuf_window_bytes = ring_bytes;
     }
 
     if (time_main) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
