@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgp.so")
-SOURCES = ["api.cu", "sweep.cu", "sweep_se.cu", "sweep_m32.cu", "sweep_m52.cu", "sweep4_se.cu", "sweep4_m32.cu", "sweep4_m52.cu", "dense.cu", "dense_coop.cu", "uncertain.cu", "theta.cu", "comm.cu"]
+SOURCES = ["api.cu", "sweep.cu", "sweep_se.cu", "sweep_m32.cu", "sweep_m52.cu", "sweep4_se.cu", "sweep4_m32.cu", "sweep4_m52.cu", "dense.cu", "dense_coop.cu", "uncertain.cu", "theta.cu", "inmsg.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default"]
 

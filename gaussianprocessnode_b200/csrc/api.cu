@@ -132,7 +132,7 @@ void sgp_destroy(sgp_ctx* ctx) {
     cudaFree(ctx->Z_dev); if (!ctx->stats_external) cudaFree(ctx->stats_dev); cudaFree(ctx->work_dev); cudaFree(ctx->zrec_dev); cudaFree(ctx->exptab_dev);
     cudaFree(ctx->dense_dev); cudaFree(ctx->info_dev); cudaFree(ctx->KuuL_dev); cudaFree(ctx->sp_X_dev); cudaFree(ctx->sp_w_dev);
     cudaFree(ctx->sp_y_dev); cudaFree(ctx->sweep_dbg_dev); cudaFree(ctx->theta_dev); cudaFree(ctx->Kinv_dev); cudaFree(ctx->kuu_dinv_dev);
-    cudaFree(ctx->dinv_dev); cudaFree(ctx->post_dev); cudaFree(ctx->unc_dev); cudaFree(ctx->kbuf_dev); cudaFree(ctx->sweep_flags_dev); cudaFree(ctx->flush_dev);
+    cudaFree(ctx->dinv_dev); cudaFree(ctx->post_dev); cudaFree(ctx->unc_dev); cudaFree(ctx->kbuf_dev); cudaFree(ctx->sweep_flags_dev); cudaFree(ctx->flush_dev); cudaFree(ctx->in_dev);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -55,6 +55,7 @@ struct sgp_ctx {
     double* exptab_dev = nullptr;
     double* dense_dev = nullptr; size_t dense_cap = 0;     // M x M scratch for factorisations
     int* info_dev = nullptr;
+    double* in_dev = nullptr; size_t in_cap = 0;           // scratch of sgp_in_logmessage (inmsg.cu)
     double* theta_dev = nullptr; size_t theta_cap = 0;     // scratch of the theta objective / gradient (theta.cu)
 
     // K_uu factor

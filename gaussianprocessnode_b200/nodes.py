@@ -508,3 +508,91 @@ def num_error(ytrue, y):
 def error_rate(ytrue, y):
     """gp_helperfunction.jl:156-158."""
     return num_error(ytrue, y) / len(ytrue)
+
+
+# ---- @rule MultiSGP(:in) (SURVEY.md section 8f row 4) ---------------------------------------------------------------------------------
+def _in_operands(q_v, q_w, meta: MultiSGPMeta, D: int):
+    """What every node's :in message shares (MultiSGPnode.jl:175-181): Mv = [mu_v^(1) ... mu_v^(D)] (M x D), S = sumRvblk_W, tr(W)."""
+    W = np.asarray(mean(q_w), dtype=np.float64)
+    mu_v, Sigma_v = mean_cov(q_v)
+    M = np.asarray(meta.Xu).shape[0]
+    Rv = np.asarray(Sigma_v, dtype=np.float64) + np.outer(mu_v, mu_v)
+    S = sum(Rv[i * M:(i + 1) * M, j * M:(j + 1) * M] * W[i, j] for i in range(D) for j in range(D))
+    Mv = np.asarray(mu_v, dtype=np.float64).reshape(D, M).T
+    return W, Mv, S
+
+
+def multi_rule_in(q_outs, q_v, q_w, q_theta, meta: MultiSGPMeta):
+    """@rule MultiSGP(:in, Marginalisation) -- MultiSGPnode.jl:162-185 (q_out Gaussian), :187-211 (PointMass) -- for a whole chain of
+    nodes: returns `logpdf(Xp)`, the batched counterpart of the N closures `log_backwardmess`: Xp (N, P, d) -> (N, P) values
+    (with grad=True / hess=True also the analytic derivatives), evaluated by sgp_in_logmessage in one call."""
+    _configure(meta, mean(q_theta))
+    ctx = _ctx(meta)
+    Y = np.stack([np.asarray(q.value if isinstance(q, PointMass) else mean(q), dtype=np.float64) for q in q_outs])
+    W, Mv, S = _in_operands(q_v, q_w, meta, Y.shape[1])
+    R = Y @ W                                                     # row n = (W mu_y,n)'  (W symmetric)
+    ctx.kuu_factor(getattr(meta, "kuu_jitter", 1e-12), fetch=False)        # Pendulum_Wishart_2d.ipynb:2542-2543: cholinv(Kuu + 1e-12 I)
+    trW = float(np.trace(W))
+
+    def logpdf(Xp, grad=False, hess=False):
+        return ctx.in_logmessage(np.asarray(Xp, dtype=np.float64), Mv, S, trW, R=R, grad=grad, hess=hess)
+    return logpdf
+
+
+def multi_prod_gaussian_logpdf(lefts, logpdf):
+    """`ReactiveMP.prod(::GenericProd, left::MvGaussian, right::ContinuousMultivariateLogPdf)` (MultiSGPnode.jl:38-45) for N (left_n,
+    right_n) pairs at once: the 2d+1 spherical-radial points of every left_n go through ONE sgp_in_logmessage call; the moment
+    matching (2d+1 terms per node) is host arithmetic.  Returns (means (N, d), covs (N, d, d)); a node whose mean is NaN keeps left_n."""
+    ms = np.stack([np.asarray(mean_cov(q)[0], dtype=np.float64) for q in lefts])
+    Ps = np.stack([np.asarray(mean_cov(q)[1], dtype=np.float64) for q in lefts])
+    N, d = ms.shape
+    L = np.linalg.cholesky(Ps)
+    c = np.sqrt(d + 1.0)
+    # srcubature (SURVEY.md 8a row a9): centre with weight 1/(d+1), m +- sqrt(d+1) L e_j with weight 1/(2(d+1))
+    pts = np.concatenate([ms[:, None, :], ms[:, None, :] + c * np.swapaxes(L, 1, 2), ms[:, None, :] - c * np.swapaxes(L, 1, 2)], axis=1)
+    wts = np.concatenate([[1.0 / (d + 1.0)], np.full(2 * d, 0.5 / (d + 1.0))])
+    g = np.exp(logpdf(pts)) * wts[None, :]
+    Zn = g.sum(1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mu = np.einsum("np,npd->nd", g, pts) / Zn[:, None]
+        dl = pts - mu[:, None, :]
+        cov = np.einsum("np,npi,npj->nij", g, dl, dl) / Zn[:, None, None]
+    bad = np.isnan(mu[:, 0])
+    mu[bad] = ms[bad]; cov[bad] = Ps[bad]
+    return mu, cov
+
+
+def multi_rule_in_laplace(q_outs, q_ins, q_v, q_w, q_theta, meta: MultiSGPMeta, iterations=50, tol=1e-12):
+    """@rule MultiSGP(:in) -- MultiSGPnode.jl:213-236: mode m_z of every node's backward message from mean(q_in) and W_z = Hessian of
+    the negative log message there; returns (xi (N, d) = W_z m_z, W_z (N, d, d), m_z).  The reference runs LBFGS (20 iterations,
+    ForwardDiff gradient) per node and Zygote.hessian; here all N nodes advance together by damped Newton steps on the analytic
+    gradient / Hessian of sgp_in_logmessage (a step is halved until the message does not decrease; a non-positive-definite Hessian
+    falls back to a gradient step)."""
+    logpdf = multi_rule_in(q_outs, q_v, q_w, q_theta, meta)
+    x = np.stack([np.asarray(mean_cov(q)[0], dtype=np.float64) for q in q_ins])
+    N, d = x.shape
+    f, g, H = logpdf(x[:, None, :], hess=True)
+    f = f[:, 0]; g = g[:, 0]; H = H[:, 0]
+    for _ in range(iterations):
+        step = np.empty_like(x)
+        for n in range(N):
+            try:
+                np.linalg.cholesky(-H[n])
+                step[n] = np.linalg.solve(-H[n], g[n])
+            except np.linalg.LinAlgError:
+                step[n] = g[n] / max(np.linalg.norm(H[n], 2), 1e-12)
+        t = np.ones(N)
+        active = np.linalg.norm(g, axis=1) > tol
+        if not active.any():
+            break
+        for _ls in range(30):
+            xn = x + (t * active)[:, None] * step
+            fn, gn, Hn = logpdf(xn[:, None, :], hess=True)
+            fn = fn[:, 0]
+            worse = active & ~(fn >= f - 1e-14 * np.abs(f))
+            if not worse.any():
+                break
+            t[worse] *= 0.5
+        x, f, g, H = xn, fn, gn[:, 0], Hn[:, 0]
+    Wz = -H
+    return np.einsum("nij,nj->ni", Wz, x), Wz, x

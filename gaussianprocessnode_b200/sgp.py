@@ -243,6 +243,22 @@ class SGPContext:
         self._ck(self.lib.sgp_predict_mean(self.h, Xt.shape[0], _p(Xt), _p(mu_v), _p(out)))
         return out
 
+    def in_logmessage(self, Xp, Mv, S, trW, R=None, grad=False, hess=False):
+        """log backward message of `@rule MultiSGP(:in)` at P points for each of N nodes (sgp_in_logmessage).
+        Xp: (N, P, d); Mv: (M, D_out) columns mu_v^(d); S: (M, M) = sumRvblk_W; R: (N, D_out) rows (W mu_y,n)' or None.
+        Returns f (N, P) [, grad (N, P, d)] [, hess (N, P, d, d)].  Needs kuu_factor."""
+        Xp = _f64(Xp)
+        N, P, d = Xp.shape
+        M = self.M
+        Mv = np.asfortranarray(np.asarray(Mv, dtype=np.float64).reshape(M, -1))
+        Dout = Mv.shape[1]
+        S = np.asfortranarray(np.asarray(S, dtype=np.float64).reshape(M, M))
+        Rc = None if R is None else _f64(R, (N, Dout))
+        f = np.empty((N, P)); g = np.empty((N, P, d)) if (grad or hess) else None; h = np.empty((N, P, d, d)) if hess else None
+        self._ck(self.lib.sgp_in_logmessage(self.h, N, P, _p(Xp), Dout, _p(Rc), _p(Mv), _p(S), float(trW), _p(f), _p(g), _p(h)))
+        out = (f,) + ((g,) if grad or hess else ()) + ((h,) if hess else ())
+        return out if len(out) > 1 else f
+
     def theta_objective(self, mu_v, Uv, w, jitter=0.0, grad=True):
         """(F, dF/dvariance, dF/dlengthscale[D]) of the theta step on the resident data (sgp_theta_objective)."""
         M = self.M

@@ -138,6 +138,18 @@ int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* m
 int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const double* Uv, double w, double jitter, double* value,
                         double* dvariance, double* dlengthscale);
 
+/* ---- backward message towards the input of MultiSGP ------------------------------------- */
+/* `@rule MultiSGP(:in, Marginalisation)` (GPnode/MultiSGPnode.jl:162-185, 187-211, 213-236) for N nodes at once.  Per node the reference
+ * returns the closure
+ *   log_backwardmess(x) = -1/2 tr(W) (k(x,x) - k_u(x)' Kuu^-1 k_u(x)) + sumdiagV' k_u(x) - 1/2 k_u(x)' sumRvblk_W k_u(x),
+ * sumdiagV = sum_d mu_v^(d) (W mu_y)_d, sumRvblk_W = sum_ij W_ij R_v^{ij}, which ReactiveMP evaluates at the cubature points of the forward
+ * message (`prod` override :38-45) or minimises (LBFGS, :213-236).  This call evaluates it at P points for each of the N nodes:
+ *   Xp: d x P x N (point p of node n = d contiguous doubles),  R: N x D_out, row n = (W mu_y,n)' (NULL = ones),  Mv: M x D_out, column d =
+ *   mu_v^(d),  S: M x M = sumRvblk_W,  trW = tr(W);   f: P x N values,  grad: d x P x N (optional),  hess: d x d x P x N (optional; analytic,
+ *   SE-ARD only -- what ForwardDiff / Zygote.hessian return in the Laplace variant).  Needs sgp_kuu_factor (K_uu^-1). */
+int sgp_in_logmessage(sgp_ctx* ctx, int64_t N, int P, const double* Xp, int D_out, const double* R, const double* Mv, const double* S,
+                      double trW, double* f, double* grad, double* hess);
+
 /* ---- multi-GPU: N is sharded over ranks, one ctx per rank/GPU --------------------------------------------- */
 /* NCCL unique id (128 bytes) created on rank 0 and handed to the other ranks by the host. */
 int sgp_comm_unique_id(char id[128]);

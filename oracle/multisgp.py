@@ -102,3 +102,62 @@ def average_energy(mu_y, Sigma_y, q_in, mu_v, Sigma_v, W_bar, E_logW, theta, met
     return (0.5 * D * LOG2PI - 0.5 * E_logW + 0.5 * np.trace(W_bar @ Ry)
             + 0.5 * np.trace(W_bar) * (psi0 - np.sum(meta.Kuu_inverse * psi2))
             - np.sum(sumdiagV * psi1) + 0.5 * np.sum(psi2 * sumRvblk_W))
+
+
+def rule_in_logpdf(mu_y, mu_v, Sigma_v, W, theta, meta):
+    """MultiSGPnode.jl:162-185 (q_out Gaussian) / :187-211 (PointMass): the closure log_backwardmess(x), written exactly as the
+    reference has it (Psi0, Psi1_trans, Psi2 closures; sumdiagV; sumRvblk_W)."""
+    mu_y = np.asarray(mu_y, dtype=np.float64)
+    D = mu_y.size
+    var, ell, kind = meta.kernel(theta)
+    Z = np.asarray(meta.Xu, dtype=np.float64)
+    M = Z.shape[0]
+    Rv = Sigma_v + np.outer(mu_v, mu_v)
+    V = np.outer(mu_v, mu_y) @ W
+    sumdiagV = sum_diagonal_M(V, M)
+    blk = create_blockmatrix(Rv, D, M)
+    sumRvblk_W = sum(blk[i][j] * W[i, j] for i in range(D) for j in range(D))
+
+    def log_backwardmess(x):
+        x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+        psi0 = kernel_matrix(x[None, :], x[None, :], var, ell, kind)[0, 0]
+        psi1 = kernel_matrix(x[None, :], Z, var, ell, kind)[0]
+        psi2 = np.outer(psi1, psi1)
+        return (-0.5 * np.trace(W) * (psi0 - np.sum(meta.Kuu_inverse * psi2)) + np.sum(sumdiagV * psi1) - 0.5 * np.sum(psi2 * sumRvblk_W))
+    return log_backwardmess
+
+
+def prod_gaussian_logpdf(m, P, logpdf):
+    """`prod(::GenericProd, left::MvGaussian, right::ContinuousMultivariateLogPdf)` (MultiSGPnode.jl:38-45): moment matching with
+    the spherical-radial cubature points of `left`; ReactiveMP's approximate_meancov restated from its definition (unvendored:
+    parity unpinned):  Z = sum w g(x),  mean = sum w g(x) x / Z,  cov = sum w g(x) (x - mean)(x - mean)' / Z,  g = exp(logpdf).
+    Returns `left` unchanged when the mean is NaN."""
+    pts, wts = cub.sigma_points(cub.SRCUBATURE, m, P)
+    g = np.array([np.exp(logpdf(pt)) for pt in pts])
+    Zn = np.sum(wts * g)
+    mean = (wts * g) @ pts / Zn
+    if np.isnan(mean[0]):
+        return np.asarray(m, dtype=np.float64), np.asarray(P, dtype=np.float64)
+    dlt = pts - mean
+    cov = (dlt * (wts * g)[:, None]).T @ dlt / Zn
+    return mean, cov
+
+
+def rule_in_laplace(mu_y, x0, mu_v, Sigma_v, W, theta, meta, iters=200):
+    """MultiSGPnode.jl:213-236: mode m_z of the backward message from x0 = mean(q_in) and W_z = Hessian of the negative log
+    message there -> (xi = W_z m_z, W_z).  The reference runs Optim's LBFGS for 20 iterations with a ForwardDiff gradient and
+    takes Zygote.hessian; Optim is not vendored (parity unpinned), so the oracle converges scipy's L-BFGS-B instead and
+    differentiates numerically: the two agree wherever the reference's 20 iterations have converged."""
+    from scipy.optimize import minimize
+    f = rule_in_logpdf(mu_y, mu_v, Sigma_v, W, theta, meta)
+    neg = lambda x: -f(x)
+    res = minimize(neg, np.asarray(x0, dtype=np.float64), method="L-BFGS-B", options=dict(maxiter=iters, ftol=1e-15, gtol=1e-12))
+    mz = res.x
+    d = mz.size
+    h = 1e-4
+    H = np.zeros((d, d))
+    for i in range(d):
+        for j in range(d):
+            ei = np.eye(d)[i] * h; ej = np.eye(d)[j] * h
+            H[i, j] = (neg(mz + ei + ej) - neg(mz + ei - ej) - neg(mz - ei + ej) + neg(mz - ei - ej)) / (4 * h * h)
+    return H @ mz, H, mz
