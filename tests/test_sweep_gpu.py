@@ -201,3 +201,28 @@ def test_one_call_host_step_equals_set_data_plus_sweep(ctx):
     ctx.set_data(X, y, yv); b = ctx.sweep_psi()
     assert a[0] == b[0] and a[3] == b[3] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert np.array_equal(ctx.sweep_psi()[2], a[2])          # the data stay resident after the one-call step
+
+
+@pytest.mark.parametrize("N,D,M,slab_mb,kind", [(20000, 8, 1024, "1", 0), (20000, 3, 300, "0.3", 0), (9000, 2, 100, "0.05", 0), (6000, 8, 300, "0.2", 2)])
+def test_many_slabs_ring_wraparound(ctx, N, D, M, slab_mb, kind, monkeypatch):
+    # the generate-once kernel cuts N into slabs whose K_uf panel lives in a ring of three L2 panels; tiny panels force dozens of slabs
+    # (ring wrap-around, generation / consumption counters, RED accumulation across slabs, clipped last slab) on a small problem
+    monkeypatch.setenv("SGP_SWEEP_SLAB_MB", slab_mb)
+    rng = np.random.default_rng(N + M)
+    X = rng.normal(size=(N, D)); Z = rng.normal(size=(M, D)); y = rng.normal(size=N); w = rng.uniform(0.5, 1.5, N)
+    ell = 0.9 + rng.random(D) * 1.5
+    for wts in (None, w):
+        ctx.set_kernel(1.3, ell, D=D, kind=kind); ctx.set_inducing(Z); ctx.set_data(X, y, None, wts)
+        psi0, psi1, psi2, sy2 = ctx.sweep_psi()
+        o0, o1, o2, oy = batched.psi_stats_point(X, y, Z, 1.3, ell, kind=kind, weights=wts)
+        assert abs(psi0 - o0) <= TOL * abs(o0) and fro(psi1, o1) <= TOL and fro(psi2, o2) <= TOL, (fro(psi1, o1), fro(psi2, o2))
+    a = ctx.sweep_psi()[2]; b = ctx.sweep_psi()[2]
+    assert np.array_equal(a, b)                       # deterministic across launches
+
+
+def test_first_fused_kernel_still_matches(ctx, monkeypatch):
+    # SGP_SWEEP_IMPL=3: the first fused kernel (K_uf regenerated in shared memory per tile), kept as the fallback path
+    monkeypatch.setenv("SGP_SWEEP_IMPL", "3")
+    rng = np.random.default_rng(77)
+    X = rng.normal(size=(5000, 8)); Z = rng.normal(size=(300, 8)); y = rng.normal(size=5000)
+    _check(ctx, X, y, Z, 1.1, np.full(8, 1.7))
