@@ -136,11 +136,27 @@ struct Sm4 {
     unsigned long long *full, *empty, *xfull;
 };
 
+// thread 0: raw points of generator group gi (kGC chunks from chunk c_lo + gi * kGC; the last group may be shorter) -> X stage (xg + gi) % kXStages
+template <int TM, int NB, int DPAD, bool WEIGHTED>
+__device__ __forceinline__ void issue_points(const Params& p, const Sm4& sm, const long long c_lo, const int nchunks, const int gi, const unsigned xg) {
+    using S = Smem4<TM, NB, DPAD>;
+    constexpr int GP = S::GP;
+    const int D = p.D;
+    const int s = (xg + gi) % kXStages;
+    double* st = sm.u + (S::xstage - S::u) + (size_t)s * S::XSTAGE;
+    const long long n0 = (c_lo + (long long)gi * kGC) * NB;
+    const unsigned npts = (unsigned)min(kGC, nchunks - gi * kGC) * NB;
+    mbar_expect_tx(&sm.xfull[s], npts * (unsigned)(D * 8 + 8 + (WEIGHTED ? 8 : 0)));
+    tma_load_1d(st, p.X + n0 * D, npts * D * 8, &sm.xfull[s]);
+    tma_load_1d(st + GP * SGP_MAX_D, p.y + n0, npts * 8, &sm.xfull[s]);
+    if (WEIGHTED) tma_load_1d(st + GP * SGP_MAX_D + GP, p.w + n0, npts * 8, &sm.xfull[s]);
+}
+
 // ---- G phase: this CTA's share of the slab's K_uf panel: row block `blk`, absolute chunks [c_lo, c_hi) -------------------------
 template <int TM, int NB, int DPAD, int NT, int KIND, bool WEIGHTED>
 __device__ __forceinline__ void gen_phase(const Params& p, const Sm4& sm, const int blk, const long long c_lo, const long long c_hi,
                                           const long long slab_c0, double* __restrict__ panel, unsigned& xg,
-                                          double (&psi1_acc)[TM / (NT / 4)][2]) {
+                                          double (&psi1_acc)[TM / (NT / 4)][2], const bool preissued) {
     using S = Smem4<TM, NB, DPAD>;
     constexpr int LDB = S::LDB, REC = S::REC, ZR = S::ZR;
     constexpr int NWARPS = NT / 32;
@@ -164,16 +180,7 @@ __device__ __forceinline__ void gen_phase(const Params& p, const Sm4& sm, const 
     constexpr int GP = S::GP;
     const int ngroups = (nchunks + kGC - 1) / kGC;
 
-    auto issue = [&](int gi) {   // thread 0 only: raw points of group gi (kGC chunks, the last group may be shorter)
-        const int s = (xg + gi) % kXStages;
-        double* st = xstage + (size_t)s * S::XSTAGE;
-        const long long n0 = (c_lo + (long long)gi * kGC) * NB;
-        const unsigned npts = (unsigned)min(kGC, nchunks - gi * kGC) * NB;
-        mbar_expect_tx(&sm.xfull[s], npts * (unsigned)(D * 8 + 8 + (WEIGHTED ? 8 : 0)));
-        tma_load_1d(st, p.X + n0 * D, npts * D * 8, &sm.xfull[s]);
-        tma_load_1d(st + GP * SGP_MAX_D, p.y + n0, npts * 8, &sm.xfull[s]);
-        if (WEIGHTED) tma_load_1d(st + GP * SGP_MAX_D + GP, p.w + n0, npts * 8, &sm.xfull[s]);
-    };
+    auto issue = [&](int gi) { issue_points<TM, NB, DPAD, WEIGHTED>(p, sm, c_lo, nchunks, gi, xg); };   // thread 0 only
     // raw staged group -> scaled records, all warps: a half-warp lane owns a point, the two half-warps split the dimensions
     auto prep = [&](int gi) {
         const unsigned gg = xg + gi;
@@ -220,7 +227,7 @@ __device__ __forceinline__ void gen_phase(const Params& p, const Sm4& sm, const 
         }
         zbias[r] = (gm < p.M) ? ((KIND == SGP_KERNEL_SE ? p.log_var_s : 0.0) - 0.5 * a) : -1.0e300;
     }
-    if (tid == 0)
+    if (tid == 0 && !preissued)
         for (int gi = 0; gi < kXStages - 1 && gi < ngroups; ++gi) issue(gi);
     __syncwarp();
     prep(0);
@@ -724,9 +731,21 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
         for (int s = 0; s < kXStages; ++s) mbar_init(&sm.xfull[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int i = tid; i < SGP_EXP_TAB; i += NT) sm.tab[i] = p.exptab[i];
-
     const int bcta = blockIdx.x;
+    // generator ownership: CTA i generates row block (i * nblk) / ncta
+    const int gblk = (int)(((long long)bcta * p.nblk) / p.ncta);
+    const int glo = gen_lo(gblk, p.ncta, p.nblk), ghi = gen_lo(gblk + 1, p.ncta, p.nblk);
+    const int gk = bcta - glo, gcnt = ghi - glo;
+    if (tid == 0) {    // the first generator phase's raw points: their DRAM latency overlaps the set-up below
+        const long long scs0 = min(p.slab_chunks, p.chunks);
+        const long long c_lo = scs0 * gk / gcnt, c_hi = scs0 * (gk + 1) / gcnt;
+        const int nch = (int)(c_hi - c_lo), ngr = (nch + kGC - 1) / kGC;
+        for (int gi = 0; gi < kXStages - 1 && gi < ngr; ++gi) issue_points<TM, NB, DPAD, WEIGHTED>(p, sm, c_lo, nch, gi, 0u);
+    }
+    // exp table: loads first, stores after the scalar sums below (their loads overlap)
+    double tabv[SGP_EXP_TAB / NT];
+#pragma unroll
+    for (int i = 0; i < SGP_EXP_TAB / NT; ++i) tabv[i] = p.exptab[tid + i * NT];
     if (tid == 32) {   // this CTA's segments of a full slab (the same partition for every slab; the last slab clips the chunk ranges)
         const long long q0 = cta_pos(p.total_cost, p.ncta, bcta), q1 = cta_pos(p.total_cost, p.ncta, bcta + 1);
         long long pre = 0;
@@ -735,14 +754,14 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
             const int wt = (I == J) ? p.w_diag : p.w_off;
             long long lo = 0, hi = 0;
             if (pre + (long long)wt * p.slab_units + p.w_fixed > q0) seg_range(q0, q1, pre, wt, p.w_fixed, p.slab_units, lo, hi);
-            if (lo < hi && ns < kMaxSeg) {
+            if (lo < hi && ns < kMaxSeg - 4) {
                 int* e = sm.segtab + 8 * ns++;
                 e[0] = I; e[1] = J; e[2] = bcta + t; e[3] = (int)lo; e[4] = (int)hi;
             }
             pre += (long long)wt * p.slab_units + p.w_fixed;
             if (++J > I) { ++I; J = 0; }
         }
-        if (ns < kMaxSeg) sm.segtab[8 * ns] = -1;
+        sm.segtab[8 * ns] = -1;
     }
     {   // sum_n w_n and sum_n w_n (y_n^2 + yv_n) over this CTA's stripe of points
         const long long n_lo = p.N * bcta / p.ncta, n_hi = p.N * (bcta + 1) / p.ncta;
@@ -753,12 +772,14 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
             sy = fma(wn, fma(yn, yn, vn), sy);
         }
 #pragma unroll
+        for (int i = 0; i < SGP_EXP_TAB / NT; ++i) sm.tab[tid + i * NT] = tabv[i];
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             sw += __shfl_xor_sync(0xffffffffu, sw, o);
             sy += __shfl_xor_sync(0xffffffffu, sy, o);
         }
-        double* red = sm.u;
-        if (lane == 0) { red[2 * warp] = sw; red[2 * warp + 1] = sy; fence_proxy_async(); }   // the TMA stages alias this scratch
+        double* red = reinterpret_cast<double*>(sm.segtab) + (kMaxSeg - 4) * 4;      // the last four (unused) entries of the segment table
+        if (lane == 0) { red[2 * warp] = sw; red[2 * warp + 1] = sy; }
         __syncthreads();
         if (tid == 0) {
             double a = 0.0, b = 0.0;
@@ -766,14 +787,9 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
             p.scal_partial[2 * bcta] = a;
             p.scal_partial[2 * bcta + 1] = b;
         }
-        // (gen_phase / the grid barrier synchronise before the union region is reused)
     }
 
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    // generator ownership
-    const int gblk = (int)(((long long)bcta * p.nblk) / p.ncta);
-    const int glo = gen_lo(gblk, p.ncta, p.nblk), ghi = gen_lo(gblk + 1, p.ncta, p.nblk);
-    const int gk = bcta - glo, gcnt = ghi - glo;
     double psi1_acc[RB][2];
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) psi1_acc[rb][0] = psi1_acc[rb][1] = 0.0;
@@ -791,7 +807,7 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
         // the panel is free once every CTA has consumed the slab that lived in it (slab s - nring)
         if (s >= p.nring && tid == 0) spin_ge(fl + p.nblk, (unsigned)(s / p.nring) * (unsigned)p.ncta);
         if (p.dbg) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-        gen_phase<TM, NB, DPAD, NT, KIND, WEIGHTED>(p, sm, gblk, slab_c0 + scs * gk / gcnt, slab_c0 + scs * (gk + 1) / gcnt, slab_c0, panel, xg, psi1_acc);
+        gen_phase<TM, NB, DPAD, NT, KIND, WEIGHTED>(p, sm, gblk, slab_c0 + scs * gk / gcnt, slab_c0 + scs * (gk + 1) / gcnt, slab_c0, panel, xg, psi1_acc, s == 0);
         fence_proxy_async();          // generic-proxy writes (panel in global, scratch in shared) before the async-proxy (TMA) accesses
         __threadfence();
         __syncthreads();
