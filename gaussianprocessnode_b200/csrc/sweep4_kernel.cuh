@@ -554,7 +554,7 @@ __host__ __device__ inline int gen_lo(int b, int ncta, int nblk) { return (int)(
 // phase 2 (after the last grid barrier): as reduce_items of sweep_kernel.cuh, with Psi1 summed over the generator CTAs of the
 // row block and the scalars over all CTAs -- always in CTA order: deterministic
 template <int TM, int NT>
-__device__ __forceinline__ void reduce_items4(const Params& p, double* __restrict__ S_, int* __restrict__ ibuf) {
+__device__ __forceinline__ void reduce_items4(const Params& p, double* __restrict__ S_, int* __restrict__ ibuf, long long* tr) {
     constexpr int SR = 4, STRIPES = TM / SR, NWARPS = NT / 32, LDS_ = TM + 1;
     constexpr int NBATCH = 4;                        // stripes whose loads are in flight together (S_ holds NBATCH stripes)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -563,6 +563,8 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
     int* slots = ibuf + NWARPS;
     int it = it0;
     while (it < it1) {
+        long long r0_ = 0, r1_ = 0, r2_ = 0;
+        if (p.dbg) r0_ = clock64();
         const int tile = it / STRIPES;
         const int s_lo = it - tile * STRIPES, s_hi = min(STRIPES, s_lo + (it1 - it));      // this CTA's stripes of the tile
         // the tile's workspace slots in CTA order: one candidate CTA per thread (ncta <= NT)
@@ -589,8 +591,10 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
             slots[before] = tid + tile;
         }
         __syncthreads();
+        if (p.dbg) { r1_ = clock64(); tr[0] += r1_ - r0_; }
         const bool diag = (I == J);
         for (int sb = s_lo; sb < s_hi; sb += NBATCH) {
+            if (p.dbg) r1_ = clock64();
             const int nb = min(NBATCH, s_hi - sb);
             if (tid < SR * TM / 2) {
                 const int e = 2 * tid, rl = e / TM, c = e - rl * TM;
@@ -612,6 +616,7 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                 for (int q = 0; q < NBATCH; ++q) { S_[(q * SR + rl) * LDS_ + c] = v[q].x; S_[(q * SR + rl) * LDS_ + c + 1] = v[q].y; }
             }
             __syncthreads();
+            if (p.dbg) { r2_ = clock64(); tr[1] += r2_ - r1_; }
             for (int q = 0; q < nb; ++q) {
                 const int r0 = (sb + q) * SR;
                 const double* Sq = S_ + (size_t)q * SR * LDS_;
@@ -625,25 +630,30 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                         if (gi < p.M && gj < p.M && (diag ? c < r : true)) p.psi2[(size_t)gj + (size_t)gi * p.M] = Sq[rl * LDS_ + c];
                     }
                 }
-                if (diag && tid < SR) {
-                    const int r = r0 + tid, gi = I * TM + r;
-                    if (gi < p.M) {
-                        double v = 0.0;
-                        const int lo = gen_lo(I, p.ncta, p.nblk), hi = gen_lo(I + 1, p.ncta, p.nblk);
-                        for (int qq = lo; qq < hi; ++qq) v += __ldcg(p.psi1_partial + (size_t)qq * TM + r);
-                        p.psi1[gi] = v;
-                    }
+                if (diag && warp < SR) {      // Psi1 row r0 + warp: a lane per generator CTA of the row block, fixed-shape tree -> deterministic
+                    const int r = r0 + warp, gi = I * TM + r;
+                    const int lo = gen_lo(I, p.ncta, p.nblk), hi = gen_lo(I + 1, p.ncta, p.nblk);
+                    double v = 0.0;
+                    for (int qq = lo + lane; qq < hi; qq += 32) v += __ldcg(p.psi1_partial + (size_t)qq * TM + r);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0 && gi < p.M) p.psi1[gi] = v;
                 }
             }
             __syncthreads();                                 // S_ is reused by the next batch
+            if (p.dbg) tr[2] += clock64() - r2_;
         }
-        if (tile == 0 && s_lo == 0 && tid == 0) {
+        if (tile == 0 && s_lo == 0 && warp == NWARPS - 1) {      // scalars: a lane per CTA stripe, fixed-shape tree -> deterministic
             double sw = 0.0, sy = 0.0;
-            for (int q = 0; q < p.ncta; ++q) { sw += __ldcg(p.scal_partial + 2 * q); sy += __ldcg(p.scal_partial + 2 * q + 1); }
-            p.scal[0] = p.variance * sw;   // Psi0 = sum_n w_n k(x_n, x_n)
-            p.scal[1] = sy;                // sum_n w_n (ybar^2 + yvar)
-            p.scal[2] = sw;
-            p.scal[3] = (double)p.N;
+            for (int q = lane; q < p.ncta; q += 32) { sw += __ldcg(p.scal_partial + 2 * q); sy += __ldcg(p.scal_partial + 2 * q + 1); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sw += __shfl_xor_sync(0xffffffffu, sw, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+            if (lane == 0) {
+                p.scal[0] = p.variance * sw;   // Psi0 = sum_n w_n k(x_n, x_n)
+                p.scal[1] = sy;                // sum_n w_n (ybar^2 + yvar)
+                p.scal[2] = sw;
+                p.scal[3] = (double)p.N;
+            }
         }
         it += s_hi - s_lo;
     }
@@ -877,12 +887,15 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     __threadfence();
     grid.sync();
     if (p.dbg) t_k3 = clock64();
-    reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)));
+    long long tr[3] = {0, 0, 0};
+    reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)), tr);
     if (p.xr.nranks > 1) xchg_allreduce<NT>(p.xr, grid);
     if (p.dbg && tid == 0) {   // timeline of this CTA: {setup clocks, slab-loop clocks, 4, cta}, {final barrier clocks, phase-2 (+ exchange) clocks, 5, cta}
         long long* d = p.dbg + 4 * (size_t)(p.ncta + p.ntiles) + 8 * (size_t)p.ncta;
         d[8 * bcta + 0] = t_k1 - t_k0; d[8 * bcta + 1] = t_k2 - t_k1; d[8 * bcta + 2] = 4; d[8 * bcta + 3] = bcta;
         d[8 * bcta + 4] = t_k3 - t_k2; d[8 * bcta + 5] = clock64() - t_k3; d[8 * bcta + 6] = 5; d[8 * bcta + 7] = bcta;
+        long long* d2 = d + 8 * (size_t)p.ncta;
+        d2[4 * bcta + 0] = tr[0]; d2[4 * bcta + 1] = tr[1]; d2[4 * bcta + 2] = 6; d2[4 * bcta + 3] = tr[2];
     }
 }
 

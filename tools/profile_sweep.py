@@ -39,6 +39,10 @@ if "--clocks" in sys.argv:
     if len(q4):
         print("timeline (clocks, mean / max over CTAs): setup %.0f / %.0f, slab loop %.0f / %.0f, final barrier %.0f / %.0f, phase 2 %.0f / %.0f" % (
               q4[:, 0].mean(), q4[:, 0].max(), q4[:, 1].mean(), q4[:, 1].max(), q5[:, 0].mean(), q5[:, 0].max(), q5[:, 1].mean(), q5[:, 1].max()))
+    q6 = r[r[:, 2] == 6]
+    if len(q6):
+        print("phase 2 (clocks, mean / max over CTAs): slot discovery %.0f / %.0f, partial loads %.0f / %.0f, stores %.0f / %.0f" % (
+              q6[:, 0].mean(), q6[:, 0].max(), q6[:, 1].mean(), q6[:, 1].max(), q6[:, 3].mean(), q6[:, 3].max()))
     r = r[r[:, 2] < 2]
     for dg in (0, 1):       # least-squares  clocks = a * chunks + b  over the segments (per slab pass: b is per segment and slab)
         q = r[r[:, 2] == dg].astype(float)
