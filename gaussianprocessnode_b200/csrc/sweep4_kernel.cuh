@@ -100,7 +100,7 @@ __device__ __forceinline__ void spin_ge(const unsigned* flag, unsigned target) {
 }
 
 // Shared memory (doubles): tab[2048] | barriers | union { consumer: stage[3] = { Ki [NB][LDB] | Kj [NB][LDB] | w [NB] }
-//                                                        generator: xstage[4] | rec[3][NB][REC] | zrec[TM][ZR] | zbias[TM]
+//                                                        generator: xstage[3] (one group of 128 raw points each) | rec[2][128][REC] | zrec[TM][ZR] | zbias[TM]
 //                                                        phase 2: S_ | ibuf }
 template <int TM, int NB, int DPAD>
 struct Smem4 {
@@ -111,7 +111,7 @@ struct Smem4 {
     static constexpr int XSTAGE = GP * SGP_MAX_D + 2 * GP;
     static constexpr int KSTAGE = 2 * NB * LDB + NB;
     static constexpr size_t tab = 0;
-    static constexpr size_t bars = tab + SGP_EXP_TAB;          // full[3] empty[3] xfull[4]
+    static constexpr size_t bars = tab + SGP_EXP_TAB;          // full[3] empty[3] xfull[3]
     static constexpr size_t segtab = bars + 16;                // this CTA's segments: kMaxSeg x {I, J, slot, lo, hi, -, -, -} (ints)
     static constexpr size_t u = segtab + kMaxSeg * 4;
     // consumer view

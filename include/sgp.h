@@ -78,7 +78,9 @@ int sgp_set_data_dev(sgp_ctx* ctx, int64_t N, const double* X_dev, const double*
  *   psi0 = sum_n w_n k(x_n,x_n),  psi1[M] = K_uf (w .* ybar),  psi2[M*M] = K_uf diag(w) K_uf' (full symmetric),
  *   sum_y2 = sum_n w_n (ybar_n^2 + yvar_n).
  * Any output pointer may be NULL (result stays on the device for the calls below).  With a communicator attached
- * (sgp_comm_init) the statistics are all-reduced over ranks before they are returned. */
+ * (sgp_comm_init) the call is COLLECTIVE: every rank must make it, and the statistics are summed over the ranks before they are
+ * returned (inside the sweep kernel through NVLink peer memory, or by one NCCL all-reduce); a rank that never arrives makes the
+ * others fail with SGP_ERR_CUDA after a time-out instead of hanging. */
 int sgp_sweep_psi(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2);
 
 /* sgp_set_data + sgp_sweep_psi as ONE call with a single host synchronisation: the per-step call of a host whose data change
@@ -151,7 +153,10 @@ int sgp_in_logmessage(sgp_ctx* ctx, int64_t N, int P, const double* Xp, int D_ou
                       double trW, double* f, double* grad, double* hess);
 
 /* ---- multi-GPU: N is sharded over ranks, one ctx per rank/GPU --------------------------------------------- */
-/* NCCL unique id (128 bytes) created on rank 0 and handed to the other ranks by the host. */
+/* NCCL unique id (128 bytes) created on rank 0 and handed to the other ranks by the host.  sgp_comm_init is collective: it creates the
+ * NCCL communicator and, on a single node with peer access (<= 8 ranks), maps one exchange region per rank into all peers through CUDA
+ * IPC so that the sweep kernel can sum the statistics itself (SGP_COMM_P2P=0 forces the NCCL path; M <= 2048 by default,
+ * SGP_COMM_P2P_MAXM raises it). */
 int sgp_comm_unique_id(char id[128]);
 int sgp_comm_init(sgp_ctx* ctx, int nranks, int rank, const char id[128]);
 

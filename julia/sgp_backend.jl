@@ -91,3 +91,51 @@ function grad_llh_new!(grad, θ; y_data, x_data, v, Uv, w, kernel, Xu, chunk_siz
     grad[2:end] .= dℓ .* σ′.(θ[2:end])
     return grad
 end
+
+
+# ---- one call per mini-batch: H2D of the batch, sweep, D2H of the statistics with a single host synchronisation -----------
+# (sgp_sweep_psi_host; X D×N, y N; Ψ1 / Ψ2 best wrapped around sgp_pinned_alloc memory)
+function sweep_psi_host!(meta::UniSGPMeta, X::Matrix{Float64}, y::Vector{Float64})
+    ψ0 = Ref(0.0); sy2 = Ref(0.0)
+    sgp_check(meta.h, ccall((:sgp_sweep_psi_host, libsgp), Cint,
+                            (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}),
+                            meta.h.ptr, size(X, 2), X, y, C_NULL, C_NULL, ψ0, vec(meta.Ψ1_trans), meta.Ψ2, sy2))
+    return ψ0[], sy2[]
+end
+
+# ---- MultiSGP :in messages for a whole chain (GPnode/MultiSGPnode.jl:162-236, prod override :38-45) ------------------------------
+# Xp: d×P×N cubature points (P per node), R: D×N columns W μ_y,n (row-major N×D for the library = this array's memory), Mv = reshape(μ_v, M, D),
+# S = sum(create_blockmatrix(Σ_v + μ_v μ_v', D, M) .* W).  Returns f (P×N); with derivatives = true also ∇f (d×P×N) and ∇²f (d×d×P×N).
+function in_logmessage(meta, Xp::Array{Float64,3}, R::Matrix{Float64}, Mv::Matrix{Float64}, S::Matrix{Float64}, trW::Float64; derivatives = false)
+    d, P, N = size(Xp); D = size(Mv, 2)
+    f = Matrix{Float64}(undef, P, N)
+    g = derivatives ? Array{Float64,3}(undef, d, P, N) : nothing
+    H = derivatives ? Array{Float64,4}(undef, d, d, P, N) : nothing
+    sgp_check(meta.h, ccall((:sgp_in_logmessage, libsgp), Cint,
+                            (Ptr{Cvoid}, Int64, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                            meta.h.ptr, N, P, Xp, D, R, Mv, S, trW, f, derivatives ? g : C_NULL, derivatives ? H : C_NULL))
+    return derivatives ? (f, g, H) : f
+end
+
+# the prod override for all N (left_n, right_n) pairs: spherical-radial points of every left_n -> ONE library call -> moment matching
+function prod_gaussian_logpdf_batch(meta, ms::Matrix{Float64}, Ps::Array{Float64,3}, R, Mv, S, trW)        # ms d×N, Ps d×d×N
+    d, N = size(ms); c = sqrt(d + 1.0)
+    Xp = Array{Float64,3}(undef, d, 2d + 1, N)
+    for n in 1:N
+        L = cholesky(Symmetric(Ps[:, :, n])).L
+        Xp[:, 1, n] = ms[:, n]
+        for j in 1:d
+            Xp[:, 1 + j, n] = ms[:, n] + c * L[:, j]; Xp[:, 1 + d + j, n] = ms[:, n] - c * L[:, j]
+        end
+    end
+    wts = vcat(1 / (d + 1), fill(0.5 / (d + 1), 2d))
+    g = exp.(in_logmessage(meta, Xp, R, Mv, S, trW)) .* wts                      # P×N
+    out = Vector{Any}(undef, N)
+    for n in 1:N
+        Z = sum(g[:, n]); μ = Xp[:, :, n] * g[:, n] / Z
+        if isnan(μ[1]); out[n] = MvNormalMeanCovariance(ms[:, n], Ps[:, :, n]); continue; end      # MultiSGPnode.jl:40-41
+        Δ = Xp[:, :, n] .- μ
+        out[n] = MvNormalMeanCovariance(μ, (Δ .* g[:, n]') * Δ' / Z)
+    end
+    return out
+end
