@@ -1,8 +1,8 @@
 // The data sweep of the sparse variational GP node: host-side launch logic of the two sweep kernels.
-//   sweep4_kernel.cuh  generate-once sweep (default): K_uf generated once per sweep into an L2-resident ring of slab panels,
+//   sweep4_kernel.cuh  generate-once sweep (M > 384): K_uf generated once per sweep into an L2-resident ring of slab panels,
 //                      consumed by a TMA-fed FP64 DMMA SYRK; see the notes at the top of that file and DESIGN.md section 4.1
-//   sweep_kernel.cuh   the first fused kernel (K_uf tiles regenerated in shared memory inside every Psi2 tile): SGP_SWEEP_IMPL=3,
-//                      and the fallback for shapes outside the first one's range.  Its notes follow.
+//   sweep_kernel.cuh   the first fused kernel (K_uf tiles regenerated in shared memory inside every Psi2 tile): M <= 384, where few row
+//                      blocks make the regeneration cheap, and the fallback for shapes outside the other one's range.  Its notes follow.
 //
 // Fused K_uf-tile generator + FP64 DMMA SYRK.
 //
@@ -140,8 +140,14 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
     {
         const long long chunks_ = (N + NB - 1) / NB;
         if (chunks_ * NB > Ncap) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: data buffers must be padded to a multiple of 32 points");
+        // Which kernel: the generate-once sweep pays off when K_uf would otherwise be regenerated often -- nblk + 1 times with nblk row blocks
+        // of 128 -- and when a slab carries enough tile work per CTA; measured crossover (tools/compare_sweep_kernels.py): nblk >= 4, i.e.
+        // M > 384 (M = 512: 1.02-1.09x, 640: 1.07x, 1024: 1.2-1.3x; M <= 384: the first fused kernel is 8-20 % faster at large N).
+        // SGP_SWEEP_IMPL=3 / 4 forces one of them.
         const char* impl = std::getenv("SGP_SWEEP_IMPL");
-        if (!(impl && impl[0] == '3')) {
+        const int nblk_ = (ctx->M + 127) / 128;
+        const bool want4 = impl && impl[0] == '4' ? true : impl && impl[0] == '3' ? false : (ctx->M > 192 && nblk_ >= 4);
+        if (want4) {
             int rc4 = sweep_launch4(ctx, X, y, yv, w, N, time_main);
             if (rc4 <= 0) return rc4;      // 1 = shape outside the generate-once kernel's range: fall through
         }

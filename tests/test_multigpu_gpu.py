@@ -28,7 +28,7 @@ def _worker(rank, world, port, out, p2p):
     uid = [SGPContext.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     rng = np.random.default_rng(11)
-    N, D, M = 50_001, 8, 300
+    N, D, M = 50_001, 8, 600                                      # M > 384: the generate-once kernel, which carries the fused exchange
     X = rng.normal(size=(N, D)); y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=N); yv = rng.uniform(0, 0.1, N)
     Z = X[:M].copy(); ell = np.full(D, 2.0)
     ctx = SGPContext(rank); ctx.set_kernel(1.2, ell); ctx.set_inducing(Z)

@@ -125,8 +125,9 @@ def test_many_tiles_per_cta(ctx, N, D, M):
     _check(ctx, X, y, Z, 0.9, np.full(D, 1.8))
 
 
-def test_pinned_buffers_and_segment_clocks(ctx):
+def test_pinned_buffers_and_segment_clocks(ctx, monkeypatch):
     from gaussianprocessnode_b200 import pinned_empty
+    monkeypatch.setenv("SGP_SWEEP_IMPL", "4")          # the record layout checked below is the generate-once kernel's
     rng = np.random.default_rng(21)
     N, D, M = 5000, 8, 256
     X = pinned_empty((N, D)); X[...] = rng.normal(size=(N, D))
@@ -208,6 +209,7 @@ def test_many_slabs_ring_wraparound(ctx, N, D, M, slab_mb, kind, monkeypatch):
     # the generate-once kernel cuts N into slabs whose K_uf panel lives in a ring of three L2 panels; tiny panels force dozens of slabs
     # (ring wrap-around, generation / consumption counters, RED accumulation across slabs, clipped last slab) on a small problem
     monkeypatch.setenv("SGP_SWEEP_SLAB_MB", slab_mb)
+    monkeypatch.setenv("SGP_SWEEP_IMPL", "4")          # (by default M <= 384 goes to the first fused kernel)
     rng = np.random.default_rng(N + M)
     X = rng.normal(size=(N, D)); Z = rng.normal(size=(M, D)); y = rng.normal(size=N); w = rng.uniform(0.5, 1.5, N)
     ell = 0.9 + rng.random(D) * 1.5
