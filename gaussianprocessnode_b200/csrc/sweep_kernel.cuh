@@ -312,14 +312,16 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     // MMA mapping.  Off-diagonal tile: WR x 4 warps, a WM x WN register tile each.  Diagonal tile: only the lower triangle
     // is needed (the reduce kernel mirrors it), i.e. 10 of the 16 SB x SB sub-blocks (SB = TM/4).  They are dealt out so
     // that every scheduler (warps w and w+4) gets exactly 2.5: slot 0 = one sub-block for every warp (the off-diagonal ones to
-    // warps 0-3, the diagonal ones to warps 4-7), slot 1 = HALF a sub-block (SB x SB/2) for warps 0-3: (2,0) left / right,
-    // (3,0) left / right.  40 DMMAs per k-step and scheduler instead of 64.
+    // warps 0-3, the diagonal ones to warps 4-7), slot 1 = a QUARTER sub-block (SB x 8) for every warp, cut from (2,0) and (3,0).
+    // 40 DMMAs per k-step and scheduler instead of 64, 20 per warp.
     constexpr int SB = TM / 4, SI = SB / 8;
     static_assert(!DIAG || NWARPS == 8, "diagonal sub-block schedule is written for 8 warps");
     const int wr = warp >> 2, wc = warp & 3;
     const int s0r = (0x32103321 >> (4 * warp)) & 0xf, s0c = (0x32102110 >> (4 * warp)) & 0xf;   // warps 7..0: rows 3,2,1,0,3,3,2,1
-    const int s1r = warp < 2 ? 2 : 3, s1c0 = (warp & 1) * (SB / 2);                           // slot 1: column half of (2,0) / (3,0)
-    const bool has1 = DIAG && warp < 4;
+    // slot 1: the two left-over sub-blocks (2,0) and (3,0) cut into SI column blocks of 8, one per warp (TM = 128: every warp carries 16 + 4
+    // DMMAs per k-step, so the two warps of a scheduler stay balanced -- one warp alone reaches only 76 % of the DMMA rate)
+    const int s1r = warp < SI ? 2 : 3, s1c0 = (warp % SI) * 8;
+    const bool has1 = DIAG && warp < 2 * SI;
     const int a_off = (DIAG ? s0r * SB : wr * WM) + (lane >> 2);              // + 8*i
     const int b_off = (DIAG ? s0c * SB : TM + wc * WN) + (lane >> 2);         // + 8*j
     const int a1_off = s1r * SB + (lane >> 2), b1_off = s1c0 + (lane >> 2);
@@ -347,7 +349,7 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
     auto body = [&](auto gen_tag, const int c) {
         constexpr bool GEN = decltype(gen_tag)::value;
         constexpr int FI = DIAG ? SI : MI, FJ = DIAG ? SI : NJ;   // fragment blocks of the (slot-0) tile
-        constexpr int FJ1 = (FJ + 1) / 2;                        // slot 1 of a diagonal tile: half the columns
+        constexpr int FJ1 = 1;                                   // slot 1 of a diagonal tile: one 8-column block
         constexpr int DPK = FI * FJ;                  // DMMAs per k-step (diagonal: of slot 0)
         constexpr int TOTAL = KSPAN * DPK;            // DMMAs one generator unit is interleaved with
         static_assert(TOTAL >= NST, "generator schedule");
@@ -442,7 +444,7 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const SmemPtrs
 #pragma unroll
             for (int i = 0; i < SI; ++i)
 #pragma unroll
-                for (int j = 0; j < (sl ? (SI + 1) / 2 : SI); ++j) {
+                for (int j = 0; j < (sl ? 1 : SI); ++j) {
                     const int rr = r0 + 8 * i + (lane >> 2), cc = c0 + 8 * j + 2 * (lane & 3);
                     *reinterpret_cast<double2*>(out + rr * TM + cc) = make_double2(acc[sl * SI + i][j][0], acc[sl * SI + i][j][1]);
                 }
