@@ -132,7 +132,8 @@ void sgp_destroy(sgp_ctx* ctx) {
     cudaFree(ctx->Z_dev); if (!ctx->stats_external) cudaFree(ctx->stats_dev); cudaFree(ctx->work_dev); cudaFree(ctx->zrec_dev); cudaFree(ctx->exptab_dev);
     cudaFree(ctx->dense_dev); cudaFree(ctx->info_dev); cudaFree(ctx->KuuL_dev); cudaFree(ctx->sp_X_dev); cudaFree(ctx->sp_w_dev);
     cudaFree(ctx->sp_y_dev); cudaFree(ctx->sweep_dbg_dev); cudaFree(ctx->theta_dev); cudaFree(ctx->Kinv_dev); cudaFree(ctx->kuu_dinv_dev);
-    cudaFree(ctx->dinv_dev); cudaFree(ctx->post_dev); cudaFree(ctx->unc_dev); cudaFree(ctx->kbuf_dev); cudaFree(ctx->sweep_flags_dev); cudaFree(ctx->flush_dev); cudaFree(ctx->in_dev);
+    cudaFree(ctx->dinv_dev); cudaFree(ctx->post_dev); cudaFree(ctx->unc_dev); if (ctx->fetch_host) cudaFreeHost(ctx->fetch_host);
+    cudaFree(ctx->kbuf_dev); cudaFree(ctx->sweep_flags_dev); cudaFree(ctx->flush_dev); cudaFree(ctx->in_dev);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -179,6 +180,11 @@ static int alloc_data(sgp_ctx* ctx, int64_t N) {
     SGP_CUDA(ctx, cudaMalloc((void**)&ctx->y_dev, (size_t)cap * sizeof(double)));
     SGP_CUDA(ctx, cudaMalloc((void**)&ctx->yv_dev, (size_t)cap * sizeof(double)));
     SGP_CUDA(ctx, cudaMalloc((void**)&ctx->w_dev, (size_t)cap * sizeof(double)));
+    // zeroed ONCE: the sweep stages whole chunks of 32 points, and rows [N, cap) only have to hold finite values (they generate exact zeros)
+    SGP_CUDA(ctx, cudaMemsetAsync(ctx->X_dev, 0, (size_t)cap * ctx->D * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, (size_t)cap * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaMemsetAsync(ctx->yv_dev, 0, (size_t)cap * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaMemsetAsync(ctx->w_dev, 0, (size_t)cap * sizeof(double), ctx->stream));
     ctx->Ncap = cap; ctx->Dcap = ctx->D;
     return SGP_OK;
 }
@@ -201,21 +207,14 @@ static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* y
     int rc = alloc_data(ctx, N > 0 ? N : 32); if (rc) return rc;
     const int D = ctx->D;
     const size_t cap = (size_t)ctx->Ncap;
-    // the sweep stages whole chunks of 32 points: rows [N, cap) must hold finite values (they generate exact zeros)
-    const size_t n = (size_t)N, tail = cap - n;
-    if (tail) SGP_CUDA(ctx, cudaMemsetAsync(ctx->X_dev + n * D, 0, tail * D * sizeof(double), ctx->stream));
+    // the sweep stages whole chunks of 32 points: rows [N, cap) hold zeros from the allocation or finite values of an earlier, longer data
+    // set -- either way they generate exact zeros (no per-upload memset)
+    const size_t n = (size_t)N;
     if (n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->X_dev, X, n * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (ybar && n) {
-        SGP_CUDA(ctx, cudaMemcpyAsync(ctx->y_dev, ybar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        if (tail) SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev + n, 0, tail * sizeof(double), ctx->stream));
-    } else {
-        SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, cap * sizeof(double), ctx->stream));
-    }
+    if (ybar && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->y_dev, ybar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, cap * sizeof(double), ctx->stream));
     if (yvar && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->yv_dev, yvar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (wts && n) {
-        SGP_CUDA(ctx, cudaMemcpyAsync(ctx->w_dev, wts, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        if (tail) SGP_CUDA(ctx, cudaMemsetAsync(ctx->w_dev + n, 0, tail * sizeof(double), ctx->stream));
-    }
+    if (wts && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->w_dev, wts, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->N = N; ctx->have_yv = yvar != nullptr; ctx->have_w = wts != nullptr; ctx->have_stats = false;
     return SGP_OK;
 }
@@ -251,12 +250,21 @@ static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, d
     const size_t M = (size_t)ctx->M, Do = (size_t)ctx->Dout;
     double* s2 = ctx->stats_dev; double* s1 = s2 + M * M; double* sc = s1 + M * Do;
     if (psi2) SGP_CUDA(ctx, cudaMemcpyAsync(psi2, s2, M * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (psi1) SGP_CUDA(ctx, cudaMemcpyAsync(psi1, s1, M * Do * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    double sc_h[4] = {0, 0, 0, 0};
-    SGP_CUDA(ctx, cudaMemcpyAsync(sc_h, sc, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    // Psi1 and the scalars are adjacent on the device: ONE copy into a pinned staging buffer, split on the host
+    const size_t small = M * Do + 4;
+    if (ctx->fetch_cap < small) {
+        if (ctx->fetch_host) cudaFreeHost(ctx->fetch_host);
+        ctx->fetch_host = nullptr; ctx->fetch_cap = 0;
+        SGP_CUDA(ctx, cudaHostAlloc((void**)&ctx->fetch_host, (small + 1024) * sizeof(double), cudaHostAllocDefault));
+        ctx->fetch_cap = small + 1024;
+    }
+    double* stage = ctx->fetch_host;
+    if (psi1) SGP_CUDA(ctx, cudaMemcpyAsync(stage, s1, small * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    else SGP_CUDA(ctx, cudaMemcpyAsync(stage + M * Do, sc, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (psi0) *psi0 = sc_h[0];
-    if (sum_y2) *sum_y2 = sc_h[1];
+    if (psi1) memcpy(psi1, stage, M * Do * sizeof(double));
+    if (psi0) *psi0 = stage[M * Do];
+    if (sum_y2) *sum_y2 = stage[M * Do + 1];
     return SGP_OK;
 }
 

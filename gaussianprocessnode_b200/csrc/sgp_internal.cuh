@@ -50,6 +50,7 @@ struct sgp_ctx {
     double* zrec_dev = nullptr;  size_t zrec_cap = 0;      // prepared inducing rows
     void* kbuf_window = nullptr; size_t kbuf_window_bytes = 0;   // L2 access-policy window currently set on the stream
     double* kbuf_dev = nullptr;  size_t kbuf_cap = 0;      // L2-resident K_uf panel of one slab (generate-once sweep)
+    double* fetch_host = nullptr; size_t fetch_cap = 0;    // pinned staging of the small results (Psi1 | scalars)
     void* flush_dev = nullptr; size_t flush_cap = 0;       // L2 flush buffer of sgp_sweep_timed_flushed
     unsigned* sweep_flags_dev = nullptr;                   // generation / consumption counters of the generate-once sweep
     double* exptab_dev = nullptr;

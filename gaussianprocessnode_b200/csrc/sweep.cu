@@ -73,8 +73,10 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     const int nring = nslabs > 2 ? 3 : nslabs;
     rc = sgp_ensure(ctx, &ctx->kbuf_dev, &ctx->kbuf_cap, (size_t)nring * slab_chunks * chunk_doubles); if (rc) return rc;
     if (3 * (nblk + 1) > 1024) return 1;
-    if (!ctx->sweep_flags_dev) SGP_CUDA(ctx, cudaMalloc((void**)&ctx->sweep_flags_dev, 1024 * sizeof(unsigned)));
-    SGP_CUDA(ctx, cudaMemsetAsync(ctx->sweep_flags_dev, 0, (size_t)nring * (nblk + 1) * sizeof(unsigned), ctx->stream));
+    if (!ctx->sweep_flags_dev) {      // zeroed once; every sweep kernel leaves the counters zeroed when it ends
+        SGP_CUDA(ctx, cudaMalloc((void**)&ctx->sweep_flags_dev, 1024 * sizeof(unsigned)));
+        SGP_CUDA(ctx, cudaMemsetAsync(ctx->sweep_flags_dev, 0, 1024 * sizeof(unsigned), ctx->stream));
+    }
     size_t need_stats = (size_t)M * M + (size_t)M + 8;
     rc = sgp_ensure_stats(ctx, need_stats); if (rc) return rc;
     ctx->Dout = 1;

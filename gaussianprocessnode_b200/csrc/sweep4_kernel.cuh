@@ -889,6 +889,9 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     if (p.dbg) t_k3 = clock64();
     long long tr[3] = {0, 0, 0};
     reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)), tr);
+    // the dependency counters are dead after the last grid barrier: leave them zeroed for the next launch (no memset per sweep on the host)
+    if (bcta == 0)
+        for (int i = tid; i < p.nring * (p.nblk + 1); i += NT) p.flags[i] = 0u;
     if (p.xr.nranks > 1) xchg_allreduce<NT>(p.xr, grid);
     if (p.dbg && tid == 0) {   // timeline of this CTA: {setup clocks, slab-loop clocks, 4, cta}, {final barrier clocks, phase-2 (+ exchange) clocks, 5, cta}
         long long* d = p.dbg + 4 * (size_t)(p.ncta + p.ntiles) + 8 * (size_t)p.ncta;
