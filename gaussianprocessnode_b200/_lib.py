@@ -41,6 +41,7 @@ SIGNATURES = {
     "sgp_theta_objective": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_double, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
     "sgp_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "sgp_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "sgp_uncertain_node_terms": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sgp_in_logmessage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p, c_double_p, c_double_p,
                           ctypes.c_double, c_double_p, c_double_p, c_double_p]),
     "sgp_sweep_timed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p]),

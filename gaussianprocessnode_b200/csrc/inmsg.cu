@@ -96,7 +96,82 @@ __global__ void in_reduce_kernel(const double* __restrict__ Xp, const double* __
     }
 }
 
+// one warp per node: sums over the node's S sigma points of  w k(x,x),  w k' Kinv k,  w k' mu_v,  w |Uv k|^2
+__global__ void node_terms_kernel(const double* __restrict__ K, const double* __restrict__ Q, const double* __restrict__ T, const double* __restrict__ wv,
+                                  const double* __restrict__ mu, double* __restrict__ out, long long N, int S, int M, double variance) {
+    const long long n = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const long long p = n * S + s;
+        const double w = wv[p];
+        double q = 0.0, l = 0.0, t2 = 0.0;
+        for (int m = lane; m < M; m += 32) {
+            const double k = K[p * M + m], t = T[p * M + m];
+            q = fma(k, Q[p * M + m], q);
+            l = fma(k, mu[m], l);
+            t2 = fma(t, t, t2);
+        }
+        a0 = fma(w, variance, a0); a1 = fma(w, q, a1); a2 = fma(w, l, a2); a3 = fma(w, t2, a3);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (lane == 0) { out[n] = a0; out[N + n] = a1; out[2 * N + n] = a2; out[3 * N + n] = a3; }
+}
+// out[0] = trace of the M x M matrix A, out[1] = |B|_F^2   (single block, fixed order)
+__global__ void trace_frob_kernel(const double* __restrict__ A, const double* __restrict__ B, int M, double* __restrict__ out) {
+    __shared__ double s0[256], s1[256];
+    double t = 0.0, f = 0.0;
+    for (int i = threadIdx.x; i < M; i += 256) t += A[(size_t)i * M + i];
+    for (size_t i = threadIdx.x; i < (size_t)M * M; i += 256) f = fma(B[i], B[i], f);
+    s0[threadIdx.x] = t; s1[threadIdx.x] = f;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; } __syncthreads(); }
+    if (threadIdx.x == 0) { out[0] = s0[0]; out[1] = s1[0]; }
+}
+
 }  // namespace
+
+extern "C" int sgp_uncertain_node_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* psi0_n, double* q_kinv_n, double* lin_n, double* q_rv_n,
+                                        double* tr_kinv, double* frob_uv) {
+    if (!ctx) return SGP_ERR_ARG;
+    if (ctx->sp_N <= 0 || ctx->sp_S <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "uncertain_node_terms: needs the sigma-point cloud of a preceding sgp_sweep_psi_uncertain (methods 0-2)");
+    if (!ctx->have_kuu || !ctx->Kinv_dev) SGP_FAIL(ctx, SGP_ERR_ARG, "uncertain_node_terms: sgp_kuu_factor first");
+    if (!mu_v || !Uv) SGP_FAIL(ctx, SGP_ERR_ARG, "uncertain_node_terms: mu_v and Uv required");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const int M = ctx->M, D = ctx->D, S = ctx->sp_S;
+    const long long N = ctx->sp_N, NP = N * S;
+    const size_t MM = (size_t)M * M, KM = (size_t)NP * M;
+    const size_t need = MM + M + SGP_MAX_D + 3 * KM + 4 * (size_t)N + 64;
+    int rc = sgp_ensure(ctx, &ctx->in_dev, &ctx->in_cap, need); if (rc) return rc;
+    double* Uvd = ctx->in_dev; double* mud = Uvd + MM; double* elld = mud + M; double* K = elld + SGP_MAX_D; double* Q = K + KM; double* T = Q + KM;
+    double* out = T + KM; double* sc = out + 4 * (size_t)N;
+    double ell_inv[SGP_MAX_D] = {0};
+    for (int d = 0; d < D; ++d) ell_inv[d] = 1.0 / ctx->ell[d];
+    cudaStream_t st = ctx->stream;
+    SGP_CUDA(ctx, cudaMemcpyAsync(Uvd, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, st));
+    SGP_CUDA(ctx, cudaMemcpyAsync(mud, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, st));
+    SGP_CUDA(ctx, cudaMemcpyAsync(elld, ell_inv, sizeof ell_inv, cudaMemcpyHostToDevice, st));
+    in_kmat_kernel<<<(unsigned)((KM + 255) / 256), 256, 0, st>>>(ctx->sp_X_dev, ctx->Z_dev, K, nullptr, NP, M, D, ctx->kind, ctx->variance, elld, 0);
+    SGP_CUDA(ctx, cudaGetLastError());
+    rc = sgp_gemm(ctx, 0, 0, M, (int)NP, M, 1.0, ctx->Kinv_dev, M, K, M, 0.0, Q, M, 0); if (rc) return rc;
+    rc = sgp_gemm(ctx, 0, 0, M, (int)NP, M, 1.0, Uvd, M, K, M, 0.0, T, M, 0); if (rc) return rc;
+    node_terms_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, st>>>(K, Q, T, ctx->sp_w_dev, mud, out, N, S, M, ctx->variance);
+    trace_frob_kernel<<<1, 256, 0, st>>>(ctx->Kinv_dev, Uvd, M, sc);
+    SGP_CUDA(ctx, cudaGetLastError());
+    if (psi0_n) SGP_CUDA(ctx, cudaMemcpyAsync(psi0_n, out, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (q_kinv_n) SGP_CUDA(ctx, cudaMemcpyAsync(q_kinv_n, out + N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (lin_n) SGP_CUDA(ctx, cudaMemcpyAsync(lin_n, out + 2 * N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (q_rv_n) SGP_CUDA(ctx, cudaMemcpyAsync(q_rv_n, out + 3 * N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    double sch[2] = {0.0, 0.0};
+    SGP_CUDA(ctx, cudaMemcpyAsync(sch, sc, sizeof sch, cudaMemcpyDeviceToHost, st));
+    SGP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (tr_kinv) *tr_kinv = sch[0];
+    if (frob_uv) *frob_uv = sch[1];
+    return SGP_OK;
+}
 
 extern "C" int sgp_in_logmessage(sgp_ctx* ctx, int64_t N, int P, const double* Xp, int D_out, const double* R, const double* Mv, const double* S,
                                  double trW, double* f, double* grad, double* hess) {

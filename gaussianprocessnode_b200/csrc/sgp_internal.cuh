@@ -67,6 +67,7 @@ struct sgp_ctx {
 
     // uncertain-input scratch (sigma-point cloud)
     double *sp_X_dev = nullptr, *sp_w_dev = nullptr, *sp_y_dev = nullptr; size_t sp_cap = 0;
+    int64_t sp_N = 0; int sp_S = 0;                         // nodes / sigma points per node of the resident cloud (0 = none)
     double* unc_dev = nullptr; size_t unc_cap = 0;          // arena for the per-call scratch of sgp_sweep_psi_uncertain
 
     // resident prior / posterior of v (api.cu: post_*): [Lambda_prior | xi_prior | mu | Sigma | Uv]

@@ -476,6 +476,7 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
         sigma_kernel<<<nb((size_t)N, 128), 128, 0, ctx->stream>>>(method, p, d, N, S, mean_d, cov_d, (R_d && D_out == 1) ? R_d : nullptr, gh_d,
                                                                  ctx->sp_X_dev, ctx->sp_w_dev, ctx->sp_y_dev, ctx->info_dev);
         UC(cudaGetLastError());
+        ctx->sp_N = N; ctx->sp_S = S;          // the cloud stays resident for sgp_uncertain_node_terms
         // weighted fused sweep over the cloud: Psi2 = sum w k k', Psi1 (D_out = 1) = sum w r k, Psi0 = sigma^2 sum w
         rc = sgp_sweep_launch(ctx, ctx->sp_X_dev, ctx->sp_y_dev, nullptr, ctx->sp_w_dev, (int64_t)NS, (int64_t)cap, false);
         if (rc) { cleanup(); return rc; }
@@ -484,6 +485,7 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
             psi1n_cloud_kernel<<<nb((size_t)N * M), 256, 0, ctx->stream>>>(ctx->sp_X_dev, ctx->sp_w_dev, ctx->Z_dev, ell_inv_d, p1n_d, N, S, M, d,
                                                                            ctx->kind, ctx->variance);
     } else {
+        ctx->sp_N = 0; ctx->sp_S = 0;          // closed form: no sigma-point cloud
         const int RS = 2 * d * d + 2 + d;
         double* rec_d = nullptr;
         rec_d = take((size_t)N * RS);

@@ -344,6 +344,51 @@ def prod_uncertain(left, right: BufferUniSGP):
     return MvNormalWeightedMeanPrecision(xi0 + w * psi1, Lam0 + w * psi2)
 
 
+def _uncertain_node_terms(q_outs, q_ins, q_v, q_theta, meta: UniSGPMeta):
+    """Per-node I1_n, I2_n of the uncertain-input UniSGP rules (UniSGPnode.jl:177-192, 290-313) for a whole set of nodes: the sigma-point
+    cloud of ONE sgp_sweep_psi_uncertain, then sgp_uncertain_node_terms (kernel columns of all sigma points -> K_uu^-1 K and U_v K tile
+    GEMMs -> per-node weighted sums).  The reference adds 1e-8 I to every Psi2_n and clamps both terms to [1e-12, 1e12] per node."""
+    _configure(meta, mean(q_theta))
+    ctx = _ctx(meta)
+    _ensure_kuu(meta)
+    mid, p = _method_of(meta)
+    mv = [mean_var(q) for q in q_ins]
+    means = np.stack([np.atleast_1d(np.asarray(m, dtype=np.float64)) for m, _ in mv])
+    covs = np.stack([np.atleast_2d(np.asarray(v, dtype=np.float64)) for _, v in mv])
+    N = means.shape[0]
+    ctx.sweep_psi_uncertain(mid, means, covs, R=None, D_out=1, p=p)          # builds (and leaves resident) the sigma-point cloud
+    psi0, qk, lin, qr, tr_kinv, frob_uv = ctx.uncertain_node_terms(mean(q_v), meta.Uv, N)
+    I1 = np.clip(psi0 - qk - 1e-8 * tr_kinv, 1e-12, 1e12)
+    if q_outs is None:
+        return I1, None, lin
+    yv = [mean_var(q) for q in q_outs]
+    y = np.array([float(a) for a, _ in yv]); vy = np.array([float(b) for _, b in yv])
+    I2 = np.clip(y * y + vy - 2.0 * y * lin + qr + 1e-8 * frob_uv, 1e-12, 1e12)
+    return I1, I2, lin
+
+
+def rule_w_uncertain(q_outs, q_ins, q_v, q_theta, meta: UniSGPMeta):
+    """@rule UniSGP(:w, Marginalisation) (q_out, q_in::UnivariateGaussianDistributionsFamily, ...) -- UniSGPnode.jl:177-192 -- for a whole set
+    of nodes: the N messages GammaShapeRate(1.5, (I1_n + I2_n) / 2) (the clamps are per node, so the messages are returned individually)."""
+    I1, I2, _ = _uncertain_node_terms(q_outs, q_ins, q_v, q_theta, meta)
+    return [GammaShapeRate(1.5, 0.5 * float(a + b)) for a, b in zip(I1, I2)]
+
+
+def rule_out_uncertain(q_ins, q_v, q_w, q_theta, meta: UniSGPMeta):
+    """@rule UniSGP(:out, Marginalisation) (q_in::UnivariateGaussianDistributionsFamily, ...) -- UniSGPnode.jl:85-93: NormalMeanPrecision(Psi1_n' mu_v, w_bar)."""
+    _, _, lin = _uncertain_node_terms(None, q_ins, q_v, q_theta, meta)
+    w = mean(q_w)
+    return [NormalMeanPrecision(float(v), w) for v in lin]
+
+
+def average_energy_uncertain(q_outs, q_ins, q_v, q_w, q_theta, meta: UniSGPMeta):
+    """@average_energy UniSGP (q_out, q_in::UnivariateGaussianDistributionsFamily, ..., q_w::GammaShapeRate) -- UniSGPnode.jl:290-313: the N
+    per-node energies U_n = (I1_n w_bar - E[ln w] + ln 2 pi + I2_n w_bar) / 2."""
+    I1, I2, _ = _uncertain_node_terms(q_outs, q_ins, q_v, q_theta, meta)
+    w_bar = mean(q_w)
+    return 0.5 * (I1 * w_bar - mean_log(q_w) + LOG2PI + I2 * w_bar)
+
+
 @dataclass
 class MultiSGPMeta:
     """helper_functions/gp_helperfunction.jl:55-64 -- same fields, same order (GPCache is scratch only and has no

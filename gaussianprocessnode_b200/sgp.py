@@ -243,6 +243,17 @@ class SGPContext:
         self._ck(self.lib.sgp_predict_mean(self.h, Xt.shape[0], _p(Xt), _p(mu_v), _p(out)))
         return out
 
+    def uncertain_node_terms(self, mu_v, Uv, N):
+        """Per-node (Psi0_n, tr(Kuu^-1 Psi2_n), Psi1_n' mu_v, tr(Uv'Uv Psi2_n)) of the last sweep_psi_uncertain's N nodes, plus tr(Kuu^-1) and |Uv|_F^2
+        (sgp_uncertain_node_terms)."""
+        M = self.M
+        mu_v = _f64(mu_v, (M,))
+        Uv = np.asfortranarray(np.asarray(Uv, dtype=np.float64).reshape(M, M))
+        outs = [np.empty(int(N)) for _ in range(4)]
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._ck(self.lib.sgp_uncertain_node_terms(self.h, _p(mu_v), _p(Uv), *[_p(o) for o in outs], ctypes.byref(a), ctypes.byref(b)))
+        return outs[0], outs[1], outs[2], outs[3], a.value, b.value
+
     def in_logmessage(self, Xp, Mv, S, trW, R=None, grad=False, hess=False):
         """log backward message of `@rule MultiSGP(:in)` at P points for each of N nodes (sgp_in_logmessage).
         Xp: (N, P, d); Mv: (M, D_out) columns mu_v^(d); S: (M, M) = sumRvblk_W; R: (N, D_out) rows (W mu_y,n)' or None.

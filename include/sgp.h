@@ -140,6 +140,16 @@ int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* m
 int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const double* Uv, double w, double jitter, double* value,
                         double* dvariance, double* dlengthscale);
 
+/* Per-NODE expectations for the uncertain-input UniSGP rules, from the sigma-point cloud of the preceding sgp_sweep_psi_uncertain (methods 0-2,
+ * resident on the device): `@rule UniSGP(:w)` (GPnode/UniSGPnode.jl:177-192), `:out` (:85-93), `@average_energy` (:290-313).  These rules clamp
+ * I1 and I2 per node, so they need per-node values, not sums:
+ *   psi0_n = Psi0_n,  q_kinv_n = tr(Kuu^-1 Psi2_n),  lin_n = Psi1_n' mu_v (the :out mean),  q_rv_n = tr(Uv' Uv Psi2_n)   -- N doubles each, any may be NULL;
+ *   tr_kinv = tr(Kuu^-1), frob_uv = |Uv|_F^2 (what the reference's `+ 1e-8 I` on Psi2 adds to the two traces).
+ * The host finishes I1 = clamp(psi0_n - q_kinv_n - 1e-8 tr_kinv), I2 = clamp(y^2 + v - 2 y lin_n + q_rv_n + 1e-8 frob_uv).  mu_v (M), Uv (M x M upper,
+ * column-major) are inputs; needs sgp_kuu_factor. */
+int sgp_uncertain_node_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* psi0_n, double* q_kinv_n, double* lin_n, double* q_rv_n,
+                             double* tr_kinv, double* frob_uv);
+
 /* ---- backward message towards the input of MultiSGP ------------------------------------- */
 /* `@rule MultiSGP(:in, Marginalisation)` (GPnode/MultiSGPnode.jl:162-185, 187-211, 213-236) for N nodes at once.  Per node the reference
  * returns the closure

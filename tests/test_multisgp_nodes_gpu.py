@@ -113,3 +113,40 @@ def test_unisgp_uncertain_v_rule_matches_per_node_fold():
         msg = nd.rule_v_uncertain(nd.PointMass(y[n]), nd.NormalMeanVariance(m[n], v[n]), nd.PointMass(w), nd.PointMass(theta), meta)
         marginal = nd.prod_uncertain(marginal, msg)
     assert fro(marginal.xi, left[0]) < 1e-10 and fro(marginal.Lam, left[1]) < 1e-10
+
+
+@pytest.mark.parametrize("method", [(cub.GAUSSHERMITE, 21), (cub.SRCUBATURE, 0), (cub.GENUT, 0)])
+def test_unisgp_uncertain_w_out_energy_rules_match_per_node_rules(method):
+    # @rule UniSGP(:w) / (:out) / @average_energy with q_in Gaussian (UniSGPnode.jl:177-192, 85-93, 290-313): per-NODE results (the reference
+    # clamps I1, I2 per node and adds 1e-8 I to every Psi2_n) from sgp_uncertain_node_terms against the oracle's per-node rules
+    from gaussianprocessnode_b200 import nodes as nd
+    from scipy.linalg import cholesky
+    rng = np.random.default_rng(9)
+    N, M = 80, 16
+    Z = np.linspace(-4, 4, M)
+    m = rng.normal(size=N) * 2.0; v = rng.uniform(0.01, 0.3, N); y = rng.normal(size=N); vy = rng.uniform(0.0, 0.2, N)
+    theta = np.array([0.4, 0.9])
+    kern = lambda t: (kernels.softplus(t[0]), kernels.softplus(t[1:]), 0)
+    var, ell, _ = kern(theta)
+    jitter = 1e-6
+    Kuu = kernels.kuu(Z[:, None], var, ell, jitter=jitter)
+    KuuL = np.linalg.cholesky(Kuu)
+    mu_v = rng.normal(size=M); C = rng.normal(size=(M, M)) * 0.2
+    Sigma_v = C @ C.T + 0.05 * np.eye(M)
+    Uv = cholesky(Sigma_v + np.outer(mu_v, mu_v), lower=False)
+    ometa = unisgp.UniSGPMeta(method if method[0] == cub.GAUSSHERMITE else method[0], Z, np.zeros((1, 1)), np.zeros((M, 1)), np.zeros((M, M)), KuuL, kern, Uv, 0, N)
+    meta = nd.UniSGPMeta(method if method[0] == cub.GAUSSHERMITE else method[0], Z, np.zeros((1, 1)), np.zeros((M, 1)), np.zeros((M, M)), None, kern, Uv, 0, N)
+    meta.kuu_jitter = jitter
+    q_outs = [nd.NormalMeanVariance(y[n], vy[n]) for n in range(N)]
+    q_ins = [nd.NormalMeanVariance(m[n], v[n]) for n in range(N)]
+    q_v = nd.MvNormalMeanCovariance(mu_v, Sigma_v); q_w = nd.GammaShapeRate(3.0, 0.7); q_theta = nd.PointMass(theta)
+    msgs = nd.rule_w_uncertain(q_outs, q_ins, q_v, q_theta, meta)
+    outs = nd.rule_out_uncertain(q_ins, q_v, q_w, q_theta, meta)
+    U = nd.average_energy_uncertain(q_outs, q_ins, q_v, q_w, q_theta, meta)
+    for n in range(N):
+        shape, rate = unisgp.rule_w_uncertain(y[n], vy[n], (m[n], v[n]), mu_v, theta, ometa)
+        assert msgs[n].a == shape and abs(msgs[n].b - rate) <= 1e-9 * max(abs(rate), 1e-3)
+        om, _ = unisgp.rule_out_uncertain((m[n], v[n]), mu_v, 3.0 / 0.7, theta, ometa)
+        assert abs(outs[n].m - om) <= 1e-10 * max(abs(om), 1.0)
+        oU = unisgp.average_energy_uncertain(y[n], vy[n], (m[n], v[n]), mu_v, (3.0, 0.7), theta, ometa)
+        assert abs(U[n] - oU) <= 1e-9 * max(abs(oU), 1.0)
