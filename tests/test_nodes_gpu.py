@@ -58,6 +58,13 @@ def test_unisgp_pass_matches_per_point_reference_schedule(classification):
         q_out = nd.NormalMeanVariance(y[n], yv[n]) if classification else nd.PointMass(y[n])
         U += nd.average_energy(q_out, nd.PointMass(X[n]), q_v, nd.GammaShapeRate(*q_w), q_theta, meta)
     assert abs(U - o_U) < 1e-8 * abs(o_U)
+    if not classification:
+        # q_out, q_in, q_w all PointMass (UniSGPnode.jl:411-436): E[ln w] = ln w, chol(Sigma_v + mu mu').U recomputed by the rule
+        o_Up = sum(unisgp.average_energy_pointmass_wpoint(y[n], X[n], o_mu, o_Sig, w, theta, ometa) for n in range(N))
+        Up = 0.0
+        for n in range(N):
+            Up += nd.average_energy(nd.PointMass(y[n]), nd.PointMass(X[n]), q_v, qw, q_theta, meta)
+        assert abs(Up - o_Up) < 1e-8 * abs(o_Up)
     out = nd.rule_out(nd.PointMass(X[0]), q_v, qw, q_theta, meta)
     ref_m, _ = unisgp.rule_out_pointmass(X[0], o_mu, w, theta, ometa)
     assert abs(out.m - ref_m) < 1e-10 * max(abs(ref_m), 1.0) and out.w == w
