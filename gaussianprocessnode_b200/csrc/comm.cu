@@ -70,16 +70,23 @@ void setup_p2p(sgp_ctx* ctx, SgpComm* c) {
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
     if (ok) ok = cudaIpcGetMemHandle(&mine, c->region) == cudaSuccess;
-    // handles (64 bytes each) + one success word per rank travel through NCCL
-    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    // handles (64 bytes each) + one success word + the device's PCI identity per rank travel through NCCL
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 16;
+    long long pci = -1;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->dev) == cudaSuccess)
+            pci = ((long long)prop.pciDomainID << 32) | ((long long)prop.pciBusID << 16) | (long long)prop.pciDeviceID;
+    }
     char* dev = nullptr;
     std::vector<char> host(rec * c->nranks, 0);
     bool ok_all = cudaMalloc((void**)&dev, rec * (c->nranks + 1)) == cudaSuccess;
     if (ok_all) {
-        char mine_rec[sizeof(cudaIpcMemHandle_t) + 8];
+        char mine_rec[sizeof(cudaIpcMemHandle_t) + 16];
         memcpy(mine_rec, &mine, sizeof mine);
         long long flag = ok ? 1 : 0;
         memcpy(mine_rec + sizeof mine, &flag, 8);
+        memcpy(mine_rec + sizeof mine + 8, &pci, 8);
         ok_all = cudaMemcpyAsync(dev + rec * c->nranks, mine_rec, rec, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
         if (a.AllGather(dev + rec * c->nranks, dev, rec, /*ncclChar*/ 0, c->comm, ctx->stream) != 0) ok_all = false;
         if (cudaMemcpyAsync(host.data(), dev, rec * c->nranks, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) ok_all = false;
@@ -90,6 +97,15 @@ void setup_p2p(sgp_ctx* ctx, SgpComm* c) {
     if (ok_all)
         for (int q = 0; q < c->nranks; ++q) { long long f = 0; memcpy(&f, host.data() + rec * q + sizeof(cudaIpcMemHandle_t), 8); good += f == 1; }
     bool mapped = ok_all && good == c->nranks;
+    // two ranks on ONE device cannot run their sweep kernels side by side (time-sliced contexts): the in-kernel barriers would never meet
+    if (mapped)
+        for (int a_ = 0; a_ < c->nranks && mapped; ++a_)
+            for (int b_ = a_ + 1; b_ < c->nranks; ++b_) {
+                long long pa = 0, pb = 0;
+                memcpy(&pa, host.data() + rec * a_ + sizeof(cudaIpcMemHandle_t) + 8, 8);
+                memcpy(&pb, host.data() + rec * b_ + sizeof(cudaIpcMemHandle_t) + 8, 8);
+                if (pa == pb || pa < 0 || pb < 0) { mapped = false; break; }
+            }
     if (mapped) {
         for (int q = 0; q < c->nranks && mapped; ++q) {
             if (q == c->rank) { c->peers[q] = c->region; continue; }
