@@ -49,7 +49,7 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     const int ntiles = nblk * (nblk + 1) / 2;
     const long long chunks = (N + NB - 1) / NB;
     // slab: as many chunks as keep the panel (nblk x 32 x (TM + 4) doubles per chunk) inside the L2 budget
-    double slab_mb = 16.0;        // per panel; the ring holds three: 48 MB is what stays in the L2 (persisting window) without DRAM re-reads
+    double slab_mb = 20.0;        // per panel; the ring holds three: 60 MB is what stays in the L2 (persisting window) without DRAM re-reads
     if (const char* e = std::getenv("SGP_SWEEP_SLAB_MB")) { double v = std::atof(e); if (v > 0.0) slab_mb = v; }
     const size_t chunk_doubles = (size_t)nblk * NB * (TM + 4);
     long long max_slab = (long long)(slab_mb * 1048576.0 / (chunk_doubles * sizeof(double)));

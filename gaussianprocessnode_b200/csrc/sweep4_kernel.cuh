@@ -396,10 +396,55 @@ __device__ __forceinline__ void seg_prologue(const Params& p, const Sm4& sm, con
 }
 
 
+// Adds (first = false) or stores (first = true) a warp-tiled register accumulator into workspace slot `slot`.  The CTA is the slot's only
+// writer and a thread always owns the same elements, so the fire-and-forget reductions (RED.ADD.F64, no round trip) arrive in slab order:
+// deterministic.
+template <int TM, int NT, bool DIAG>
+__device__ __forceinline__ void store_acc4(const Params& p, const double (&acc)[TM / 16][TM / 32][2], const int slot, const bool first) {
+    constexpr int NWARPS = NT / 32, WR = NT / 128, WM = TM / WR, WN = TM / 4, MI = WM / 8, NJ = WN / 8, SB = TM / 4, SI = SB / 8, FJ1 = 1;
+    constexpr int AI = DIAG ? 2 * SI : MI, AJ = DIAG ? SI : NJ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = warp >> 2, wc = warp & 3;
+    const int s0r = (0x32103321 >> (4 * warp)) & 0xf, s0c = (0x32102110 >> (4 * warp)) & 0xf;
+    const int s1r = warp < SI ? 2 : 3, s1c0 = (warp % SI) * 8;
+    const bool has1 = DIAG && warp < 2 * SI;
+    (void)NWARPS;
+    double* out = p.partial + (size_t)slot * (TM * TM);
+    auto put = [&](double* q, double v0, double v1) {
+        if (first) *reinterpret_cast<double2*>(q) = make_double2(v0, v1);
+        else {
+            asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;\n" ::"l"(q), "d"(v0) : "memory");
+            asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;\n" ::"l"(q + 1), "d"(v1) : "memory");
+        }
+    };
+    if (DIAG) {
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            if (sl == 1 && !has1) break;
+            const int r0 = (sl ? s1r : s0r) * SB, c0 = sl ? s1c0 : s0c * SB;
+#pragma unroll
+            for (int i = 0; i < SI; ++i)
+#pragma unroll
+                for (int j = 0; j < (sl ? FJ1 : SI); ++j) {
+                    const int rr = r0 + 8 * i + (lane >> 2), cc = c0 + 8 * j + 2 * (lane & 3);
+                    put(out + rr * TM + cc, acc[sl * SI + i][j][0], acc[sl * SI + i][j][1]);
+                }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < AI; ++i)
+#pragma unroll
+            for (int j = 0; j < AJ; ++j) {
+                const int rr = wr * WM + 8 * i + (lane >> 2), cc = wc * WN + 8 * j + 2 * (lane & 3);
+                put(out + rr * TM + cc, acc[i][j][0], acc[i][j][1]);
+            }
+    }
+}
+
 // the segment's main loop and epilogue (its first loads were started by seg_prologue); `nx` = the CTA's next segment of the slab
 template <int TM, int NB, int DPAD, int NT, bool WEIGHTED, bool DIAG>
 __device__ __forceinline__ void run_segment4(const Params& p, const Sm4& sm, const Slab4& sl, const Seg4& sg, const Seg4& nx, unsigned& g,
-                                             long long& t_wait) {
+                                             long long& t_wait, double (&acc)[TM / 16][TM / 32][2], const bool zero_acc, const bool flush) {
     const bool first = sl.first;
     const int nchunks = sg.n, slot = sg.slot;
     using S = Smem4<TM, NB, DPAD>;
@@ -434,11 +479,13 @@ __device__ __forceinline__ void run_segment4(const Params& p, const Sm4& sm, con
     const int a1_off = s1r * SB + (lane >> 2) + kq * LDB, b1_off = s1c0 + (lane >> 2) + kq * LDB;
     const int w_off = 2 * NB * LDB + kq;
 
-    double acc[AI][AJ][2];
+    static_assert(AI == TM / 16 && AJ == TM / 32, "accumulator tile");
+    if (zero_acc) {
 #pragma unroll
-    for (int i = 0; i < AI; ++i)
+        for (int i = 0; i < AI; ++i)
 #pragma unroll
-        for (int j = 0; j < AJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < AJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
 
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
@@ -507,38 +554,7 @@ __device__ __forceinline__ void run_segment4(const Params& p, const Sm4& sm, con
     if (tid == 0 && nx.valid) seg_prologue<TM, NB, DPAD, WEIGHTED>(p, sm, sl, nx, g, t_wait);     // its tiles fly during the epilogue
     __syncwarp();
 
-    // ---- epilogue: add the register tile into the workspace slot.  This CTA is the slot's only writer and a thread always owns the
-    // same elements, so the fire-and-forget reductions (RED.ADD.F64, no round trip) arrive in slab order: deterministic.
-    double* out = p.partial + (size_t)slot * (TM * TM);
-    auto put = [&](double* q, double v0, double v1) {
-        if (first) *reinterpret_cast<double2*>(q) = make_double2(v0, v1);
-        else {
-            asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;\n" ::"l"(q), "d"(v0) : "memory");
-            asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;\n" ::"l"(q + 1), "d"(v1) : "memory");
-        }
-    };
-    if (DIAG) {
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-            if (sl == 1 && !has1) break;
-            const int r0 = (sl ? s1r : s0r) * SB, c0 = sl ? s1c0 : s0c * SB;
-#pragma unroll
-            for (int i = 0; i < SI; ++i)
-#pragma unroll
-                for (int j = 0; j < (sl ? FJ1 : SI); ++j) {
-                    const int rr = r0 + 8 * i + (lane >> 2), cc = c0 + 8 * j + 2 * (lane & 3);
-                    put(out + rr * TM + cc, acc[sl * SI + i][j][0], acc[sl * SI + i][j][1]);
-                }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < AI; ++i)
-#pragma unroll
-            for (int j = 0; j < AJ; ++j) {
-                const int rr = wr * WM + 8 * i + (lane >> 2), cc = wc * WN + 8 * j + 2 * (lane & 3);
-                put(out + rr * TM + cc, acc[i][j][0], acc[i][j][1]);
-            }
-    }
+    if (flush) store_acc4<TM, NT, DIAG>(p, acc, slot, first);
     if (p.dbg && tid == 0) {
         const long long dt = clock64() - t_start;
         if (first) { p.dbg[4 * slot + 0] = sg.khi - sg.klo; p.dbg[4 * slot + 1] = dt; }      // k-steps (1/8 chunk)
@@ -826,6 +842,9 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     };
 
     if (p.dbg) t_k1 = clock64();
+    double acc[TM / 16][TM / 32][2];
+    const bool keep = sm.segtab[0] >= 0 && sm.segtab[8] < 0;      // exactly one segment per slab (CTA-uniform; the table is complete: barrier above)
+    bool kept = false;
     generate(0);
     for (int s = 0; s < p.nslabs; ++s) {
         if (s + 1 < p.nslabs) generate(s + 1);        // one slab ahead: the consumers of slab s + 1 will not wait for it
@@ -859,12 +878,19 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
         if (cur.valid && tid == 0) seg_prologue<TM, NB, DPAD, WEIGHTED>(p, sm, sl, cur, g, t_wait);
         while (cur.valid) {
             const Seg4 nx = next_seg();
-            if (cur.I == cur.J) run_segment4<TM, NB, DPAD, NT, WEIGHTED, true>(p, sm, sl, cur, nx, g, t_wait);
-            else run_segment4<TM, NB, DPAD, NT, WEIGHTED, false>(p, sm, sl, cur, nx, g, t_wait);
+            // a CTA with ONE segment per slab keeps its register tile across the slabs and stores it once after the last one
+            const bool zero_acc = !keep || !kept;
+            if (cur.I == cur.J) run_segment4<TM, NB, DPAD, NT, WEIGHTED, true>(p, sm, sl, cur, nx, g, t_wait, acc, zero_acc, !keep);
+            else run_segment4<TM, NB, DPAD, NT, WEIGHTED, false>(p, sm, sl, cur, nx, g, t_wait, acc, zero_acc, !keep);
+            kept = true;
             cur = nx;
         }
         __syncthreads();              // every warp has received its last K_uf tile of the slab
         if (tid == 0) red_release_inc(p.flags + (size_t)(s % p.nring) * (p.nblk + 1) + p.nblk);
+    }
+    if (keep && kept) {
+        if (sm.segtab[0] == sm.segtab[1]) store_acc4<TM, NT, true>(p, acc, sm.segtab[2], true);
+        else store_acc4<TM, NT, false>(p, acc, sm.segtab[2], true);
     }
     if (p.dbg && tid == 0) {   // records after the segment slots: {generator chunks, generator clocks, 2, cta}, {1, dependency-wait clocks, 3, cta}
         long long* d = p.dbg + 4 * (size_t)(p.ncta + p.ntiles);
