@@ -821,6 +821,7 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     for (int rb = 0; rb < RB; ++rb) psi1_acc[rb][0] = psi1_acc[rb][1] = 0.0;
     unsigned g = 0, xg = 0;
     long long t_gen = 0, t_wait = 0, n_gen = 0;     // instrumentation (p.dbg)
+    long long t_pro = 0, t_seg = 0, t_end = 0;      // per slab: first prologue, segments, closing barrier
     // generate slab s into panel s % nring and publish it
     auto generate = [&](int s) {
         const long long slab_c0 = (long long)s * p.slab_chunks;
@@ -874,8 +875,11 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
             }
             return sg;
         };
+        long long tq0 = 0, tq1 = 0, tq2 = 0;
+        if (p.dbg) tq0 = clock64();
         Seg4 cur = next_seg();
         if (cur.valid && tid == 0) seg_prologue<TM, NB, DPAD, WEIGHTED>(p, sm, sl, cur, g, t_wait);
+        if (p.dbg) { tq1 = clock64(); t_pro += tq1 - tq0; }
         while (cur.valid) {
             const Seg4 nx = next_seg();
             // a CTA with ONE segment per slab keeps its register tile across the slabs and stores it once after the last one
@@ -885,8 +889,10 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
             kept = true;
             cur = nx;
         }
+        if (p.dbg) { tq2 = clock64(); t_seg += tq2 - tq1; }
         __syncthreads();              // every warp has received its last K_uf tile of the slab
         if (tid == 0) red_release_inc(p.flags + (size_t)(s % p.nring) * (p.nblk + 1) + p.nblk);
+        if (p.dbg) t_end += clock64() - tq2;
     }
     if (keep && kept) {
         if (sm.segtab[0] == sm.segtab[1]) store_acc4<TM, NT, true>(p, acc, sm.segtab[2], true);
@@ -925,6 +931,8 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
         d[8 * bcta + 4] = t_k3 - t_k2; d[8 * bcta + 5] = clock64() - t_k3; d[8 * bcta + 6] = 5; d[8 * bcta + 7] = bcta;
         long long* d2 = d + 8 * (size_t)p.ncta;
         d2[4 * bcta + 0] = tr[0]; d2[4 * bcta + 1] = tr[1]; d2[4 * bcta + 2] = 6; d2[4 * bcta + 3] = tr[2];
+        long long* d3 = d2 + 4 * (size_t)p.ncta;
+        d3[4 * bcta + 0] = t_pro; d3[4 * bcta + 1] = t_seg; d3[4 * bcta + 2] = 7; d3[4 * bcta + 3] = t_end;
     }
 }
 

@@ -43,6 +43,10 @@ if "--clocks" in sys.argv:
     if len(q6):
         print("phase 2 (clocks, mean / max over CTAs): slot discovery %.0f / %.0f, partial loads %.0f / %.0f, stores %.0f / %.0f" % (
               q6[:, 0].mean(), q6[:, 0].max(), q6[:, 1].mean(), q6[:, 1].max(), q6[:, 3].mean(), q6[:, 3].max()))
+    q7 = r[r[:, 2] == 7]
+    if len(q7):
+        print("slab loop besides the generator (clocks per sweep, mean over CTAs): first-segment prologue %.0f, segments %.0f, closing barrier %.0f" % (
+              q7[:, 0].mean(), q7[:, 1].mean(), q7[:, 3].mean()))
     r = r[r[:, 2] < 2]
     for dg in (0, 1):       # least-squares  clocks = a * chunks + b  over the segments (per slab pass: b is per segment and slab)
         q = r[r[:, 2] == dg].astype(float)
