@@ -218,3 +218,27 @@ def test_free_energy_assembly_matches_per_node_sum():
     U = sum(unisgp.average_energy_pointmass(y[n], 0.0, X[n], mu, (a, b), th, meta) for n in range(N))
     assert abs(F - (U + batched.kl_mvn(mu, Sig, np.zeros(M), np.eye(M)) + batched.kl_gamma(a, b, 1.0, 1.0))) < 1e-9 * abs(F)
     assert np.isfinite(F)
+
+
+def test_multisgp_in_message_is_the_negative_energy_up_to_its_constant():
+    # `@rule MultiSGP(:in)` (MultiSGPnode.jl:162-211) returns exp(E[log p]) as a function of the input, `@average_energy` (:574-602) is
+    # -E[log p] with the input marginal collapsed to a point: U(x) = D/2 ln 2pi - 1/2 ln|W| + 1/2 tr(W R_y) - log_backwardmess(x).
+    # Ties the oracle's restatement of the :in rule to its energy rule (itself pinned by GPtest.jl's formulas).
+    from oracle import multisgp, cubature as cub, kernels as ker
+    rng = np.random.default_rng(3)
+    M, D, d = 9, 2, 2
+    Z = rng.normal(size=(M, d)) * 1.5
+    theta = np.array([0.3, 0.7, 1.1])
+    kern = lambda t: (ker.softplus(t[0]), ker.softplus(t[1:]), 0)
+    var, ell, _ = kern(theta)
+    Kinv = np.linalg.inv(ker.kuu(Z, var, ell, jitter=1e-10))
+    meta = multisgp.MultiSGPMeta(cub.SRCUBATURE, Z, np.zeros((1, 1)), np.zeros((M, 1)), np.zeros((M, M)), Kinv, kern)
+    W = np.array([[3.0, 0.4], [0.4, 2.0]])
+    mu_v = rng.normal(size=D * M); C = rng.normal(size=(D * M, D * M)) * 0.2; Sigma_v = C @ C.T + 0.05 * np.eye(D * M)
+    mu_y = rng.normal(size=D)
+    f = multisgp.rule_in_logpdf(mu_y, mu_v, Sigma_v, W, theta, meta)
+    const = 0.5 * D * np.log(2 * np.pi) - 0.5 * np.log(np.linalg.det(W)) + 0.5 * mu_y @ W @ mu_y
+    for _ in range(5):
+        x = rng.normal(size=d)
+        U = multisgp.average_energy(mu_y, None, (x, 1e-30 * np.eye(d)), mu_v, Sigma_v, W, np.log(np.linalg.det(W)), theta, meta)
+        assert abs(U - (const - f(x))) <= 1e-10 * max(abs(U), 1.0)
