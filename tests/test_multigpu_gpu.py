@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out, p2p):
+def _worker(rank, world, port, out, p2p, M):
     os.environ["SGP_COMM_P2P"] = "1" if p2p else "0"
     import torch
     import torch.distributed as dist
@@ -28,7 +28,7 @@ def _worker(rank, world, port, out, p2p):
     uid = [SGPContext.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     rng = np.random.default_rng(11)
-    N, D, M = 50_001, 8, 600                                      # M > 384: the generate-once kernel, which carries the fused exchange
+    N, D = 50_001, 8                                              # M > 384: the generate-once kernel, which carries the fused exchange
     X = rng.normal(size=(N, D)); y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=N); yv = rng.uniform(0, 0.1, N)
     Z = X[:M].copy(); ell = np.full(D, 2.0)
     ctx = SGPContext(rank); ctx.set_kernel(1.2, ell); ctx.set_inducing(Z)
@@ -47,8 +47,9 @@ def _worker(rank, world, port, out, p2p):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [True, False])
-def test_two_gpu_sharded_sweep_matches_single_gpu(p2p):
+@pytest.mark.parametrize("p2p,M", [(True, 600), (False, 600), (True, 300)])
+def test_two_gpu_sharded_sweep_matches_single_gpu(p2p, M):
+    # M = 300 goes to the first fused kernel, which has no exchange of its own: NCCL all-reduce on the (peer-mapped) statistics buffer
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -56,11 +57,11 @@ def test_two_gpu_sharded_sweep_matches_single_gpu(p2p):
     world = 2
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), out, p2p), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), out, p2p, M), nprocs=world, join=True)
         res = dict(out)
     assert set(res) == {0, 1}
     for r in res.values():
         assert max(r[:4]) <= 1e-12, res
         assert r[4], "repeated sweeps must give the same bits"
-        assert r[6] == (1 if p2p else 2), r                            # fused exchange: ONE launch per sweep; NCCL path: kernel + all-reduce
+        assert r[6] == (1 if (p2p and M > 384) else 2), r              # fused exchange: ONE launch per sweep; NCCL path: kernel + all-reduce
     assert res[0][5] == res[1][5], "every rank must hold bitwise identical statistics"
