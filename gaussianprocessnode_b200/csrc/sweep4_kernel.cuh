@@ -690,9 +690,17 @@ __device__ __forceinline__ void xchg_wait(const unsigned* flag, unsigned epoch) 
         if (clock64() - t0 > 40000000000ll) __trap();
     }
 }
-// Two-shot all-reduce over NVLink peer memory.  Every rank has written its statistics to its own xin.  Barrier A (flags), then rank r
+// All-reduce over NVLink peer memory (two-shot; one-shot for two ranks).  Every rank has written its statistics to its own xin.  Barrier A (flags), then rank r
 // sums elements [r, r+1) * count / R of all xin in rank order -- the same order on every rank: bitwise identical results -- and stores
 // the sums into every rank's xout (its stats buffer); barrier B.
+// Before phase 2 overwrites this rank's xin: every peer must have finished READING it in the previous exchange (flag B of epoch - 1; in the
+// two-shot form that is implied by the kernel's closing wait, in the one-shot form the peers signal it without anyone waiting at the time).
+__device__ __forceinline__ void xchg_before_phase2(const SgpXchg& x) {
+    const int tid = threadIdx.x;
+    if (tid < x.nranks) xchg_wait(reinterpret_cast<unsigned*>(x.peers[x.rank]) + 16 + tid, x.epoch - 1u);
+    __syncthreads();
+}
+
 template <int NT>
 __device__ __forceinline__ void xchg_allreduce(const SgpXchg& x, cooperative_groups::grid_group& grid) {
     const int tid = threadIdx.x, R = x.nranks;
@@ -705,6 +713,26 @@ __device__ __forceinline__ void xchg_allreduce(const SgpXchg& x, cooperative_gro
     }
     if (tid < R) xchg_wait(myflags + tid, x.epoch);         // every CTA polls the local flags: no second grid barrier
     __syncthreads();
+    if (R == 2) {
+        // ONE-SHOT for two ranks: every rank pulls the peer's whole xin and sums locally (same rank order on both: identical bits); no remote
+        // stores, no second cross-GPU wait -- the peers only learn, through flag B, that this rank is done reading their xin
+        const long long pairs = (x.count + 1) / 2;
+        const double2* in0 = reinterpret_cast<const double2*>(x.peers[0] + x.xin_off);
+        const double2* in1 = reinterpret_cast<const double2*>(x.peers[1] + x.xin_off);
+        double2* outp = reinterpret_cast<double2*>(x.peers[x.rank] + x.xout_off);
+        const long long stride = (long long)gridDim.x * NT;
+        for (long long e = (long long)blockIdx.x * NT + tid; e < pairs; e += 4 * stride) {
+            double2 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (e + u * stride < pairs) { a[u] = __ldcv(in0 + e + u * stride); b[u] = __ldcv(in1 + e + u * stride); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (e + u * stride < pairs) outp[e + u * stride] = make_double2(a[u].x + b[u].x, a[u].y + b[u].y);
+        }
+        __threadfence();
+        grid.sync();                                        // every CTA of this rank is done reading
+        if (blockIdx.x == 0 && tid < R) st_release_sys(reinterpret_cast<unsigned*>(x.peers[tid]) + 16 + x.rank, x.epoch);
+        return;
+    }
     // this rank's share, in pairs of doubles; up to U pairs per thread with all their peer loads in flight together
     constexpr int U = 2;
     const long long pairs = (x.count + 1) / 2;              // (the buffers are padded: reading / writing one double past count is harmless)
@@ -919,6 +947,7 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     __threadfence();
     grid.sync();
     if (p.dbg) t_k3 = clock64();
+    if (p.xr.nranks > 1) xchg_before_phase2(p.xr);
     long long tr[3] = {0, 0, 0};
     reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)), tr);
     // the dependency counters are dead after the last grid barrier: leave them zeroed for the next launch (no memset per sweep on the host)
