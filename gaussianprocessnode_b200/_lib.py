@@ -38,6 +38,9 @@ SIGNATURES = {
     "sgp_posterior_v_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, c_double_p, c_double_p, c_double_p]),
     "sgp_w_terms": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sgp_predict_mean": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p]),
+    "sgp_predict_probit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
+    "sgp_dense_timed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, c_float_p]),
+    "sgp_fp64_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p]),
     "sgp_theta_objective": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_double, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
     "sgp_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "sgp_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),

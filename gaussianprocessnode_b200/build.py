@@ -1,27 +1,40 @@
-"""Builds libsgp.so (hand-written CUDA for sm_100a) in-tree with nvcc.  No torch, no JIT cache: the .so travels with the repo."""
+"""Builds libsgp.so (hand-written CUDA for sm_100a) in-tree with nvcc.  No torch, no JIT cache: the .so travels with the repo.
+Objects are rebuilt only when their source or one of the headers it includes (transitively) is newer."""
 import os
+import re
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgp.so")
-SOURCES = ["api.cu", "sweep.cu", "sweep_se.cu", "sweep_m32.cu", "sweep_m52.cu", "sweep4_se.cu", "sweep4_m32.cu", "sweep4_m52.cu", "dense.cu", "dense_coop.cu", "uncertain.cu", "theta.cu", "inmsg.cu", "comm.cu"]
+SOURCES = ["api.cu", "sweep.cu", "sweep_se.cu", "sweep_m32.cu", "sweep_m52.cu", "sweep4_se.cu", "sweep4_m32.cu", "sweep4_m52.cu", "dense.cu", "dense_coop.cu",
+           "uncertain.cu", "theta.cu", "inmsg.cu", "comm.cu", "xchg.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default"]
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
 
 
-def _stale():
-    if not os.path.exists(LIB):
+def _deps(path, seen=None):
+    """the file and every quoted include reachable from it"""
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for inc in _INC.findall(open(path).read()):
+        _deps(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(HERE), "include", "sgp.h")]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
-    if not force and not _stale():
-        return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
@@ -29,6 +42,8 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
+        if not force and not _newer(obj, _deps(os.path.join(CSRC, src)) | {os.path.abspath(__file__)}):
+            continue
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
@@ -37,8 +52,9 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
-    subprocess.run(cmd, check=True)
+    if procs or force or _newer(LIB, objs):
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+        subprocess.run(cmd, check=True)
     return LIB
 
 

@@ -1,6 +1,7 @@
 // C ABI of libsgp (include/sgp.h): context, resident state, and the calls a ReactiveMP host makes in place of the
 // per-point rules.  Host pointers in, host pointers out; all device work on the context's own stream.
 #include "sgp_internal.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -12,39 +13,11 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
 
 namespace {
 
-__global__ void axpby_kernel(double* __restrict__ out, const double* __restrict__ a, double alpha, const double* __restrict__ b, double beta, size_t n) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = alpha * (a ? a[i] : 0.0) + beta * (b ? b[i] : 0.0);
-}
-__global__ void add_outer_kernel(double* __restrict__ A, const double* __restrict__ v, int M) {   // A += v v'
-    size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (e < (size_t)M * M) A[e] = fma(v[e % M], v[e / M], A[e]);
-}
-__global__ void transpose_kernel(const double* __restrict__ A, double* __restrict__ B, int M) {
-    __shared__ double t[32][33];
-    int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
-    for (int j = threadIdx.y; j < 32; j += 8) if (x < M && y0 + j < M) t[j][threadIdx.x] = A[(size_t)x + (size_t)(y0 + j) * M];
-    __syncthreads();
-    int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
-    for (int j = threadIdx.y; j < 32; j += 8) if (xo < M && yo0 + j < M) B[(size_t)xo + (size_t)(yo0 + j) * M] = t[threadIdx.x][j];
-}
-__global__ void identity_kernel(double* __restrict__ A, int M) {
-    size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (e < (size_t)M * M) A[e] = (e % M == e / M) ? 1.0 : 0.0;
-}
-// out[0] = sum_i a[i*stride_a] * b[i*stride_b]  (single block, fixed order -> deterministic)
-__global__ void dot_kernel(const double* __restrict__ a, size_t stride_a, const double* __restrict__ b, size_t stride_b, size_t n, double* __restrict__ out) {
-    __shared__ double s[256];
-    double v = 0.0;
-    for (size_t i = threadIdx.x; i < n; i += 256) v = fma(a[i * stride_a], b ? b[i * stride_b] : 1.0, v);
-    s[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) out[0] = s[0];
-}
 // out[n] = sum_m k(x_n, z_m) mu[m]   (one thread per test point, inducing rows broadcast from shared memory)
+// prob (optional) = Phi(out[n] * inv_s): the Probit(:out) message of the :out message N(out[n], 1 / w_bar), inv_s = 1 / sqrt(1 + 1 / w_bar)
 __global__ void predict_kernel(const double* __restrict__ Xt, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ out,
-                               long long Nt, int M, int D, int kind, double variance, const double* __restrict__ ell_inv) {
+                               long long Nt, int M, int D, int kind, double variance, const double* __restrict__ ell_inv, double* __restrict__ prob,
+                               double inv_s) {
     extern __shared__ double sh[];   // chunk of inducing rows: [MC][D] + mu[MC]
     const int MC = 256;
     long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -67,7 +40,10 @@ __global__ void predict_kernel(const double* __restrict__ Xt, const double* __re
             acc = fma(k, sh[MC * D + m], acc);
         }
     }
-    if (n < Nt) out[n] = variance * acc;
+    if (n < Nt) {
+        out[n] = variance * acc;
+        if (prob) prob[n] = 0.5 * erfc(-variance * acc * inv_s * 0.70710678118654752440);
+    }
 }
 
 inline unsigned nblocks(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
@@ -113,6 +89,8 @@ int sgp_create(sgp_ctx** out, int device_id) {
     if (prop.major < 10) { delete ctx; return SGP_ERR_UNSUPPORTED; }
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    if (cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail("event");
     if (cudaMalloc((void**)&ctx->exptab_dev, SGP_EXP_TAB * sizeof(double)) != cudaSuccess) return fail("malloc");
     if (cudaMalloc((void**)&ctx->info_dev, sizeof(int)) != cudaSuccess) return fail("malloc");
@@ -133,8 +111,10 @@ void sgp_destroy(sgp_ctx* ctx) {
     cudaFree(ctx->dense_dev); cudaFree(ctx->info_dev); cudaFree(ctx->KuuL_dev); cudaFree(ctx->sp_X_dev); cudaFree(ctx->sp_w_dev);
     cudaFree(ctx->sp_y_dev); cudaFree(ctx->sweep_dbg_dev); cudaFree(ctx->theta_dev); cudaFree(ctx->Kinv_dev); cudaFree(ctx->kuu_dinv_dev);
     cudaFree(ctx->dinv_dev); cudaFree(ctx->post_dev); cudaFree(ctx->unc_dev); if (ctx->fetch_host) cudaFreeHost(ctx->fetch_host);
-    cudaFree(ctx->kbuf_dev); cudaFree(ctx->sweep_flags_dev); cudaFree(ctx->flush_dev); cudaFree(ctx->in_dev);
+    cudaFree(ctx->kbuf_dev); cudaFree(ctx->sweep_flags_dev); cudaFree(ctx->flush_dev); cudaFree(ctx->in_dev); cudaFree(ctx->wt_dev); cudaFree(ctx->pred_dev);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -200,6 +180,7 @@ int sgp_set_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, c
 // H2D copies enqueued on the ctx stream, no host synchronisation
 static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts) {
     if (check(ctx)) return SGP_ERR_ARG;
+    SGP_RANGE("sgp_upload");
     if (!ctx->have_kernel) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data: set_kernel first (D is taken from it)");
     if (N < 0 || (N > 0 && !X)) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data: X required");
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
@@ -247,6 +228,7 @@ int sgp_set_data_dev(sgp_ctx* ctx, int64_t N, const double* X_dev, const double*
 }
 
 static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2) {
+    SGP_RANGE("sgp_fetch");
     const size_t M = (size_t)ctx->M, Do = (size_t)ctx->Dout;
     double* s2 = ctx->stats_dev; double* s1 = s2 + M * M; double* sc = s1 + M * Do;
     if (psi2) SGP_CUDA(ctx, cudaMemcpyAsync(psi2, s2, M * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -268,32 +250,36 @@ static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, d
     return SGP_OK;
 }
 
-static int sweep_resident(sgp_ctx* ctx, bool time_main) {
+}  // extern "C"
+int sgp_sweep_resident(sgp_ctx* ctx, bool time_main) {
     if (ctx->N <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: no data (sgp_set_data)");
+    SGP_RANGE("sgp_sweep");
+    ctx->stats_of_data = false;
     ctx->want_exchange = true;
     int rc = sgp_sweep_launch(ctx, ctx->X_dev, ctx->y_dev, ctx->have_yv ? ctx->yv_dev : nullptr, ctx->have_w ? ctx->w_dev : nullptr, ctx->N,
                               ctx->Ncap, time_main);
     ctx->want_exchange = false;
     if (rc) return rc;
     if (ctx->comm && !ctx->last_sweep_exchanged) {       // (the generate-once kernel exchanges over peer memory inside its own launch)
-        size_t cnt = (size_t)ctx->M * ctx->M + (size_t)ctx->M * ctx->Dout + 4;
-        rc = sgp_comm_allreduce(ctx, ctx->stats_dev, cnt); if (rc) return rc;
+        rc = sgp_comm_allreduce_stats(ctx, ctx->M, ctx->Dout); if (rc) return rc;
         ctx->last_launches += 1;
     }
+    ctx->stats_of_data = true;       // the resident statistics are those of the resident data (summed over the ranks)
     return SGP_OK;
 }
+extern "C" {
 
 int sgp_sweep_psi(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2) {
     if (check(ctx)) return SGP_ERR_ARG;
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
-    int rc = sweep_resident(ctx, false); if (rc) return rc;
+    int rc = sgp_sweep_resident(ctx, false); if (rc) return rc;
     return fetch_stats(ctx, psi0, psi1, psi2, sum_y2);
 }
 
 int sgp_sweep_psi_host(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts, double* psi0,
                        double* psi1, double* psi2, double* sum_y2) {
     int rc = upload_data(ctx, N, X, ybar, yvar, wts); if (rc) return rc;
-    rc = sweep_resident(ctx, false); if (rc) return rc;
+    rc = sgp_sweep_resident(ctx, false); if (rc) return rc;
     return fetch_stats(ctx, psi0, psi1, psi2, sum_y2);       // the one host synchronisation of the step
 }
 
@@ -312,7 +298,7 @@ int sgp_sweep_timed(sgp_ctx* ctx, int reps, float* ms_per_sweep, float* ms_main_
     double main_sum = 0.0;
     SGP_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     for (int r = 0; r < reps; ++r) {
-        int rc = sweep_resident(ctx, true); if (rc) return rc;
+        int rc = sgp_sweep_resident(ctx, true); if (rc) return rc;
         // main-kernel time needs its own pair of events per repetition; read it back after the sync below for r == reps-1
         if (r + 1 < reps) {
             SGP_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
@@ -350,7 +336,7 @@ int sgp_sweep_timed_flushed(sgp_ctx* ctx, int reps, int flush_mb, float* ms_per_
         if (fbytes && cudaMemsetAsync(ctx->flush_dev, r & 0xff, fbytes, ctx->stream) != cudaSuccess) { rc = SGP_ERR_CUDA; break; }
         if (cudaEventRecord(ev[4 * r], ctx->stream) != cudaSuccess) { rc = SGP_ERR_CUDA; break; }
         ctx->ev[2] = ev[4 * r + 2]; ctx->ev[3] = ev[4 * r + 3];       // the launcher brackets the main kernel with ev[2] / ev[3]
-        rc = sweep_resident(ctx, true);
+        rc = sgp_sweep_resident(ctx, true);
         if (rc == SGP_OK && cudaEventRecord(ev[4 * r + 1], ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
     }
     ctx->ev[2] = keep2; ctx->ev[3] = keep3;
@@ -411,6 +397,7 @@ int sgp_stats_dev(sgp_ctx* ctx, double** psi2_dev, double** psi1_dev, double** s
 int sgp_kuu_factor(sgp_ctx* ctx, double jitter, double* L) {
     if (check(ctx)) return SGP_ERR_ARG;
     if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "kuu_factor: set_kernel and set_inducing first");
+    SGP_RANGE("sgp_kuu_factor");
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
     const int M = ctx->M;
     if (ctx->KuuL_M != M) {
@@ -422,23 +409,18 @@ int sgp_kuu_factor(sgp_ctx* ctx, double jitter, double* L) {
         ctx->KuuL_M = M;
     }
     ctx->have_kuu = false;
-    int rc = sgp_kuu_build(ctx, ctx->KuuL_dev, jitter); if (rc) return rc;
-    rc = sgp_potrf_lower(ctx, ctx->KuuL_dev, M); if (rc) return rc;
-    // keep the diagonal-block inverses (the next factorisation overwrites ctx->dinv_dev) and K_uu^-1 = L^-T L^-1, which the
-    // :w rule / energy / theta step contract with Psi2
-    const size_t nd = (size_t)((M + 63) / 64) * 64 * 64;
-    rc = sgp_ensure(ctx, &ctx->kuu_dinv_dev, &ctx->kuu_dinv_cap, nd); if (rc) return rc;
-    SGP_CUDA(ctx, cudaMemcpyAsync(ctx->kuu_dinv_dev, ctx->dinv_dev, nd * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    {
-        const size_t MM = (size_t)M * M;
-        double* d = ctx->dense_dev + 64;                     // scratch: X = L^-1, Tmp
-        rc = sgp_trtri_lower(ctx, ctx->KuuL_dev, d, d + MM, ctx->Kinv_dev, M); if (rc) return rc;
-    }
-    ctx->have_kuu = true;
-    if (L) {
-        SGP_CUDA(ctx, cudaMemcpyAsync(L, ctx->KuuL_dev, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    // ONE cooperative launch: K_uu = kernelmatrix(Xu) + jitter I -> L (and the inverses of its diagonal blocks, which sgp_kuu_solve uses)
+    // -> X = L^-1 -> K_uu^-1 = X' X, which the :w rule / energy / theta step contract with Psi2
+    const size_t nd = (size_t)((M + 63) / 64) * 64 * 64, MM = (size_t)M * M;
+    int rc = sgp_ensure(ctx, &ctx->kuu_dinv_dev, &ctx->kuu_dinv_cap, nd); if (rc) return rc;
+    double* d = ctx->dense_dev + 64;
+    SgpDenseJob j;
+    j.M = M; j.build = 2; j.jitter = jitter; j.A = ctx->KuuL_dev; j.Dinv = ctx->kuu_dinv_dev; j.X = d; j.Tmp = d + MM; j.S = ctx->Kinv_dev;
+    rc = sgp_dense_job(ctx, j); if (rc) return rc;
+    if (ctx->dense_timing) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (L) SGP_CUDA(ctx, cudaMemcpyAsync(L, ctx->KuuL_dev, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = sgp_dense_info(ctx, "kuu_factor"); if (rc) return rc;
+    ctx->have_kuu = true; ctx->kuu_jitter = jitter;
     return SGP_OK;
 }
 
@@ -480,47 +462,50 @@ __global__ void isotropic_kernel(double* __restrict__ A, int M, double diag) {
     if (e < (size_t)M * M) A[e] = (e % M == e / M) ? diag : 0.0;
 }
 
-// The N-th prod on the resident prior: Lambda = Lambda_p + w Psi2, xi = xi_p + w Psi1 -> Sigma, mu, Uv (resident).
+// The N-th prod on the resident prior: Lambda = Lambda_p + w Psi2, xi = xi_p + w Psi1 -> Sigma, mu (and, when the host wants it, Uv).
 // carry: the posterior's natural parameters become the resident prior (the streaming schedule of regression_kin40k.ipynb:200-213).
-static int posterior_core(sgp_ctx* ctx, double w, bool carry, bool want_uv) {
+// Two cooperative launches at most: [Lambda -> L -> L^-1 -> Sigma = L^-T L^-1 -> mu] and [Sigma + mu mu' -> its Cholesky factor -> Uv];
+// the device-to-host copies of Sigma / mu run on the second stream while the second launch factorises.
+static int posterior_core(sgp_ctx* ctx, double w, bool carry, bool want_uv, double* mu_v, double* Sigma_v, double* Uv_host) {
     const int M = ctx->M; const size_t MM = (size_t)M * M;
     double* d = ctx->dense_dev + 64;
     double *Lam = d, *X = d + MM, *T = d + 3 * MM, *xi = d + 4 * MM;
     double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM;
-    double *mu = post_mu(ctx), *Sig = post_Sig(ctx), *U = post_Uv(ctx);
-    axpby_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(Lam, post_LamP(ctx), 1.0, psi2, w, MM);      // Lambda = Lambda0 + w Psi2
-    axpby_kernel<<<nblocks(M), 256, 0, ctx->stream>>>(xi, post_xiP(ctx), 1.0, psi1, w, M);          // xi = xi0 + w Psi1
-    if (carry) {
-        SGP_CUDA(ctx, cudaMemcpyAsync(post_LamP(ctx), Lam, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        SGP_CUDA(ctx, cudaMemcpyAsync(post_xiP(ctx), xi, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    int rc = sgp_potrf_lower(ctx, Lam, M); if (rc) return rc;                               // Lambda = L L'
-    rc = sgp_trtri_lower(ctx, Lam, X, T, Sig, M); if (rc) return rc;                        // X = L^-1, Sigma = X' X
-    rc = sgp_gemm(ctx, 0, 0, M, 1, M, 1.0, Sig, M, xi, M, 0.0, mu, M, 0); if (rc) return rc; // mu = Sigma xi
+    int rc = sgp_ensure(ctx, &ctx->dinv_dev, &ctx->dinv_cap, (size_t)((M + 63) / 64) * 64 * 64); if (rc) return rc;
+    SgpDenseJob a;
+    a.M = M; a.build = 1; a.S2 = psi2; a.s1 = psi1; a.P = post_LamP(ctx); a.xip = post_xiP(ctx); a.xi = xi; a.w = w; a.carry = carry ? 1 : 0;
+    a.A = Lam; a.Dinv = ctx->dinv_dev; a.X = X; a.Tmp = T; a.S = post_Sig(ctx); a.mu = post_mu(ctx);
+    rc = sgp_dense_job(ctx, a); if (rc) return rc;
     ctx->have_post = true; ctx->have_post_uv = false;
+    const bool early = (Sigma_v || mu_v) && want_uv;            // something to copy while the second factorisation runs
+    if (early) {
+        SGP_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+        SGP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_copy, 0));
+        if (Sigma_v) SGP_CUDA(ctx, cudaMemcpyAsync(Sigma_v, post_Sig(ctx), MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream2));
+        if (mu_v) SGP_CUDA(ctx, cudaMemcpyAsync(mu_v, post_mu(ctx), (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream2));
+    }
     if (want_uv) {
-        axpby_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(X, Sig, 1.0, nullptr, 0.0, MM);  // R_v = Sigma + mu mu' (X is free again)
-        add_outer_kernel<<<nblocks(MM), 256, 0, ctx->stream>>>(X, mu, M);
-        rc = sgp_potrf_lower(ctx, X, M); if (rc) return rc;
-        dim3 tg((M + 31) / 32, (M + 31) / 32), tb(32, 8);
-        transpose_kernel<<<tg, tb, 0, ctx->stream>>>(X, U, M);                              // Uv = L_R'
+        SgpDenseJob b;
+        b.M = M; b.build = 3; b.Sig = post_Sig(ctx); b.mu_in = post_mu(ctx); b.A = X; b.Dinv = ctx->dinv_dev; b.Ut = post_Uv(ctx);
+        b.reset_info = 0;                                       // keep a non-positive pivot of the first factorisation on record
+        rc = sgp_dense_job(ctx, b); if (rc) return rc;
         ctx->have_post_uv = true;
     }
-    SGP_CUDA(ctx, cudaGetLastError());
-    return SGP_OK;
-}
-
-static int posterior_fetch(sgp_ctx* ctx, double* mu_v, double* Sigma_v, double* Uv) {
-    const size_t M = (size_t)ctx->M, MM = M * M;
-    if (Sigma_v) SGP_CUDA(ctx, cudaMemcpyAsync(Sigma_v, post_Sig(ctx), MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (mu_v) SGP_CUDA(ctx, cudaMemcpyAsync(mu_v, post_mu(ctx), M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (Uv) SGP_CUDA(ctx, cudaMemcpyAsync(Uv, post_Uv(ctx), MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SGP_OK;
+    if (ctx->dense_timing) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (Uv_host) SGP_CUDA(ctx, cudaMemcpyAsync(Uv_host, post_Uv(ctx), MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!early) {
+        if (Sigma_v) SGP_CUDA(ctx, cudaMemcpyAsync(Sigma_v, post_Sig(ctx), MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (mu_v) SGP_CUDA(ctx, cudaMemcpyAsync(mu_v, post_mu(ctx), (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    rc = sgp_dense_info(ctx, "posterior_v");                   // the one host synchronisation of the call
+    if (early && cudaStreamSynchronize(ctx->stream2) != cudaSuccess && rc == SGP_OK) { ctx->err = "posterior_v: copy stream failure"; rc = SGP_ERR_CUDA; }
+    if (rc) { ctx->have_post = ctx->have_post_uv = false; }
+    return rc;
 }
 
 }  // extern "C"
 const double* sgp_resident_mu(sgp_ctx* ctx) { return (ctx->have_post && ctx->post_M == ctx->M) ? post_mu(ctx) : nullptr; }
+const double* sgp_resident_sigma(sgp_ctx* ctx) { return (ctx->have_post && ctx->post_M == ctx->M) ? post_Sig(ctx) : nullptr; }
 const double* sgp_resident_uv(sgp_ctx* ctx) { return (ctx->have_post && ctx->have_post_uv && ctx->post_M == ctx->M) ? post_Uv(ctx) : nullptr; }
 extern "C" {
 
@@ -554,11 +539,11 @@ int sgp_posterior_v_stream(sgp_ctx* ctx, double w, int carry, double* mu_v, doub
     if (check(ctx)) return SGP_ERR_ARG;
     if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v_stream: run a sweep first");
     if (ctx->Dout != 1) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "posterior_v_stream: scalar-output statistics only");
+    SGP_RANGE("sgp_posterior_v_stream");
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
     int rc = ensure_post(ctx); if (rc) return rc;
     if (!ctx->have_prior) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v_stream: sgp_prior_set / sgp_prior_set_isotropic first");
-    rc = posterior_core(ctx, w, carry != 0, true); if (rc) return rc;
-    return posterior_fetch(ctx, mu_v, Sigma_v, Uv);
+    return posterior_core(ctx, w, carry != 0, Uv != nullptr, mu_v, Sigma_v, Uv);
 }
 
 int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, double w, double* mu_v, double* Sigma_v, double* Uv) {
@@ -566,9 +551,15 @@ int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, doub
     if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v: run a sweep first");
     if (ctx->Dout != 1) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "posterior_v: scalar-output statistics only (MultiSGP folds kron(W, Psi2) on the host)");
     if (!xi0 || !Lambda0) SGP_FAIL(ctx, SGP_ERR_ARG, "posterior_v: prior natural parameters required");
-    int rc = sgp_prior_set(ctx, xi0, Lambda0); if (rc) return rc;
-    rc = posterior_core(ctx, w, false, Uv != nullptr); if (rc) return rc;
-    return posterior_fetch(ctx, mu_v, Sigma_v, Uv);
+    SGP_RANGE("sgp_posterior_v");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    int rc = ensure_post(ctx); if (rc) return rc;
+    const size_t M = (size_t)ctx->M;
+    // the prior's natural parameters: enqueued, no host synchronisation of their own (this call returns only after its final one)
+    SGP_CUDA(ctx, cudaMemcpyAsync(post_LamP(ctx), Lambda0, M * M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(post_xiP(ctx), xi0, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_prior = true;
+    return posterior_core(ctx, w, false, Uv != nullptr, mu_v, Sigma_v, Uv);
 }
 
 int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI1, double* sumI2) {
@@ -577,25 +568,27 @@ int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI
     if (!ctx->have_kuu) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: sgp_kuu_factor first");
     if (ctx->Dout != 1) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "w_terms: scalar-output statistics only");
     if ((mu_v == nullptr) != (Uv == nullptr)) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: pass both mu_v and Uv, or neither (resident posterior)");
-    if (!mu_v && !(ctx->have_post && ctx->have_post_uv && ctx->post_M == ctx->M)) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: no resident posterior (sgp_posterior_v first)");
+    if (!mu_v && !sgp_resident_mu(ctx)) SGP_FAIL(ctx, SGP_ERR_ARG, "w_terms: no resident posterior (sgp_posterior_v first)");
+    SGP_RANGE("sgp_w_terms");
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
     const int M = ctx->M; const size_t MM = (size_t)M * M;
     double* d = ctx->dense_dev + 64;
-    double *U = d + MM, *C = d + 2 * MM, *mu = d + 4 * MM, *res = mu + M;
+    double *U = d + MM, *R = d + 2 * MM, *mu = d + 4 * MM, *res = mu + M;
     double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM; double* scal = psi1 + M;
+    int rc = SGP_OK;
     if (mu_v) {
+        // the host's (previous sweep's) posterior: R_v = Uv' Uv, then <K_uu^-1, Psi2>, <R_v, Psi2>, mu' Psi1 in one pass
         SGP_CUDA(ctx, cudaMemcpyAsync(U, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         SGP_CUDA(ctx, cudaMemcpyAsync(mu, mu_v, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, U, M, U, M, 0.0, R, M, 0); if (rc) return rc;
+        rc = sgp_wterms_reduce(ctx, ctx->Kinv_dev, psi2, R, nullptr, mu, psi1, M, res); if (rc) return rc;
     } else {
-        U = post_Uv(ctx); mu = post_mu(ctx);
+        // resident posterior: <R_v, Psi2> = <Sigma_v, Psi2> + mu_v' Psi2 mu_v -- no Cholesky factor of R_v needed
+        rc = sgp_wterms_reduce(ctx, ctx->Kinv_dev, psi2, sgp_resident_sigma(ctx), sgp_resident_mu(ctx), sgp_resident_mu(ctx), psi1, M, res); if (rc) return rc;
     }
-    int rc = SGP_OK;
-    rc = sgp_dot(ctx, ctx->Kinv_dev, 1, psi2, 1, MM, res); if (rc) return rc;                            // tr(K_uu^-1 Psi2) = <K_uu^-1, Psi2>
-    rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, U, M, psi2, M, 0.0, C, M, 0); if (rc) return rc; // Uv Psi2
-    rc = sgp_dot(ctx, C, 1, U, 1, MM, res + 1); if (rc) return rc;                                       // <Uv Psi2, Uv>
-    dot_kernel<<<1, 256, 0, ctx->stream>>>(mu, 1, psi1, 1, (size_t)M, res + 2);                        // mu' Psi1
-    double h[3], sc[4];
-    SGP_CUDA(ctx, cudaMemcpyAsync(h, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->dense_timing) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    double h[4], sc[4];
+    SGP_CUDA(ctx, cudaMemcpyAsync(h, res, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SGP_CUDA(ctx, cudaMemcpyAsync(sc, scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (sumI1) *sumI1 = sc[0] - h[0];
@@ -603,33 +596,115 @@ int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI
     return SGP_OK;
 }
 
-int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* mu_v, double* out) {
+static int predict_impl(sgp_ctx* ctx, const char* what, int64_t Nt, const double* Xt, const double* mu_v, double w_bar, double* out, double* prob) {
     if (check(ctx)) return SGP_ERR_ARG;
-    if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "predict_mean: set_kernel and set_inducing first");
-    if (Nt < 1 || !Xt || !mu_v || !out) SGP_FAIL(ctx, SGP_ERR_ARG, "predict_mean: bad arguments");
+    if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, std::string(what) + ": set_kernel and set_inducing first");
+    if (Nt < 1 || !Xt || !mu_v || !out) SGP_FAIL(ctx, SGP_ERR_ARG, std::string(what) + ": bad arguments");
+    if (prob && !(w_bar > 0.0)) SGP_FAIL(ctx, SGP_ERR_ARG, std::string(what) + ": w_bar > 0 required");
+    SGP_RANGE("sgp_predict");
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
     const int M = ctx->M, D = ctx->D;
-    double *xt = nullptr, *o = nullptr, *mu = nullptr;
-    SGP_CUDA(ctx, cudaMalloc((void**)&xt, (size_t)Nt * D * sizeof(double)));
-    cudaMalloc((void**)&o, (size_t)Nt * sizeof(double));
-    cudaMalloc((void**)&mu, ((size_t)M + SGP_MAX_D) * sizeof(double));
-    int rc = SGP_OK;
+    // scratch from the context's arena: [Xt (Nt x D) | out (Nt) | prob (Nt) | mu (M) | 1 / ell (D)]
+    const size_t need = (size_t)Nt * D + 2 * (size_t)Nt + (size_t)M + SGP_MAX_D + 8;
+    int rc = sgp_ensure(ctx, &ctx->pred_dev, &ctx->pred_cap, need); if (rc) return rc;
+    double* xt = ctx->pred_dev; double* o = xt + (size_t)Nt * D; double* pr = o + Nt; double* mu = pr + Nt;
     double inv[SGP_MAX_D];
     for (int d = 0; d < D; ++d) inv[d] = 1.0 / ctx->ell[d];
-    if (!o || !mu) rc = SGP_ERR_CUDA;
-    if (!rc && cudaMemcpyAsync(xt, Xt, (size_t)Nt * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
-    if (!rc && cudaMemcpyAsync(mu, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
-    if (!rc && cudaMemcpyAsync(mu + M, inv, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
-    if (!rc) {
-        size_t sh = (size_t)256 * (D + 1) * sizeof(double);
-        predict_kernel<<<nblocks((size_t)Nt, 128), 128, sh, ctx->stream>>>(xt, ctx->Z_dev, mu, o, Nt, M, D, ctx->kind, ctx->variance, mu + M);
-        if (cudaGetLastError() != cudaSuccess) rc = SGP_ERR_CUDA;
+    SGP_CUDA(ctx, cudaMemcpyAsync(xt, Xt, (size_t)Nt * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(mu, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(mu + M, inv, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t sh = (size_t)256 * (D + 1) * sizeof(double);
+    predict_kernel<<<nblocks((size_t)Nt, 128), 128, sh, ctx->stream>>>(xt, ctx->Z_dev, mu, o, Nt, M, D, ctx->kind, ctx->variance, mu + M, prob ? pr : nullptr,
+                                                                       prob ? 1.0 / std::sqrt(1.0 + 1.0 / w_bar) : 0.0);
+    SGP_CUDA(ctx, cudaGetLastError());
+    SGP_CUDA(ctx, cudaMemcpyAsync(out, o, (size_t)Nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (prob) SGP_CUDA(ctx, cudaMemcpyAsync(prob, pr, (size_t)Nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // (inv[] is a stack buffer)
+    return SGP_OK;
+}
+
+int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* mu_v, double* out) {
+    return predict_impl(ctx, "predict_mean", Nt, Xt, mu_v, 1.0, out, nullptr);
+}
+
+int sgp_predict_probit(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* mu_v, double w_bar, double* mean_f, double* var_f, double* prob_y) {
+    if (!prob_y) { if (ctx) ctx->err = "predict_probit: prob_y required"; return SGP_ERR_ARG; }
+    int rc = predict_impl(ctx, "predict_probit", Nt, Xt, mu_v, w_bar, mean_f, prob_y); if (rc) return rc;
+    if (var_f) *var_f = 1.0 / w_bar;
+    return SGP_OK;
+}
+
+
+// ---- measurement hooks of the M x M path (bench.py `dense` leg) ---------------------------------------------------------------------
+// Device time (CUDA events on the ctx stream, kernels only: from the call's first enqueue to its last kernel) of `reps` calls of
+//   what = 0: sgp_kuu_factor(jitter)   1: sgp_posterior_v_stream(w, carry = 0) with Uv   2: ... without Uv   3: sgp_w_terms (resident posterior)
+// on the resident state (needs a sweep; 1-3 need a resident prior, 3 a posterior and K_uu).  Returns the mean per call.
+int sgp_dense_timed(sgp_ctx* ctx, int what, double w, double jitter, int reps, float* ms_per_call) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (reps < 1 || what < 0 || what > 3 || !ms_per_call) SGP_FAIL(ctx, SGP_ERR_ARG, "dense_timed: bad arguments");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    double tot = 0.0;
+    int rc = SGP_OK;
+    for (int r = 0; r < reps && rc == SGP_OK; ++r) {
+        SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->dense_timing = true;
+        if (cudaEventRecord(ctx->ev[0], ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
+        double a = 0.0, b = 0.0;
+        if (rc == SGP_OK) {
+            if (what == 0) rc = sgp_kuu_factor(ctx, jitter, nullptr);
+            else if (what == 1 || what == 2) {
+                if (!ctx->have_stats || !ctx->have_prior || ctx->Dout != 1) { ctx->err = "dense_timed: needs a sweep and a resident prior"; rc = SGP_ERR_ARG; }
+                else { rc = ensure_post(ctx); if (rc == SGP_OK) rc = posterior_core(ctx, w, false, what == 1, nullptr, nullptr, nullptr); }
+            } else rc = sgp_w_terms(ctx, nullptr, nullptr, &a, &b);
+        }
+        ctx->dense_timing = false;
+        if (rc == SGP_OK) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(ctx->ev[1]) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) != cudaSuccess) rc = SGP_ERR_CUDA;
+            tot += ms;
+        }
     }
-    if (!rc && cudaMemcpyAsync(out, o, (size_t)Nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = SGP_ERR_CUDA;
-    cudaFree(xt); cudaFree(o); cudaFree(mu);
-    if (rc == SGP_ERR_CUDA) ctx->err = "predict_mean: CUDA failure";
-    return rc;
+    if (rc == SGP_ERR_CUDA && ctx->err.empty()) ctx->err = "dense_timed: CUDA failure";
+    if (rc) return rc;
+    *ms_per_call = (float)(tot / reps);
+    return SGP_OK;
 }
 
 }  // extern "C"
+
+// FP64 tensor-pipe peak measured on THIS device: every warp keeps 16 independent DMMA.8x8x4 accumulator chains busy (registers only)
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* __restrict__ out, int iters, double seed) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = seed * (threadIdx.x + 1) * 1e-3, b = seed * (threadIdx.x + 3) * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;       // never true: keeps the chains alive
+}
+
+extern "C" int sgp_fp64_peak(sgp_ctx* ctx, int ms_target, double* dmma_tflops) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!dmma_tflops || ms_target < 1) SGP_FAIL(ctx, SGP_ERR_ARG, "fp64_peak: bad arguments");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    const int grid = 4 * ctx->num_sms;
+    int iters = 20000;
+    double best = 0.0;
+    for (int pass = 0; pass < 4; ++pass) {
+        SGP_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        fp64_peak_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->exptab_dev, iters, 1.0e-3);
+        SGP_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        SGP_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0.f; SGP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        const double flops = (double)grid * 8.0 * iters * 16.0 * 512.0;          // warps x iterations x chains x (8 x 8 x 4 FMA = 512 FLOP)
+        if (pass > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+        if (pass == 0 && ms > 0.f) iters = (int)std::min(4.0e6, std::max(1000.0, iters * (double)ms_target / ms));
+    }
+    *dmma_tflops = best;
+    return SGP_OK;
+}

@@ -167,7 +167,7 @@ extern "C" int sgp_comm_init(sgp_ctx* ctx, int nranks, int rank, const char id[1
     return SGP_OK;
 }
 
-int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count) {
+int sgp_comm_allreduce_nccl(sgp_ctx* ctx, double* buf, size_t count) {
     if (!ctx->comm) return SGP_OK;
     NcclApi& a = api();
     ncclResult_t r = a.AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm->comm, ctx->stream);

@@ -1,6 +1,7 @@
 // libsgp internals shared by the translation units (not part of the public ABI; see include/sgp.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -17,6 +18,8 @@ struct sgp_ctx {
     int dev = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;           // copies that overlap the next kernel (created with the context)
+    cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
 
@@ -44,6 +47,7 @@ struct sgp_ctx {
     bool stats_external = false;    // stats_dev lives in the peer-mapped exchange region of the communicator (comm.cu)
     int Dout = 1;
     bool have_stats = false;
+    bool stats_of_data = false;     // ... and they are the statistics of the resident data set (not of a sigma-point cloud / theta scratch)
 
     // scratch
     double* work_dev = nullptr;  size_t work_cap = 0;      // split-N partials
@@ -56,11 +60,13 @@ struct sgp_ctx {
     double* exptab_dev = nullptr;
     double* dense_dev = nullptr; size_t dense_cap = 0;     // M x M scratch for factorisations
     int* info_dev = nullptr;
+    double* pred_dev = nullptr; size_t pred_cap = 0;       // scratch of sgp_predict_mean / sgp_predict_probit
+    double* wt_dev = nullptr;                              // block partials + ticket of sgp_wterms_reduce
     double* in_dev = nullptr; size_t in_cap = 0;           // scratch of sgp_in_logmessage (inmsg.cu)
     double* theta_dev = nullptr; size_t theta_cap = 0;     // scratch of the theta objective / gradient (theta.cu)
 
     // K_uu factor
-    double* KuuL_dev = nullptr; int KuuL_M = 0; bool have_kuu = false;
+    double* KuuL_dev = nullptr; int KuuL_M = 0; bool have_kuu = false; double kuu_jitter = 0.0;
     double* Kinv_dev = nullptr;                            // K_uu^-1 (full symmetric), refreshed by sgp_kuu_factor
     double* kuu_dinv_dev = nullptr; size_t kuu_dinv_cap = 0; // inverses of the 64 x 64 diagonal blocks of KuuL
     double* dinv_dev = nullptr; size_t dinv_cap = 0;       // ... of the factor produced by the last sgp_potrf_lower
@@ -81,6 +87,7 @@ struct sgp_ctx {
     bool want_exchange = false;           // set by the public sweep calls: theta / uncertain-input sweeps keep their statistics local
     bool last_sweep_exchanged = false;    // the last sweep kernel already summed the statistics over the ranks
     float last_main_ms = 0.f;
+    bool dense_timing = false;            // sgp_dense_timed: the M x M calls record ev[1] after their last kernel
     long long* sweep_dbg_dev = nullptr;   // optional per-segment clocks (sgp_sweep_debug_clocks)
     int sweep_dbg_slots = 0;
 };
@@ -94,6 +101,13 @@ struct sgp_ctx {
         }                                                                                            \
     } while (0)
 
+// NVTX range over a host-side call of the library (upload / sweep / posterior / fetch): visible in Nsight Systems timelines, free otherwise
+struct SgpRange {
+    explicit SgpRange(const char* name) { nvtxRangePushA(name); }
+    ~SgpRange() { nvtxRangePop(); }
+};
+#define SGP_RANGE(name) SgpRange sgp_range__(name)
+
 #define SGP_FAIL(ctx, code, msg) do { (ctx)->err = (msg); return (code); } while (0)
 
 int sgp_ensure(sgp_ctx* ctx, double** p, size_t* cap, size_t need_doubles);
@@ -101,19 +115,38 @@ int sgp_ensure(sgp_ctx* ctx, double** p, size_t* cap, size_t need_doubles);
 // sweep.cu
 int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const double* yv, const double* w, int64_t N,
                      int64_t Ncap, bool time_main);
-// dense.cu
-int sgp_potrf_lower(sgp_ctx* ctx, double* A, int M);                              // in place, column-major, lower
-int sgp_trsm_lower(sgp_ctx* ctx, const double* L, double* B, int M, int nrhs, bool trans);  // L X = B or L' X = B
-// dense_coop.cu
+// dense_coop.cu: one cooperative kernel per M x M job: [build A] -> Cholesky -> [X = L^-1, S = X'X] -> [mu = S xi] -> [Ut = L']
+struct SgpDenseJob {
+    int M = 0;
+    int build = 0;             // 0: A as given | 1: A = P + w S2, xi = xip + w s1 (carry: P <- A, xip <- xi) | 2: A = K_uu(Z) + jitter I | 3: A = Sig + mu_in mu_in'
+    double* A = nullptr;       // M x M column-major, factored in place (L lower, strict upper triangle zeroed)
+    double* Dinv = nullptr;    // [ceil(M/64)][64 x 64] inverses of the diagonal blocks of L
+    const double* S2 = nullptr; const double* s1 = nullptr; double* P = nullptr; double* xip = nullptr; double* xi = nullptr; double w = 0.0; int carry = 0;
+    double jitter = 0.0;
+    const double* Sig = nullptr; const double* mu_in = nullptr;
+    double* X = nullptr; double* Tmp = nullptr; double* S = nullptr;    // optional inverse: X = L^-1, S = (L L')^-1 (full symmetric), Tmp = M x M scratch
+    double* mu = nullptr;      // optional: mu = S xi
+    double* Ut = nullptr;      // optional: Ut = L' (upper)
+    long long* clk = nullptr;  // optional: 8 phase clocks of CTA 0
+    int reset_info = 1;        // zero ctx->info_dev before the launch
+};
+int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& job);                          // enqueues; no host synchronisation
+int sgp_dense_info(sgp_ctx* ctx, const char* what);                               // synchronises; non-positive pivot -> SGP_ERR_NOT_PD
+int sgp_potrf_lower(sgp_ctx* ctx, double* A, int M);                              // in place, column-major, lower (synchronises)
 int sgp_trsm_lower_dinv(sgp_ctx* ctx, const double* L, const double* dinv, double* B, double* tmp, int M, int nrhs, bool trans);
-int sgp_trtri_lower(sgp_ctx* ctx, const double* L, double* X, double* Tmp, double* S, int M);   // X = L^-1, S = X' X (optional)
-int sgp_kuu_build(sgp_ctx* ctx, double* K, double jitter);
+// dense.cu: deterministic reductions
+int sgp_dot(sgp_ctx* ctx, const double* a, size_t sa, const double* b, size_t sb, size_t n, double* out);
+// out[0] = <Kinv, Psi2>, out[1] = <R + mu_outer mu_outer', Psi2>, out[2] = mu' psi1, out[3] = trace(Kinv)   (R, mu_outer, Kinv may be null)
+int sgp_wterms_reduce(sgp_ctx* ctx, const double* Kinv, const double* Psi2, const double* R, const double* mu_outer, const double* mu,
+                      const double* psi1, int M, double* out);
 // api.cu: resident posterior (mu [M], Uv [M x M upper]) or nullptr when there is none
 const double* sgp_resident_mu(sgp_ctx* ctx);
 const double* sgp_resident_uv(sgp_ctx* ctx);
-int sgp_dot(sgp_ctx* ctx, const double* a, size_t sa, const double* b, size_t sb, size_t n, double* out);   // deterministic
+const double* sgp_resident_sigma(sgp_ctx* ctx);
+int sgp_sweep_resident(sgp_ctx* ctx, bool time_main);     // sweep of the resident data, statistics summed over the ranks
 // comm.cu
-int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count);
+int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count);          // xchg.cu: peer-memory kernel, or NCCL when the regions are not mapped
+int sgp_comm_allreduce_stats(sgp_ctx* ctx, int M, int D_out);               // ... of the resident statistics (packed lower triangle on the wire)
 void sgp_comm_destroy(sgp_ctx* ctx);
 // Peer-memory exchange fused into the sweep kernel (single node, <= 8 ranks): every rank owns a region
 // [flags A | flags B | xin (cap doubles) | xout (cap doubles)] that all peers map through CUDA IPC.
@@ -122,7 +155,7 @@ struct SgpXchg {
     unsigned epoch = 0;            // barrier value of this sweep (flags are monotonic, never reset)
     char* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // region of rank q as mapped here
     size_t xin_off = 0, xout_off = 0;   // byte offsets inside a region; flags A at 0, flags B at 64
-    long long count = 0;           // doubles exchanged: M*M + M + 4
+    long long count = 0;           // capacity check only: doubles of the unpacked statistics
 };
 bool sgp_comm_xchg(sgp_ctx* ctx, size_t need_doubles, SgpXchg* x);     // fills x (and bumps the epoch) if the fused exchange is available
 int sgp_ensure_stats(sgp_ctx* ctx, size_t need_doubles);               // stats_dev: exchange region when available, else an own buffer

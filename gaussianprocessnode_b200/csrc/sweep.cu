@@ -93,11 +93,12 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     p.slab_doubles = (long long)(slab_chunks * chunk_doubles); p.nring = nring;
     p.partial = ctx->work_dev; p.psi1_partial = p.partial + (size_t)nslots * TM * TM; p.scal_partial = p.psi1_partial + (size_t)ncta * TM;
     p.psi2 = ctx->stats_dev; p.psi1 = p.psi2 + (size_t)M * M; p.scal = p.psi1 + M;
-    // multi-GPU: phase 2 writes this rank's statistics into its exchange region and the kernel sums them over the ranks through peer
-    // memory (two-shot: every rank reduces 1/R of the buffer and stores the result into every rank's stats buffer)
+    // multi-GPU: phase 2 writes this rank's statistics into its exchange region (Psi2 as the packed lower triangle) and the kernel sums them
+    // over the ranks through peer memory (one-shot pull: every rank reads all contributions and adds them in rank order, xchg.cuh)
     ctx->last_sweep_exchanged = false;
     if (ctx->want_exchange && sgp_comm_xchg(ctx, (size_t)M * M + M + 4, &p.xr)) {
-        p.psi2 = reinterpret_cast<double*>(p.xr.peers[p.xr.rank] + p.xr.xin_off); p.psi1 = p.psi2 + (size_t)M * M; p.scal = p.psi1 + M;
+        p.psi2 = reinterpret_cast<double*>(p.xr.peers[p.xr.rank] + p.xr.xin_off); p.psi1 = p.psi2 + (size_t)M * (M + 1) / 2; p.scal = p.psi1 + M;
+        p.stats_out = ctx->stats_dev;
         ctx->last_sweep_exchanged = true;
     }
 
@@ -138,6 +139,7 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
 int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const double* yv, const double* w, int64_t N, int64_t Ncap,
                      bool time_main) {
     if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: set_kernel and set_inducing first");
+    ctx->stats_of_data = false;      // set again by the caller that sweeps the resident data set (sgp_sweep_resident)
     constexpr int NB = 32;
     {
         const long long chunks_ = (N + NB - 1) / NB;

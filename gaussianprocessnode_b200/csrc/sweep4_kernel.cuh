@@ -5,7 +5,7 @@
 // regeneration is paid from the MMA budget (2 176 of 10 368 pipe clocks per off-diagonal chunk).  Here every K_uf value is
 // generated exactly ONCE per sweep:
 //
-//   for each slab of the N range (sized so that its K_uf panel, M x slab points, stays in the 126 MB L2; a ring of two panels):
+//   for each slab of the N range (sized so that its K_uf panel, M x slab points, stays in the 126 MB L2; a ring of three panels):
 //     G phase   every CTA generates its share of the slab's panel -- (row block, chunk range) -- with the same DMMA-dot +
 //               table-exp generator and writes it to the panel, laid out exactly as the consumer's shared-memory tile:
 //               [chunk][row block][32 points][TM + 4]; Psi1 += k (w y) is folded in here.  Then it bumps the row block's
@@ -18,9 +18,10 @@
 //   grid barrier, phase 2: deterministic reduction of the segment partials, mirror, Psi1, scalars.
 //
 // There is no grid-wide barrier inside the slab loop: CTAs run up to a slab apart, so load imbalance averages out over the
-// sweep.  K_uf is never streamed from HBM: the two panels are rewritten in place slab after slab and are read from L2.
+// sweep.  K_uf is never streamed from HBM: the ring's panels are rewritten in place slab after slab and are read from L2.
 #pragma once
 #include "sweep_kernel.cuh"
+#include "xchg.cuh"
 
 namespace sgp_sweep4 {
 
@@ -64,7 +65,8 @@ struct Params {
     double center[SGP_MAX_D];
     double log_var_s;
     double variance;
-    SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none)
+    SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none): psi2 / psi1 / scal then point into this rank's xin, Psi2 as the PACKED lower triangle
+    double* stats_out;            // ... and the sums over the ranks land here (full symmetric Psi2 | Psi1 | scalars)
 };
 
 __device__ __forceinline__ void mbar_wait_(unsigned long long* bar, unsigned parity) {
@@ -575,6 +577,7 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
     constexpr int NBATCH = 4;                        // stripes whose loads are in flight together (S_ holds NBATCH stripes)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nitems = p.ntiles * STRIPES;
+    const bool packed = p.xr.nranks > 1;
     const int it0 = (int)((long long)nitems * blockIdx.x / gridDim.x), it1 = (int)((long long)nitems * (blockIdx.x + 1) / gridDim.x);
     int* slots = ibuf + NWARPS;
     int it = it0;
@@ -637,11 +640,12 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                 const int r0 = (sb + q) * SR;
                 const double* Sq = S_ + (size_t)q * SR * LDS_;
                 for (int e = tid; e < SR * TM; e += NT) {
-                    {   // psi2[gi + gj*M]: SR consecutive rows = one 32-byte sector per column
+                    {   // psi2[gi + gj*M]: SR consecutive rows = one 32-byte sector per column (multi-GPU: column gj of the packed lower triangle)
                         const int rl = e % SR, c = e / SR, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
-                        if (gi < p.M && gj < p.M && (!diag || c <= r)) p.psi2[(size_t)gi + (size_t)gj * p.M] = Sq[rl * LDS_ + c];
+                        if (gi < p.M && gj < p.M && (!diag || c <= r))
+                            p.psi2[packed ? (size_t)(sgp_xchg::tri_col(gj, p.M) + gi - gj) : (size_t)gi + (size_t)gj * p.M] = Sq[rl * LDS_ + c];
                     }
-                    {   // mirror psi2[gj + gi*M]: consecutive threads -> consecutive columns
+                    if (!packed) {   // mirror psi2[gj + gi*M]: consecutive threads -> consecutive columns (multi-GPU: the pull writes both halves)
                         const int rl = e / TM, c = e % TM, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
                         if (gi < p.M && gj < p.M && (diag ? c < r : true)) p.psi2[(size_t)gj + (size_t)gi * p.M] = Sq[rl * LDS_ + c];
                     }
@@ -672,95 +676,6 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
             }
         }
         it += s_hi - s_lo;
-    }
-}
-
-// ---- multi-GPU: sum of the statistics over the ranks through peer memory, inside the sweep kernel ------------------------------
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
-// wait until rank q has signalled `epoch` in this rank's flag array (a peer that never arrives means a lost rank: trap after ~20 s)
-__device__ __forceinline__ void xchg_wait(const unsigned* flag, unsigned epoch) {
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
-        __nanosleep(64);
-        if (clock64() - t0 > 40000000000ll) __trap();
-    }
-}
-// All-reduce over NVLink peer memory (two-shot; one-shot for two ranks).  Every rank has written its statistics to its own xin.  Barrier A (flags), then rank r
-// sums elements [r, r+1) * count / R of all xin in rank order -- the same order on every rank: bitwise identical results -- and stores
-// the sums into every rank's xout (its stats buffer); barrier B.
-// Before phase 2 overwrites this rank's xin: every peer must have finished READING it in the previous exchange (flag B of epoch - 1; in the
-// two-shot form that is implied by the kernel's closing wait, in the one-shot form the peers signal it without anyone waiting at the time).
-__device__ __forceinline__ void xchg_before_phase2(const SgpXchg& x) {
-    const int tid = threadIdx.x;
-    if (tid < x.nranks) xchg_wait(reinterpret_cast<unsigned*>(x.peers[x.rank]) + 16 + tid, x.epoch - 1u);
-    __syncthreads();
-}
-
-template <int NT>
-__device__ __forceinline__ void xchg_allreduce(const SgpXchg& x, cooperative_groups::grid_group& grid) {
-    const int tid = threadIdx.x, R = x.nranks;
-    __threadfence();
-    grid.sync();                                            // this rank's xin is complete (gpu scope) ...
-    unsigned* myflags = reinterpret_cast<unsigned*>(x.peers[x.rank]);
-    if (blockIdx.x == 0 && tid < R) {                       // ... and published system-wide by the signalling threads (release is cumulative)
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned*>(x.peers[tid]) + x.rank, x.epoch);
-    }
-    if (tid < R) xchg_wait(myflags + tid, x.epoch);         // every CTA polls the local flags: no second grid barrier
-    __syncthreads();
-    if (R == 2) {
-        // ONE-SHOT for two ranks: every rank pulls the peer's whole xin and sums locally (same rank order on both: identical bits); no remote
-        // stores, no second cross-GPU wait -- the peers only learn, through flag B, that this rank is done reading their xin
-        const long long pairs = (x.count + 1) / 2;
-        const double2* in0 = reinterpret_cast<const double2*>(x.peers[0] + x.xin_off);
-        const double2* in1 = reinterpret_cast<const double2*>(x.peers[1] + x.xin_off);
-        double2* outp = reinterpret_cast<double2*>(x.peers[x.rank] + x.xout_off);
-        const long long stride = (long long)gridDim.x * NT;
-        for (long long e = (long long)blockIdx.x * NT + tid; e < pairs; e += 4 * stride) {
-            double2 a[4], b[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (e + u * stride < pairs) { a[u] = __ldcv(in0 + e + u * stride); b[u] = __ldcv(in1 + e + u * stride); }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (e + u * stride < pairs) outp[e + u * stride] = make_double2(a[u].x + b[u].x, a[u].y + b[u].y);
-        }
-        __threadfence();
-        grid.sync();                                        // every CTA of this rank is done reading
-        if (blockIdx.x == 0 && tid < R) st_release_sys(reinterpret_cast<unsigned*>(x.peers[tid]) + 16 + x.rank, x.epoch);
-        return;
-    }
-    // this rank's share, in pairs of doubles; up to U pairs per thread with all their peer loads in flight together
-    constexpr int U = 2;
-    const long long pairs = (x.count + 1) / 2;              // (the buffers are padded: reading / writing one double past count is harmless)
-    const long long p0 = pairs * x.rank / R, p1 = pairs * (x.rank + 1) / R;
-    const long long stride = (long long)gridDim.x * NT;
-    for (long long e = p0 + (long long)blockIdx.x * NT + tid; e < p1; e += U * stride) {
-        double2 v[U][8];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (q < R && e + u * stride < p1) v[u][q] = __ldcv(reinterpret_cast<const double2*>(x.peers[q] + x.xin_off) + e + u * stride);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (e + u * stride >= p1) break;
-            double2 sum = v[u][0];
-#pragma unroll
-            for (int q = 1; q < 8; ++q) if (q < R) { sum.x += v[u][q].x; sum.y += v[u][q].y; }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) if (q < R) reinterpret_cast<double2*>(x.peers[q] + x.xout_off)[e + u * stride] = sum;
-        }
-    }
-    __threadfence();
-    grid.sync();                                            // this rank's share is stored everywhere
-    if (blockIdx.x == 0 && tid < R) {
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned*>(x.peers[tid]) + 16 + x.rank, x.epoch);
-        xchg_wait(myflags + 16 + tid, x.epoch);             // the kernel ends only when every peer's share has landed here
     }
 }
 
@@ -947,13 +862,18 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     __threadfence();
     grid.sync();
     if (p.dbg) t_k3 = clock64();
-    if (p.xr.nranks > 1) xchg_before_phase2(p.xr);
+    if (p.xr.nranks > 1) sgp_xchg::wait_free(p.xr);       // every peer has read this rank's previous contribution
     long long tr[3] = {0, 0, 0};
     reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)), tr);
     // the dependency counters are dead after the last grid barrier: leave them zeroed for the next launch (no memset per sweep on the host)
     if (bcta == 0)
         for (int i = tid; i < p.nring * (p.nblk + 1); i += NT) p.flags[i] = 0u;
-    if (p.xr.nranks > 1) xchg_allreduce<NT>(p.xr, grid);
+    if (p.xr.nranks > 1) {      // sum over the ranks (xchg.cuh): publish, wait for all contributions, one-shot pull, signal "done reading"
+        sgp_xchg::publish(p.xr, p.ncta);
+        sgp_xchg::gather_wait(p.xr);
+        sgp_xchg::pull_stats(p.xr, p.stats_out, p.M, p.M + 4, bcta, p.ncta);
+        sgp_xchg::done(p.xr, p.ncta);
+    }
     if (p.dbg && tid == 0) {   // timeline of this CTA: {setup clocks, slab-loop clocks, 4, cta}, {final barrier clocks, phase-2 (+ exchange) clocks, 5, cta}
         long long* d = p.dbg + 4 * (size_t)(p.ncta + p.ntiles) + 8 * (size_t)p.ncta;
         d[8 * bcta + 0] = t_k1 - t_k0; d[8 * bcta + 1] = t_k2 - t_k1; d[8 * bcta + 2] = 4; d[8 * bcta + 3] = bcta;

@@ -132,14 +132,6 @@ __global__ void finish_kernel(const double* __restrict__ partial, int nblocks, d
     total[d] += scale * a;
 }
 
-__global__ void identity_kernel2(double* __restrict__ A, int M) {
-    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (e < (size_t)M * M) A[e] = (e % M == e / M) ? 1.0 : 0.0;
-}
-__global__ void sub_kernel(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b, size_t n) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = a[i] - b[i];
-}
 // out[0] = sum_i a[i*sa] * (b ? b[i*sb] : 1)   single block, fixed order
 __global__ void dot_kernel2(const double* __restrict__ a, size_t sa, const double* __restrict__ b, size_t sb, size_t n, double* __restrict__ out) {
     __shared__ double s[256];
@@ -153,6 +145,16 @@ __global__ void dot_kernel2(const double* __restrict__ a, size_t sa, const doubl
 
 inline unsigned nb(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
+// A = (R ? R : Sig + mu mu') - Kinv, and Rv (optional) = that first term
+__global__ void amat_kernel(double* __restrict__ A, double* __restrict__ Rv, const double* __restrict__ R, const double* __restrict__ Sig, const double* __restrict__ mu,
+                            const double* __restrict__ Kinv, int M) {
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e >= (size_t)M * M) return;
+    const double r = R ? R[e] : fma(mu[e % M], mu[e / M], Sig[e]);
+    if (Rv) Rv[e] = r;
+    A[e] = r - Kinv[e];
+}
+
 }  // namespace
 
 extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const double* Uv, double w, double jitter, double* value,
@@ -160,85 +162,77 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
     if (!ctx) return SGP_ERR_ARG;
     if (!ctx->have_kernel || !ctx->have_Z || ctx->N <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: set_kernel, set_inducing and set_data first");
     if ((mu_v == nullptr) != (Uv == nullptr)) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: pass both mu_v and Uv, or neither (resident posterior)");
-    if (!mu_v && !(sgp_resident_mu(ctx) && sgp_resident_uv(ctx))) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: no resident posterior (sgp_posterior_v first)");
+    if (!mu_v && !(sgp_resident_mu(ctx) && sgp_resident_sigma(ctx))) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: no resident posterior (sgp_posterior_v first)");
     if (ctx->have_w) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "theta_objective: per-point weights are not part of the reference objective");
+    SGP_RANGE("sgp_theta_objective");
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
     const int M = ctx->M, D = ctx->D;
     const size_t MM = (size_t)M * M;
     const int64_t N = ctx->N;
     const bool want_grad = dvariance != nullptr || dlengthscale != nullptr;
 
-    // local statistics of this rank's points (the objective is a sum over n: its D + 2 scalars are all-reduced at the end)
-    int rc = sgp_sweep_launch(ctx, ctx->X_dev, ctx->y_dev, nullptr, nullptr, N, ctx->Ncap, false); if (rc) return rc;
-    rc = sgp_kuu_factor(ctx, jitter, nullptr); if (rc) return rc;
+    // The objective is linear in the statistics of the resident data at the current kernel: they are reused when the last sweep produced exactly
+    // those, otherwise the regular sweep runs (with a communicator: summed over the ranks, so that the resident statistics stay what every
+    // other call expects).  Only the data part of the gradient below is rank-local and summed at the end.
+    int rc = SGP_OK;
+    if (!(ctx->have_stats && ctx->stats_of_data && ctx->Dout == 1)) { rc = sgp_sweep_resident(ctx, false); if (rc) return rc; }
+    if (!(ctx->have_kuu && ctx->kuu_jitter == jitter)) { rc = sgp_kuu_factor(ctx, jitter, nullptr); if (rc) return rc; }
 
     const int nc_max = (int)std::min<int64_t>(N, std::max<int64_t>(1024, (int64_t)(16u << 20) / M));     // K and G chunks: 2 x 128 MB at most
     const int cblocks = 4 * ctx->num_sms;
-    // scratch: [Kinv | Rv | A | B | T] (M x M each) | v (M) | res (64) | total (SGP_MAX_D) | K chunk | G chunk | block partials
-    size_t need = 5 * MM + (size_t)M + 64 + SGP_MAX_D + (want_grad ? 2 * (size_t)M * nc_max + (size_t)cblocks * SGP_MAX_D : 0);
+    // scratch: [Rv | A | B | T] (M x M each) | v (M) | res (64) | totals (2 x SGP_MAX_D) | K chunk | G chunk | block partials
+    size_t need = 4 * MM + (size_t)M + 64 + 2 * SGP_MAX_D + (want_grad ? 2 * (size_t)M * nc_max + (size_t)cblocks * SGP_MAX_D : 0);
     rc = sgp_ensure(ctx, &ctx->theta_dev, &ctx->theta_cap, need); if (rc) return rc;
-    double* Kinv = ctx->theta_dev; double* Rv = Kinv + MM; double* A = Rv + MM; double* B = A + MM; double* T = B + MM;
-    double* vdev = T + MM; double* res = vdev + M; double* total = res + 64; double* Kc = total + SGP_MAX_D;
+    double* Rv = ctx->theta_dev; double* A = Rv + MM; double* B = A + MM; double* T = B + MM;
+    double* vdev = T + MM; double* res = vdev + M; double* total = res + 64; double* total_data = total + SGP_MAX_D; double* Kc = total_data + SGP_MAX_D;
     double* Gc = Kc + (size_t)M * nc_max; double* partial = Gc + (size_t)M * nc_max;
     double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM; double* scal = psi1 + M;
+    const double* Kinv = ctx->Kinv_dev;
 
-    // K_uu^-1 (left by sgp_kuu_factor)
-    SGP_CUDA(ctx, cudaMemcpyAsync(Kinv, ctx->Kinv_dev, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    // R_v = Uv' Uv (T holds Uv), A = R_v - K_uu^-1
+    // R_v = Uv' Uv (host posterior) or Sigma_v + mu_v mu_v' (resident posterior: no Cholesky factor needed); A = R_v - K_uu^-1
+    const double* v = nullptr;
     if (mu_v) {
         SGP_CUDA(ctx, cudaMemcpyAsync(T, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         SGP_CUDA(ctx, cudaMemcpyAsync(vdev, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, T, M, T, M, 0.0, Rv, M, 0); if (rc) return rc;
+        amat_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, nullptr, Rv, nullptr, nullptr, Kinv, M);
+        v = vdev;
     } else {
-        SGP_CUDA(ctx, cudaMemcpyAsync(T, sgp_resident_uv(ctx), MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        SGP_CUDA(ctx, cudaMemcpyAsync(vdev, sgp_resident_mu(ctx), (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        v = sgp_resident_mu(ctx);
+        amat_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, Rv, nullptr, sgp_resident_sigma(ctx), v, Kinv, M);
     }
-    rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, T, M, T, M, 0.0, Rv, M, 0); if (rc) return rc;
-    sub_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, Rv, Kinv, MM);
-    // scalars: <Kinv, Psi2>, <Rv, Psi2>, v' Psi1
-    rc = sgp_dot(ctx, Kinv, 1, psi2, 1, MM, res + 0); if (rc) return rc;
-    rc = sgp_dot(ctx, Rv, 1, psi2, 1, MM, res + 1); if (rc) return rc;
-    dot_kernel2<<<1, 256, 0, ctx->stream>>>(vdev, 1, psi1, 1, (size_t)M, res + 2);
-    SGP_CUDA(ctx, cudaMemsetAsync(total, 0, SGP_MAX_D * sizeof(double), ctx->stream));
-    SGP_CUDA(ctx, cudaMemsetAsync(res + 3, 0, sizeof(double), ctx->stream));
+    // scalars in one pass: <Kinv, Psi2>, <Rv, Psi2>, v' Psi1
+    rc = sgp_wterms_reduce(ctx, Kinv, psi2, Rv, nullptr, v, psi1, M, res); if (rc) return rc;
+    SGP_CUDA(ctx, cudaMemsetAsync(total, 0, 2 * SGP_MAX_D * sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaMemsetAsync(res + 4, 0, sizeof(double), ctx->stream));
 
     if (want_grad) {
         KParams kp{}; kp.kind = ctx->kind; kp.D = D; kp.M = M; kp.variance = ctx->variance;
         for (int d = 0; d < D; ++d) kp.ell_inv[d] = 1.0 / ctx->ell[d];
-        // B = Kinv Psi2 Kinv (T free again), tr B, K_uu part of the lengthscale gradient
+        // B = Kinv Psi2 Kinv, tr B, K_uu part of the lengthscale gradient (from the rank-summed statistics: identical on every rank)
         rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, Kinv, M, psi2, M, 0.0, T, M, 0); if (rc) return rc;
         rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, T, M, Kinv, M, 0.0, B, M, 0); if (rc) return rc;
-        dot_kernel2<<<1, 256, 0, ctx->stream>>>(B, (size_t)M + 1, nullptr, 0, (size_t)M, res + 3);
+        dot_kernel2<<<1, 256, 0, ctx->stream>>>(B, (size_t)M + 1, nullptr, 0, (size_t)M, res + 4);
         kuu_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->Z_dev, B, kp, partial);
         finish_kernel<<<1, 32, 0, ctx->stream>>>(partial, cblocks, 0.5 * w, total);
-        // data part, chunk by chunk: K chunk -> G = A K -> contraction
+        // data part (this rank's points), chunk by chunk: K chunk -> G = A K -> contraction
         for (int64_t n0 = 0; n0 < N; n0 += nc_max) {
             const int nc = (int)std::min<int64_t>(nc_max, N - n0);
             kuf_chunk_kernel<<<nb((size_t)M * nc), 256, 0, ctx->stream>>>(ctx->X_dev, ctx->Z_dev, Kc, n0, nc, kp);
             rc = sgp_gemm(ctx, 0, 0, M, nc, M, 1.0, A, M, Kc, M, 0.0, Gc, M, 0); if (rc) return rc;
-            grad_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, vdev, w, n0, nc, kp, partial);
-            finish_kernel<<<1, 32, 0, ctx->stream>>>(partial, cblocks, 1.0, total);
+            grad_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, v, w, n0, nc, kp, partial);
+            finish_kernel<<<1, 32, 0, ctx->stream>>>(partial, cblocks, 1.0, total_data);
         }
+        if (ctx->comm) { rc = sgp_comm_allreduce(ctx, total_data, (size_t)SGP_MAX_D); if (rc) return rc; }     // the only rank-local part
     }
     SGP_CUDA(ctx, cudaGetLastError());
-    // [value, dvariance, dlengthscale[D]] as one small buffer so that a communicator can sum it over ranks
-    double h[4], sc[4], tot[SGP_MAX_D];
-    SGP_CUDA(ctx, cudaMemcpyAsync(h, res, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    double h[8], sc[4], tot[2 * SGP_MAX_D];
+    SGP_CUDA(ctx, cudaMemcpyAsync(h, res, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SGP_CUDA(ctx, cudaMemcpyAsync(sc, scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SGP_CUDA(ctx, cudaMemcpyAsync(tot, total, SGP_MAX_D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SGP_CUDA(ctx, cudaMemcpyAsync(tot, total, 2 * SGP_MAX_D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    double out[2 + SGP_MAX_D];
-    out[0] = 0.5 * w * (sc[0] - h[0] + h[1]) - w * h[2];
-    out[1] = (0.5 * w * sc[0] - 0.5 * w * h[0] + w * h[1] - w * h[2] - 0.5 * w * jitter * h[3]) / ctx->variance;
-    for (int d = 0; d < D; ++d) out[2 + d] = tot[d] / (ctx->ell[d] * ctx->ell[d] * ctx->ell[d]);
-    if (ctx->comm) {
-        SGP_CUDA(ctx, cudaMemcpyAsync(res + 8, out, (2 + D) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        rc = sgp_comm_allreduce(ctx, res + 8, (size_t)(2 + D)); if (rc) return rc;
-        SGP_CUDA(ctx, cudaMemcpyAsync(out, res + 8, (2 + D) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    if (value) *value = out[0];
-    if (dvariance) *dvariance = out[1];
-    if (dlengthscale) for (int d = 0; d < D; ++d) dlengthscale[d] = out[2 + d];
-    ctx->have_stats = true;
+    if (value) *value = 0.5 * w * (sc[0] - h[0] + h[1]) - w * h[2];
+    if (dvariance) *dvariance = (0.5 * w * sc[0] - 0.5 * w * h[0] + w * h[1] - w * h[2] - 0.5 * w * jitter * h[4]) / ctx->variance;
+    if (dlengthscale) for (int d = 0; d < D; ++d) dlengthscale[d] = (tot[d] + tot[SGP_MAX_D + d]) / (ctx->ell[d] * ctx->ell[d] * ctx->ell[d]);
     return SGP_OK;
 }

@@ -47,16 +47,21 @@ __global__ void sigma_kernel(int method, int p, int d, long long N, int S, const
     if (n >= N) return;
     double L[UD * UD], m[UD];
     for (int i = 0; i < d; ++i) m[i] = mean[n * d + i];
-    for (int i = 0; i < d * d; ++i) L[i] = cov[n * d * d + i];
+    for (int i = 0; i < d * d; ++i) L[i] = (method == SGP_METHOD_POINT) ? 0.0 : cov[n * d * d + i];
     // symmetrise from both triangles (the reference hands a Hermitian view to the factorisation)
     for (int i = 0; i < d; ++i)
         for (int j = 0; j < i; ++j) { double v = 0.5 * (L[i + j * d] + L[j + i * d]); L[i + j * d] = v; L[j + i * d] = v; }
     double V00 = L[0];
-    if (!chol_small(L, d)) { atomicExch(info, 1); return; }
     double* X = Xv + n * S * d;
     double* w = wv + n * S;
     const double rn = r ? r[n] : 1.0;
     for (int s = 0; s < S; ++s) yv[n * S + s] = rn;
+    if (method == SGP_METHOD_POINT) {       // q(x_n) = delta(m_n): one point, weight 1 (the covariance is not read)
+        for (int i = 0; i < d; ++i) X[i] = m[i];
+        w[0] = 1.0;
+        return;
+    }
+    if (!chol_small(L, d)) { atomicExch(info, 1); return; }
     if (method == SGP_METHOD_SRCUBATURE) {
         // m +/- sqrt(d+1) L e_j, weight 1/(2(d+1)); centre last, weight 1/(d+1)
         const double sc = sqrt((double)d + 1.0);
@@ -405,7 +410,7 @@ inline unsigned nb(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); 
 int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double* mean, const double* cov, int D_out, const double* R,
                         double* psi0, double* psi1, double* psi2, double* psi1_n) {
     if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep_uncertain: set_kernel and set_inducing first");
-    if (N < 1 || !mean || !cov || D_out < 1) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep_uncertain: bad arguments");
+    if (N < 1 || !mean || (!cov && method != SGP_METHOD_POINT) || D_out < 1) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep_uncertain: bad arguments");
     const int d = ctx->D, M = ctx->M;
     if (d > UD) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "sweep_uncertain: input dimension <= 8");
     if (method == SGP_METHOD_CLOSED_FORM_SE && ctx->kind != SGP_KERNEL_SE) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "closed form exists for SE-ARD only");
@@ -417,7 +422,8 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
         double s = 1.0; for (int i = 0; i < d; ++i) s *= p;
         if (s > 4096.0) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "Gauss-Hermite tensor grid larger than 4096 points per input");
         S = (int)s;
-    } else if (method != SGP_METHOD_CLOSED_FORM_SE) SGP_FAIL(ctx, SGP_ERR_ARG, "unknown method");
+    } else if (method == SGP_METHOD_POINT) S = 1;
+    else if (method != SGP_METHOD_CLOSED_FORM_SE) SGP_FAIL(ctx, SGP_ERR_ARG, "unknown method");
 
     const bool need_p1n = psi1_n != nullptr || D_out > 1 || method == SGP_METHOD_CLOSED_FORM_SE;
     const size_t MM = (size_t)M * M;
@@ -440,7 +446,7 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
     cov_d = take((size_t)N * d * d);
     misc_d = take(256 + SGP_MAX_D);
     UC(cudaMemcpyAsync(mean_d, mean, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    UC(cudaMemcpyAsync(cov_d, cov, (size_t)N * d * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (cov) UC(cudaMemcpyAsync(cov_d, cov, (size_t)N * d * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (R) {
         R_d = take((size_t)N * D_out);
         UC(cudaMemcpyAsync(R_d, R, (size_t)N * D_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -543,6 +549,8 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
             if (rc) { cleanup(); return rc; }
         }
     }
+    // N sharded over ranks: the statistics are sums over the nodes of ALL ranks (the per-node Psi1_n stay local) -- COLLECTIVE like sgp_sweep_psi
+    if (ctx->comm) { rc = sgp_comm_allreduce_stats(ctx, M, D_out); if (rc) { cleanup(); return rc; } }
     int info = 0;
     UC(cudaMemcpyAsync(&info, ctx->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     double sc[4];

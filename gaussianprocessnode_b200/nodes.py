@@ -142,13 +142,10 @@ class UniSGPMeta:
     N: int
     ctx: Optional[SGPContext] = None
     kuu_jitter: float = 0.0
-    _x: List = field(default_factory=list)
-    _y: List = field(default_factory=list)
-    _yv: List = field(default_factory=list)
-    _wcount: int = 0
-    _ecount: int = 0
+    _q: Any = field(default_factory=lambda: {"v": [], "w": [], "e": []})    # one staging queue per interface: rule families may interleave
     _theta_key: Any = None
     _swept: bool = False
+    _resident_sig: Any = None                                                 # what the library currently holds (points, targets)
 
 
 def getmethod(meta): return meta.method
@@ -187,19 +184,31 @@ def _configure(meta, theta):
     ctx.set_inducing(Z)
     meta._theta_key = key
     meta._swept = False
+    meta._resident_sig = None
 
 
-def _enqueue(meta, q_out, q_in):
+def _enqueue(meta, kind, q_out, q_in):
+    """One (x_n, E[y_n], Var[y_n]) into the staging queue of interface `kind` ("v", "w", "e"); True when the queue holds meta.N entries."""
     mu_y, v_y = mean_var(q_out)
-    meta._x.append(np.atleast_1d(np.asarray(mean(q_in), dtype=np.float64)))
-    meta._y.append(float(mu_y)); meta._yv.append(float(v_y))
+    q = meta._q[kind]
+    q.append((np.atleast_1d(np.asarray(mean(q_in), dtype=np.float64)), float(mu_y), float(v_y)))
+    return len(q) == meta.N
 
 
-def _upload(meta):
+def _upload(meta, kind):
+    """Flushes the queue of interface `kind` into the library (sgp_set_data); a pass that queued exactly what is already resident
+    (the :w rule / energy after the :v rule of the same iteration) costs nothing."""
     ctx = _ctx(meta)
-    X = np.stack(meta._x[:meta.N]); y = np.array(meta._y[:meta.N]); yv = np.array(meta._yv[:meta.N])
+    q = meta._q[kind]
+    assert len(q) == meta.N, "UniSGP %s interface: %d queued points, meta.N = %d" % (kind, len(q), meta.N)
+    X = np.stack([e[0] for e in q]); y = np.array([e[1] for e in q]); yv = np.array([e[2] for e in q])
+    q.clear()
+    sig = (meta._theta_key, X.tobytes(), y.tobytes(), yv.tobytes())
+    if sig == meta._resident_sig:
+        return
     ctx.set_data(X, y, yv if np.any(yv != 0.0) else None)
-    meta._x.clear(); meta._y.clear(); meta._yv.clear()
+    meta._resident_sig = sig
+    meta._swept = False
 
 
 # ---- :v rule + prod -----------------------------------------------------------------------------------------------
@@ -207,7 +216,7 @@ def rule_v(q_out, q_in, q_w, q_theta, meta: UniSGPMeta):
     """@rule UniSGP(:v, Marginalisation) (q_out::PointMass|Gaussian, q_in::PointMass, q_w, q_theta, meta)
     -- GPnode/UniSGPnode.jl:144-158, 161-173.  Enqueues; the message is materialised by the N-th ``prod``."""
     _configure(meta, mean(q_theta))
-    _enqueue(meta, q_out, q_in)
+    _enqueue(meta, "v", q_out, q_in)
     return BufferUniSGP((float(mean(q_w)),), meta)
 
 
@@ -221,7 +230,7 @@ def prod(left, right: BufferUniSGP):
         return left
     ctx = _ctx(meta)
     w = right.qv[0]
-    _upload(meta)
+    _upload(meta, "v")
     psi0, psi1, psi2, sy2 = ctx.sweep_psi()
     meta.Psi0[...] = psi0; meta.Psi1_trans[:, 0] = psi1; meta.Psi2[...] = psi2
     meta._swept = True
@@ -244,12 +253,10 @@ def _ensure_kuu(meta):
         meta._kuu_key = meta._theta_key
 
 
-def _w_terms(meta, q_v):
+def _w_terms(meta, kind, q_v):
     ctx = _ctx(meta)
     _ensure_kuu(meta)
-    if len(meta._x) >= meta.N and meta.N > 0:    # this pass brought its own data
-        _upload(meta)
-        meta._swept = False
+    _upload(meta, kind)                          # this pass brought its own data (a no-op when it is what the :v pass left resident)
     if not meta._swept:
         ctx.sweep_psi(fetch=False)
         meta._swept = True
@@ -260,24 +267,18 @@ def rule_w(q_out, q_in, q_v, q_theta, meta: UniSGPMeta):
     """@rule UniSGP(:w, Marginalisation) -- UniSGPnode.jl:196-216, 219-238.  Neutral GammaShapeRate(1, 0) for the first
     N-1 nodes, GammaShapeRate(1 + N/2, sum_n rate_n) on the N-th: the product over the N nodes equals the reference's."""
     _configure(meta, mean(q_theta))
-    _enqueue(meta, q_out, q_in)
-    meta._wcount += 1
-    if meta._wcount != meta.N:
+    if not _enqueue(meta, "w", q_out, q_in):
         return GammaShapeRate(1.0, 0.0)
-    meta._wcount = 0
-    s1, s2 = _w_terms(meta, q_v)
+    s1, s2 = _w_terms(meta, "w", q_v)
     return GammaShapeRate(1.0 + 0.5 * meta.N, 0.5 * (s1 + s2))
 
 
 def average_energy(q_out, q_in, q_v, q_w, q_theta, meta: UniSGPMeta):
     """@average_energy UniSGP -- UniSGPnode.jl:337-359, 363-387: 0 for the first N-1 nodes, sum_n U_n on the N-th."""
     _configure(meta, mean(q_theta))
-    _enqueue(meta, q_out, q_in)
-    meta._ecount += 1
-    if meta._ecount != meta.N:
+    if not _enqueue(meta, "e", q_out, q_in):
         return 0.0
-    meta._ecount = 0
-    s1, s2 = _w_terms(meta, q_v)
+    s1, s2 = _w_terms(meta, "e", q_v)
     w_bar = mean(q_w)
     return 0.5 * w_bar * (s1 + s2) + 0.5 * meta.N * (LOG2PI - mean_log(q_w))
 
@@ -313,14 +314,14 @@ def rule_v_uncertain(q_out, q_in, q_w, q_theta, meta: UniSGPMeta):
     _configure(meta, mean(q_theta))
     m, v = mean_var(q_in)
     mu_y, _ = mean_var(q_out)
-    meta._x.append((np.atleast_1d(np.asarray(m, dtype=np.float64)), np.atleast_2d(np.asarray(v, dtype=np.float64))))
-    meta._y.append(float(mu_y))
+    meta._q["v"].append((np.atleast_1d(np.asarray(m, dtype=np.float64)), np.atleast_2d(np.asarray(v, dtype=np.float64)), float(mu_y)))
     return BufferUniSGP((float(mean(q_w)), "uncertain"), meta)
 
 
 def prod_uncertain(left, right: BufferUniSGP):
-    """The N-th fold of the uncertain-input messages: one sgp_sweep_psi_uncertain over the N queued inputs.  Each of the
-    reference's per-node messages carries Psi2_n + 1e-8 I (UniSGPnode.jl:135), so the sum carries N * 1e-8 I."""
+    """The N-th fold of the uncertain-input messages (the same `prod` UniSGPnode.jl:62-73 serves every :v variant): one
+    sgp_sweep_psi_uncertain over the N queued inputs, then the posterior exactly as `prod` does -- mean / covariance of the folded Gaussian
+    and ``meta.Uv = chol(Sigma_v + mu_v mu_v').U``.  Each per-node message carries Psi2_n + 1e-8 I (:135), so the sum carries N * 1e-8 I."""
     meta = right.meta
     meta.counter += 1
     if meta.counter != meta.N:
@@ -328,20 +329,25 @@ def prod_uncertain(left, right: BufferUniSGP):
     ctx = _ctx(meta)
     w = right.qv[0]
     mid, p = _method_of(meta)
-    means = np.stack([x[0] for x in meta._x[:meta.N]]); covs = np.stack([x[1] for x in meta._x[:meta.N]])
-    y = np.array(meta._y[:meta.N])
-    meta._x.clear(); meta._y.clear(); meta._yv.clear()
+    q = meta._q["v"]
+    assert len(q) == meta.N, "UniSGP :v interface (uncertain inputs): %d queued nodes, meta.N = %d" % (len(q), meta.N)
+    means = np.stack([e[0] for e in q]); covs = np.stack([e[1] for e in q]); y = np.array([e[2] for e in q])
+    q.clear()
+    meta._resident_sig = None; meta._swept = False
     psi0, psi1, psi2, _ = ctx.sweep_psi_uncertain(mid, means, covs, R=y[:, None], D_out=1, p=p)
     psi1 = np.asarray(psi1).reshape(-1)
-    psi2 = psi2 + meta.N * 1e-8 * np.eye(psi2.shape[0])
-    meta.Psi0[...] = psi0; meta.Psi1_trans[:, 0] = psi1; meta.Psi2[...] = psi2
+    jit = meta.N * 1e-8 * np.eye(psi2.shape[0])
+    meta.Psi0[...] = psi0; meta.Psi1_trans[:, 0] = psi1; meta.Psi2[...] = psi2 + jit
     if isinstance(left, MvNormalWeightedMeanPrecision):
         xi0, Lam0 = left.xi, left.Lam
     else:
         m0, S0 = mean_cov(left)
         Lam0 = np.linalg.inv(S0); xi0 = Lam0 @ m0
+    # the resident statistics are the un-jittered sums: the jitter rides on the prior's precision
+    mu_v, Sigma_v, Uv = ctx.posterior_v(xi0, Lam0 + w * jit, w)
+    meta.Uv = Uv
     meta.counter = 0
-    return MvNormalWeightedMeanPrecision(xi0 + w * psi1, Lam0 + w * psi2)
+    return MvNormalWeightedMeanPrecision(xi0 + w * psi1, Lam0 + w * (psi2 + jit), mu_v, Sigma_v)
 
 
 def _uncertain_node_terms(q_outs, q_ins, q_v, q_theta, meta: UniSGPMeta):
@@ -357,6 +363,7 @@ def _uncertain_node_terms(q_outs, q_ins, q_v, q_theta, meta: UniSGPMeta):
     covs = np.stack([np.atleast_2d(np.asarray(v, dtype=np.float64)) for _, v in mv])
     N = means.shape[0]
     ctx.sweep_psi_uncertain(mid, means, covs, R=None, D_out=1, p=p)          # builds (and leaves resident) the sigma-point cloud
+    meta._swept = False                                                      # the resident statistics are now the cloud's
     psi0, qk, lin, qr, tr_kinv, frob_uv = ctx.uncertain_node_terms(mean(q_v), meta.Uv, N)
     I1 = np.clip(psi0 - qk - 1e-8 * tr_kinv, 1e-12, 1e12)
     if q_outs is None:
@@ -387,6 +394,70 @@ def average_energy_uncertain(q_outs, q_ins, q_v, q_w, q_theta, meta: UniSGPMeta)
     I1, I2, _ = _uncertain_node_terms(q_outs, q_ins, q_v, q_theta, meta)
     w_bar = mean(q_w)
     return 0.5 * (I1 * w_bar - mean_log(q_w) + LOG2PI + I2 * w_bar)
+
+
+def _wpoint_energies(q_outs, q_ins, q_v, q_w, q_theta, meta: UniSGPMeta, pointmass_in):
+    """The two `q_w::PointMass` energies that add 1e-8 to EVERY element of an un-jittered K_uu, of Psi1_n and of Psi2_n and call plain `inv`
+    (UniSGPnode.jl:390-409 with q_in Gaussian, :438-458 with q_in PointMass), per node, on the library:
+      inv(K + eps 1 1') = K^-1 - c u u',  u = K^-1 1,  c = eps / (1 + eps 1'u)                      (Sherman-Morrison on the Cholesky-based K^-1)
+      tr(inv(.) (Psi2_n + eps 1 1')) = tr(K^-1 Psi2_n) - c u' Psi2_n u + eps (1'u - c (1'u)^2)
+      tr(R_v (Psi2_n + eps 1 1'))    = tr(R_v Psi2_n) + eps 1' R_v 1,      (Psi1_n + eps 1)' mu_v = Psi1_n' mu_v + eps 1' mu_v
+    with the per-node traces from sgp_uncertain_node_terms (u' Psi2_n u is the same call with the "factor" [u'; 0]).  K_uu without any jitter
+    is near-singular, so the value of the reference's LU-based `inv` is defined only up to cond(K_uu) * eps (tests/test_nodes_gpu.py states
+    the spread)."""
+    _configure(meta, mean(q_theta))
+    ctx = _ctx(meta)
+    eps = 1e-8
+    ctx.kuu_factor(0.0, fetch=False)
+    meta.KuuL = None; meta._kuu_key = None                    # the library now holds the UN-jittered factor, not meta.kuu_jitter's
+    M = np.asarray(meta.Xu).shape[0]
+    Kinv = ctx.kuu_solve(np.eye(M))
+    u = Kinv @ np.ones(M); s = float(u.sum()); c = eps / (1.0 + eps * s)
+    mu_v, Sigma_v = mean_cov(q_v)
+    Rv = np.asarray(Sigma_v, dtype=np.float64) + np.outer(mu_v, mu_v)
+    Uv = np.linalg.cholesky(Rv).T
+    if pointmass_in:
+        from .sgp import POINT
+        means = np.stack([np.atleast_1d(np.asarray(mean(q), dtype=np.float64)) for q in q_ins]); covs = None; mid, p = POINT, 0
+    else:
+        mid, p = _method_of(meta)
+        mv = [mean_var(q) for q in q_ins]
+        means = np.stack([np.atleast_1d(np.asarray(m, dtype=np.float64)) for m, _ in mv])
+        covs = np.stack([np.atleast_2d(np.asarray(v, dtype=np.float64)) for _, v in mv])
+    N = means.shape[0]
+    meta._resident_sig = None; meta._swept = False
+    ctx.sweep_psi_uncertain(mid, means, covs, R=None, D_out=1, p=p)
+    psi0, qk, lin, qr, _, _ = ctx.uncertain_node_terms(mu_v, Uv, N)
+    U2 = np.zeros((M, M)); U2[0, :] = u
+    _, _, _, quu, _, _ = ctx.uncertain_node_terms(mu_v, U2, N)
+    yv = [mean_var(q) for q in q_outs]
+    y = np.array([float(a) for a, _ in yv]); vy = np.array([float(b) for _, b in yv])
+    I1 = np.clip(psi0 - (qk - c * quu) - eps * (s - c * s * s), 1e-12, 1e12)
+    I2 = np.clip(y * y + vy - 2.0 * y * (lin + eps * float(np.sum(mu_v))) + qr + eps * float(Rv.sum()), 1e-12, 1e12)
+    w_bar = float(mean(q_w))
+    return 0.5 * (I1 * w_bar - np.log(w_bar) + LOG2PI + I2 * w_bar)
+
+
+def average_energy_uncertain_wpoint(q_outs, q_ins, q_v, q_w: PointMass, q_theta, meta: UniSGPMeta):
+    """@average_energy UniSGP (q_out Gaussian, q_in::UnivariateGaussianDistributionsFamily, q_v, q_w::PointMass, ...) -- UniSGPnode.jl:390-409: the N
+    per-node energies."""
+    return _wpoint_energies(q_outs, q_ins, q_v, q_w, q_theta, meta, False)
+
+
+def average_energy_gaussout_wpoint(q_outs, q_ins, q_v, q_w: PointMass, q_theta, meta: UniSGPMeta):
+    """@average_energy UniSGP (q_out Gaussian, q_in::PointMass, q_v, q_w::PointMass, ...) -- UniSGPnode.jl:438-458: the N per-node energies."""
+    return _wpoint_energies(q_outs, q_ins, q_v, q_w, q_theta, meta, True)
+
+
+def predict_new(x_test, q_v, q_w, q_theta, meta: UniSGPMeta):
+    """`predict_new` of the classification drivers (experiments/classification_banana.ipynb:289-293): the :out message of every test point
+    pushed through `@rule Probit(:out)`.  Returns (prediction_f: list of NormalMeanPrecision, p: Bernoulli means, p (1 - p): their variances)."""
+    _configure(meta, mean(q_theta))
+    ctx = _ctx(meta)
+    X = np.asarray(x_test, dtype=np.float64).reshape(-1, ctx.D)
+    w = float(mean(q_w))
+    m, _, prob = ctx.predict_probit(X, mean(q_v), w)
+    return [NormalMeanPrecision(float(v), w) for v in m], prob, prob * (1.0 - prob)
 
 
 @dataclass

@@ -5,7 +5,7 @@ import numpy as np
 from . import _lib
 
 SE, MATERN32, MATERN52 = 0, 1, 2
-SRCUBATURE, GENUT, GAUSSHERMITE, CLOSED_FORM_SE = 0, 1, 2, 3
+SRCUBATURE, GENUT, GAUSSHERMITE, CLOSED_FORM_SE, POINT = 0, 1, 2, 3, 4
 
 
 class SGPError(RuntimeError):
@@ -143,7 +143,7 @@ class SGPContext:
     def sweep_psi_uncertain(self, method, mean, cov, R=None, D_out=1, p=21, want_psi1_n=False):
         mean = _f64(mean).reshape(-1, self.D)
         N = mean.shape[0]
-        cov = _f64(cov).reshape(N, self.D, self.D)
+        cov = None if cov is None else _f64(cov).reshape(N, self.D, self.D)
         M = self.M
         if R is not None:
             R = _f64(R).reshape(N, D_out)
@@ -214,14 +214,15 @@ class SGPContext:
     def prior_set_isotropic(self, variance):
         self._ck(self.lib.sgp_prior_set_isotropic(self.h, float(variance)))
 
-    def posterior_v_stream(self, w, carry=True, fetch=False, out=None):
+    def posterior_v_stream(self, w, carry=True, fetch=False, out=None, want_Uv=True):
         """Posterior from the RESIDENT prior and the last sweep; with `carry` it becomes the next prior.  fetch=False copies
-        nothing back (mu_v / Uv stay resident for w_terms(None, None) / theta_objective(None, None, ...))."""
+        nothing back (mu_v / Sigma_v stay resident for w_terms(None, None) / theta_objective(None, None, ...)) and skips the
+        Cholesky factor Uv of Sigma_v + mu_v mu_v' altogether."""
         M = self.M
         if out is not None:
             mu, Sigma, Uv = out
         elif fetch:
-            mu, Sigma, Uv = np.empty(M), np.empty((M, M), order="F"), np.empty((M, M), order="F")
+            mu, Sigma, Uv = np.empty(M), np.empty((M, M), order="F"), (np.empty((M, M), order="F") if want_Uv else None)
         else:
             mu = Sigma = Uv = None
         self._ck(self.lib.sgp_posterior_v_stream(self.h, float(w), 1 if carry else 0, _p(mu), _p(Sigma), _p(Uv)))
@@ -242,6 +243,26 @@ class SGPContext:
         out = np.empty(Xt.shape[0])
         self._ck(self.lib.sgp_predict_mean(self.h, Xt.shape[0], _p(Xt), _p(mu_v), _p(out)))
         return out
+
+    def predict_probit(self, Xt, mu_v, w_bar):
+        """(mean_f, var_f, prob_y) of `predict_new` in the classification drivers (sgp_predict_probit)."""
+        Xt = _f64(Xt).reshape(-1, self.D)
+        mu_v = _f64(mu_v, (self.M,))
+        mean_f = np.empty(Xt.shape[0]); prob = np.empty(Xt.shape[0]); var_f = ctypes.c_double()
+        self._ck(self.lib.sgp_predict_probit(self.h, Xt.shape[0], _p(Xt), _p(mu_v), float(w_bar), _p(mean_f), ctypes.byref(var_f), _p(prob)))
+        return mean_f, var_f.value, prob
+
+    def dense_timed(self, what, w=1.0, jitter=0.0, reps=10):
+        """Device ms per call of kuu_factor (0) / posterior_v_stream with (1) or without (2) Uv / w_terms (3) on the resident state."""
+        ms = ctypes.c_float()
+        self._ck(self.lib.sgp_dense_timed(self.h, int(what), float(w), float(jitter), int(reps), ctypes.byref(ms)))
+        return ms.value
+
+    def fp64_peak(self, ms_target=200):
+        """FP64 DMMA peak of this device, TFLOP/s (sgp_fp64_peak)."""
+        v = ctypes.c_double()
+        self._ck(self.lib.sgp_fp64_peak(self.h, int(ms_target), ctypes.byref(v)))
+        return v.value
 
     def uncertain_node_terms(self, mu_v, Uv, N):
         """Per-node (Psi0_n, tr(Kuu^-1 Psi2_n), Psi1_n' mu_v, tr(Uv'Uv Psi2_n)) of the last sweep_psi_uncertain's N nodes, plus tr(Kuu^-1) and |Uv|_F^2

@@ -24,7 +24,11 @@ def _softplus_jac(theta, D):
     return dvar, dell
 
 
-def _load(ctx, theta, y_data, x_data, kernel, Xu):
+def _load(ctx, theta, y_data, x_data, kernel, Xu, meta=None):
+    if meta is not None:          # the node meta's context is being re-pointed: its cached kernel / data / sweep state no longer describes the library
+        meta._theta_key = None; meta._resident_sig = None; meta._swept = False
+        if hasattr(meta, "_kuu_key"):
+            meta._kuu_key = None
     k = kernel(np.asarray(theta, dtype=np.float64))
     var, ell = k[0], k[1]
     kind = k[2] if len(k) > 2 else 0
@@ -34,25 +38,32 @@ def _load(ctx, theta, y_data, x_data, kernel, Xu):
     return Z.shape[1]
 
 
-def neg_log_backwardmess_fast(theta, *, y_data, x_data, v, Uv, w, kernel, Xu, ctx=None, jitter=0.0):
-    """derivative_helper.jl:23-39 -- the value of the collapsed objective."""
+def neg_log_backwardmess_fast(theta, *, y_data, x_data, v, Uv, w, kernel, Xu, ctx=None, jitter=0.0, meta=None):
+    """derivative_helper.jl:23-39 -- the value of the collapsed objective.  `meta`: a node meta whose context is used (and whose cached
+    state is invalidated, because this call re-points the context's kernel and data)."""
+    if meta is not None and ctx is None:
+        from .nodes import _ctx
+        ctx = _ctx(meta)
     own = ctx is None
     ctx = SGPContext(0) if own else ctx
     try:
-        _load(ctx, theta, y_data, x_data, kernel, Xu)
+        _load(ctx, theta, y_data, x_data, kernel, Xu, meta)
         return ctx.theta_objective(v, Uv, w, jitter, grad=False)
     finally:
         if own:
             ctx.close()
 
 
-def grad_llh_new(grad, theta, *, y_data, x_data, v, Uv, w, kernel, Xu, chunk_size=None, kernel_jac=None, ctx=None, jitter=0.0):
+def grad_llh_new(grad, theta, *, y_data, x_data, v, Uv, w, kernel, Xu, chunk_size=None, kernel_jac=None, ctx=None, jitter=0.0, meta=None):
     """grad_llh_new!(grad, theta; ...) -- derivative_helper.jl:59-63: fills ``grad`` with d(objective)/d(theta) and returns it."""
+    if meta is not None and ctx is None:
+        from .nodes import _ctx
+        ctx = _ctx(meta)
     own = ctx is None
     ctx = SGPContext(0) if own else ctx
     try:
         theta = np.asarray(theta, dtype=np.float64)
-        D = _load(ctx, theta, y_data, x_data, kernel, Xu)
+        D = _load(ctx, theta, y_data, x_data, kernel, Xu, meta)
         _, dvar, dell = ctx.theta_objective(v, Uv, w, jitter, grad=True)
         jv, jl = kernel_jac(theta) if kernel_jac is not None else _softplus_jac(theta, D)
         grad[...] = dvar * np.asarray(jv) + np.asarray(dell) @ np.asarray(jl)

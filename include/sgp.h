@@ -42,7 +42,9 @@ enum { SGP_KERNEL_SE = 0, SGP_KERNEL_MATERN32 = 1, SGP_KERNEL_MATERN52 = 2 };
 
 /* expectation methods for uncertain inputs (ReactiveMP srcubature()/ghcubature(p), helper_functions/ut_approx.jl,
  * closed-form SE-ARD extension) */
-enum { SGP_METHOD_SRCUBATURE = 0, SGP_METHOD_GENUT = 1, SGP_METHOD_GAUSSHERMITE = 2, SGP_METHOD_CLOSED_FORM_SE = 3 };
+enum { SGP_METHOD_SRCUBATURE = 0, SGP_METHOD_GENUT = 1, SGP_METHOD_GAUSSHERMITE = 2, SGP_METHOD_CLOSED_FORM_SE = 3,
+       SGP_METHOD_POINT = 4 /* q(x_n) = PointMass(mean_n): one point of weight 1, `cov` may be NULL -- gives the per-node terms of
+                               sgp_uncertain_node_terms to the `q_in::PointMass` rules that clamp per node (GPnode/UniSGPnode.jl:438-458) */ };
 
 /* ---- lifetime -------------------------------------------------------------------------------------------- */
 int sgp_create(sgp_ctx** ctx, int device_id);
@@ -116,8 +118,10 @@ int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, doub
  *   sgp_prior_set            load a prior (host natural parameters xi0 [M], Lambda0 [M x M])
  *   sgp_prior_set_isotropic  N(0, variance I) without any host traffic
  *   sgp_posterior_v_stream   the N-th prod on the resident prior and the last sweep; carry != 0: the posterior's natural
- *                            parameters become the resident prior.  Outputs may be NULL (nothing is copied back); mu_v / Uv
- *                            of the last posterior stay resident for sgp_w_terms / sgp_theta_objective (pass NULL there). */
+ *                            parameters become the resident prior.  Outputs may be NULL (nothing is copied back); mu_v / Sigma_v
+ *                            of the last posterior stay resident for sgp_w_terms / sgp_theta_objective (pass NULL there).
+ *                            Uv == NULL skips the second Cholesky factorisation (of Sigma_v + mu_v mu_v') altogether: the resident
+ *                            consumers use <R_v, Psi2> = <Sigma_v, Psi2> + mu_v' Psi2 mu_v instead of the factor. */
 int sgp_prior_set(sgp_ctx* ctx, const double* xi0, const double* Lambda0);
 int sgp_prior_set_isotropic(sgp_ctx* ctx, double variance);
 int sgp_posterior_v_stream(sgp_ctx* ctx, double w, int carry, double* mu_v, double* Sigma_v, double* Uv);
@@ -129,6 +133,13 @@ int sgp_w_terms(sgp_ctx* ctx, const double* mu_v, const double* Uv, double* sumI
 /* `@rule UniSGP(:out)` over a test set (GPnode/UniSGPnode.jl:96-104; regression_kin40k.ipynb:289-304): out = K_*u mu_v */
 int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* mu_v, double* out);
 
+/* `predict_new` of the classification drivers (experiments/classification_banana.ipynb:289-305, GPT_classification.ipynb cell 13): the
+ * `@rule UniSGP(:out)` message N(mean_f[n], 1 / w_bar) (GPnode/UniSGPnode.jl:96-104) pushed through ReactiveMP's `@rule Probit(:out)`:
+ *   mean_f[n] = K_*u mu_v,  *var_f = 1 / w_bar (the :out message's variance: the same for every test point),
+ *   prob_y[n] = Phi(mean_f[n] / sqrt(1 + 1 / w_bar))   (mean of the Bernoulli; its variance is p (1 - p)).  var_f may be NULL. */
+int sgp_predict_probit(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* mu_v, double w_bar, double* mean_f, double* var_f,
+                       double* prob_y);
+
 /* ---- the theta step ---------------------------------------------------------- */
 /* Collapsed objective of the hyper-parameter step and its exact gradient on the resident data, at the kernel parameters
  * currently set: replaces `neg_log_backwardmess_fast` + `ForwardDiff.gradient!`
@@ -136,7 +147,9 @@ int sgp_predict_mean(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double* m
  *   F = sum_n [ w/2 k_nn - w/2 |L_u^-1 k_n|^2 + w/2 |Uv k_n|^2 - w y_n mu_v' k_n ],   K_uu = L_u L_u' (+ jitter I)
  * value = F, dvariance = dF/d sigma^2, dlengthscale[D] = dF/d ell_d (analytic; the host applies its own chain rule for the
  * raw parameters, e.g. softplus').  mu_v (M) and Uv (M x M upper, column-major) are inputs (both NULL = resident posterior).  Any output may be NULL; without
- * gradient outputs only the value is computed.  With a communicator attached the D + 2 scalars are summed over ranks. */
+ * gradient outputs only the value is computed.  The statistics of the last sgp_sweep_psi on the same data and kernel are reused (otherwise the sweep
+ * runs first); K_uu is refactored only when the kernel, Z or the jitter changed.  With a communicator attached the call is COLLECTIVE: the
+ * statistics are the rank-summed ones and the rank-local part of the gradient is summed over the ranks. */
 int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const double* Uv, double w, double jitter, double* value,
                         double* dvariance, double* dlengthscale);
 
@@ -178,6 +191,13 @@ int sgp_sweep_timed(sgp_ctx* ctx, int reps, float* ms_per_sweep, float* ms_main_
  * enqueued without a host synchronisation; the flush is outside the timed intervals (one event pair per repetition).  With a
  * communicator attached the ranks stay in lock step through the exchange itself. */
 int sgp_sweep_timed_flushed(sgp_ctx* ctx, int reps, int flush_mb, float* ms_per_sweep, float* ms_main_kernel);
+/* Device time of the M x M entry points on the resident state (CUDA events on the ctx stream around the call's kernels; no host copies):
+ * what = 0: sgp_kuu_factor(jitter), 1: sgp_posterior_v_stream(w, carry = 0) with Uv, 2: the same without Uv, 3: sgp_w_terms(NULL, NULL).
+ * Mean over `reps` calls. */
+int sgp_dense_timed(sgp_ctx* ctx, int what, double w, double jitter, int reps, float* ms_per_call);
+/* FP64 tensor-pipe (DMMA.8x8x4) peak of THIS device in TFLOP/s: a register-only loop of independent accumulator chains, about
+ * `ms_target` milliseconds per pass, best of three.  The denominator of the sweep's roofline fraction (MEASURED_PEAKS.json has no FP64 entry). */
+int sgp_fp64_peak(sgp_ctx* ctx, int ms_target, double* dmma_tflops);
 /* number of kernels the last sweep launched, and the main kernel's launch geometry */
 int sgp_last_sweep_info(sgp_ctx* ctx, int* n_launches, int* grid, int* block, int* smem_bytes);
 /* per-segment clock counters of the fused sweep kernel (load-balance tuning).  The first call switches the

@@ -17,7 +17,7 @@ def build(native=False, out=None):
     native rebuild on the box it times on (falls back to the prebuilt one if gcc is missing there)."""
     out = out or PREBUILT
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    cmd = ["gcc", "-O3", "-fPIC", "-shared", SRC, "-o", out, "-lm"]
+    cmd = ["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", SRC, "-o", out, "-lm"]
     if native:
         cmd.insert(2, "-march=native")
     subprocess.run(cmd, check=True)
@@ -40,6 +40,8 @@ def load(native=False):
     dp = ctypes.POINTER(ctypes.c_double)
     lib.sgp_port_sweep.restype = None
     lib.sgp_port_sweep.argtypes = [ctypes.c_long, ctypes.c_int, ctypes.c_int, dp, dp, dp, ctypes.c_double, dp, ctypes.c_double, dp, dp, dp, dp]
+    lib.sgp_port_sweep_mt.restype = ctypes.c_int
+    lib.sgp_port_sweep_mt.argtypes = lib.sgp_port_sweep.argtypes + [ctypes.c_int]
     lib.sgp_port_flush.restype = ctypes.c_int
     lib.sgp_port_flush.argtypes = [ctypes.c_int, dp, dp, dp, dp, dp]
     _lib = lib
@@ -50,8 +52,9 @@ def _p(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
 
-def sweep(X, y, Z, variance, ell, w, Lambda0=None, xi0=None, native=False):
-    """Reference-schedule sweep over the rows of X; returns (xi, Lambda) = prior + sum of the N per-point messages."""
+def sweep(X, y, Z, variance, ell, w, Lambda0=None, xi0=None, native=False, threads=1):
+    """Reference-schedule sweep over the rows of X; returns (xi, Lambda) = prior + sum of the N per-point messages.
+    threads != 1: the OpenMP variant (0 = all the host's threads); `sweep.last_threads` holds the number actually used."""
     lib = load(native)
     X = np.ascontiguousarray(X, dtype=np.float64); Z = np.ascontiguousarray(Z, dtype=np.float64)
     X = X[:, None] if X.ndim == 1 else X
@@ -62,8 +65,16 @@ def sweep(X, y, Z, variance, ell, w, Lambda0=None, xi0=None, native=False):
     Lam = np.zeros((M, M), order="F") if Lambda0 is None else np.asfortranarray(np.array(Lambda0, dtype=np.float64))
     xi = np.zeros(M) if xi0 is None else np.array(xi0, dtype=np.float64)
     buf = np.empty((M, M), order="F"); k = np.empty(M)
-    lib.sgp_port_sweep(N, D, M, _p(X), _p(y), _p(Z), float(variance), _p(ell), float(w), _p(Lam), _p(xi), _p(buf), _p(k))
+    if threads == 1:
+        lib.sgp_port_sweep(N, D, M, _p(X), _p(y), _p(Z), float(variance), _p(ell), float(w), _p(Lam), _p(xi), _p(buf), _p(k))
+        sweep.last_threads = 1
+    else:
+        sweep.last_threads = lib.sgp_port_sweep_mt(N, D, M, _p(X), _p(y), _p(Z), float(variance), _p(ell), float(w), _p(Lam), _p(xi), _p(buf), _p(k),
+                                                   int(threads))
     return xi, Lam
+
+
+sweep.last_threads = 1
 
 
 def flush(Lambda, xi):

@@ -9,7 +9,7 @@
  *     then prod (GPnode/UniSGPnode.jl:62-63):  (xi, Lambda) += (xi_n, Psi2)  M x M add
  * The flush of the N-th prod (cholinv + Cholesky) is sgp_port_flush.  Single thread, plain loops: this mirrors the
  * arithmetic the Julia code performs without the scheduler / allocation overhead, i.e. it is generous to the reference.
- * Build: gcc -O3 -march=native -fPIC -shared oracle/sweep_port.c -o oracle/_build/libsgp_port.so -lm
+ * Build: gcc -O3 -fopenmp -march=native -fPIC -shared oracle/sweep_port.c -o oracle/_build/libsgp_port.so -lm
  */
 #include <math.h>
 #include <stdlib.h>
@@ -37,6 +37,53 @@ void sgp_port_sweep(long N, int D, int M, const double* X, const double* y, cons
         for (int i = 0; i < M; ++i) xi[i] += k[i] * yw;            /* prod: weighted means add */
         for (long e = 0; e < (long)M * M; ++e) Lambda[e] += psi2buf[e]; /* prod: precisions add */
     }
+}
+
+/* The same schedule with the host's threads where the reference could have them: Julia hands `mul!(Psi2, k, k', w, 0)` to a threaded
+ * BLAS; here the kernel column, the rank-1 update AND the M x M add of `prod` (a single-threaded broadcast in Julia) are split over the
+ * threads -- two barriers per data point.  Bitwise the same result as sgp_port_sweep (every element has one owner, same operation order).
+ * Returns the number of threads used. */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+int sgp_port_sweep_mt(long N, int D, int M, const double* X, const double* y, const double* Z, double variance, const double* ell,
+                      double w, double* Lambda, double* xi, double* psi2buf, double* k, int nthreads) {
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+    {
+#pragma omp single
+        used = omp_get_num_threads();
+        for (long n = 0; n < N; ++n) {
+            const double* x = X + n * D;
+#pragma omp for schedule(static)
+            for (int m = 0; m < M; ++m) {
+                double r2 = 0.0;
+                for (int d = 0; d < D; ++d) {
+                    double t = (x[d] - Z[(long)m * D + d]) / ell[d];
+                    r2 += t * t;
+                }
+                k[m] = variance * exp(-0.5 * r2);
+            }   /* implicit barrier: k complete */
+            const double yw = y[n] * w;
+#pragma omp for schedule(static) nowait
+            for (int j = 0; j < M; ++j) {
+                double wk = w * k[j];
+                double* col = psi2buf + (long)j * M;
+                double* lam = Lambda + (long)j * M;
+                for (int i = 0; i < M; ++i) col[i] = k[i] * wk;          /* mul!(Psi2, k, k', w, 0) */
+                for (int i = 0; i < M; ++i) lam[i] += col[i];            /* prod: precisions add */
+                xi[j] += k[j] * yw;                                      /* prod: weighted means add */
+            }
+#pragma omp barrier
+        }
+    }
+#else
+    (void)nthreads;
+    sgp_port_sweep(N, D, M, X, y, Z, variance, ell, w, Lambda, xi, psi2buf, k);
+#endif
+    return used;
 }
 
 /* In-place lower Cholesky (column-major); returns 0 or the 1-based index of the failing pivot. */

@@ -195,6 +195,21 @@ def average_energy_gaussout_wpoint(mu_y, v_y, x, mu_v, Sigma_v, w_bar, theta, me
     return 0.5 * (I1 * w_bar - np.log(w_bar) + LOG2PI + I2 * w_bar)
 
 
+def average_energy_uncertain_wpoint(mu_y, v_y, q_in, mu_v, Sigma_v, w_bar, theta, meta):
+    """UniSGPnode.jl:390-409 (q_in Gaussian, q_w PointMass): cubature expectations, then ``.+ 1e-8`` on EVERY element of K_uu, Psi1 and
+    Psi2, plain inv, clamps."""
+    var, ell, kind = meta.kernel(theta)
+    Z = np.asarray(meta.Xu, dtype=np.float64)
+    Z = Z[:, None] if Z.ndim == 1 else Z
+    Kuu_inv = np.linalg.inv(kernel_matrix(Z, Z, var, ell, kind) + 1e-8)
+    psi0, psi1, psi2 = kernel_expectations(meta, theta, q_in[0], q_in[1])
+    psi1 = psi1 + 1e-8
+    psi2 = psi2 + 1e-8
+    I1 = np.clip(psi0 - np.trace(Kuu_inv @ psi2), 1e-12, 1e12)
+    I2 = np.clip(mu_y**2 + v_y - 2 * mu_y * (psi1 @ mu_v) + np.trace((Sigma_v + np.outer(mu_v, mu_v)) @ psi2), 1e-12, 1e12)
+    return 0.5 * (I1 * w_bar - np.log(w_bar) + LOG2PI + I2 * w_bar)
+
+
 # ---- the reference's sweep, as scheduled ----------------------------------------------------------------
 def sweep_v_pointmass(X, ybar, w, theta, meta, prior_mean, prior_cov):
     """One ``infer(iterations=1)`` pass of experiments/regression_kin40k.ipynb:147-152,185-192: prior

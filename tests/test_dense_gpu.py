@@ -50,7 +50,8 @@ def test_not_positive_definite_is_an_error(ctx):
     assert e.value.code == -3
 
 
-@pytest.mark.parametrize("N,D,M,w", [(50, 1, 20, 25.0), (2000, 2, 64, 3.0), (5000, 8, 256, 100.0), (10000, 8, 512, 1.0e4)])
+@pytest.mark.parametrize("N,D,M,w", [(50, 1, 20, 25.0), (300, 2, 33, 10.0), (2000, 2, 64, 3.0), (3000, 3, 100, 30.0), (5000, 8, 256, 100.0),
+                                     (10000, 8, 512, 1.0e4), (6000, 8, 600, 1.0e3), (4000, 8, 1000, 50.0)])
 def test_posterior_and_w_terms(ctx, N, D, M, w):
     rng = np.random.default_rng(N + M)
     X = rng.normal(size=(N, D)); y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=N)
@@ -89,6 +90,46 @@ def test_posterior_and_w_terms(ctx, N, D, M, w):
     assert abs(F_g - F_o) <= 1e-8 * abs(F_o) + (a / b) * tol1, (F_g, F_o)   # + the conditioning-limited part of sumI1
 
 
+@pytest.mark.parametrize("M", [48, 200, 512])
+def test_posterior_without_uv_feeds_the_resident_consumers(ctx, M):
+    # Uv == NULL skips the second Cholesky factorisation; the resident consumers use <R_v, Psi2> = <Sigma_v, Psi2> + mu_v' Psi2 mu_v
+    rng = np.random.default_rng(M)
+    N, D, w = 3000, 4, 40.0
+    X = rng.normal(size=(N, D)); y = np.cos(X[:, 1]) + 0.1 * rng.normal(size=N)
+    Z = X[rng.choice(N, M, replace=False)]
+    ctx.set_kernel(0.9, np.full(D, 1.4)); ctx.set_inducing(Z); ctx.set_data(X, y)
+    ctx.sweep_psi(fetch=False)
+    ctx.kuu_factor(1e-6, fetch=False)
+    ctx.prior_set_isotropic(50.0)
+    mu, Sig, Uv = ctx.posterior_v_stream(w, carry=False, fetch=True)
+    ref_w = ctx.w_terms(mu, Uv); ref_t = ctx.theta_objective(mu, Uv, w, 1e-6)
+    mu2, Sig2, none = ctx.posterior_v_stream(w, carry=False, fetch=True, want_Uv=False)
+    assert none is None and np.array_equal(mu, mu2) and np.array_equal(Sig, Sig2)
+    got_w = ctx.w_terms(None, None); got_t = ctx.theta_objective(None, None, w, 1e-6)
+    assert abs(got_w[0] - ref_w[0]) <= 1e-12 * abs(ref_w[0]) and abs(got_w[1] - ref_w[1]) <= 1e-10 * abs(ref_w[1])
+    assert abs(got_t[0] - ref_t[0]) <= 1e-10 * abs(ref_t[0]) and abs(got_t[1] - ref_t[1]) <= 1e-9 * abs(ref_t[1])
+    assert np.linalg.norm(got_t[2] - ref_t[2]) <= 1e-9 * np.linalg.norm(ref_t[2])
+
+
+def test_theta_objective_leaves_the_resident_statistics_intact(ctx):
+    # the theta step reuses (or re-creates) the statistics of the resident data: a following sgp_w_terms sees the same numbers
+    rng = np.random.default_rng(77)
+    N, D, M, w = 2000, 3, 96, 25.0
+    X = rng.normal(size=(N, D)); y = np.sin(X[:, 0]); yv = rng.uniform(0.0, 0.3, N)
+    Z = X[:M].copy()
+    ctx.set_kernel(1.1, np.full(D, 1.2)); ctx.set_inducing(Z); ctx.set_data(X, y, yv)
+    p0, p1, p2, sy = ctx.sweep_psi()
+    ctx.kuu_factor(1e-6, fetch=False); ctx.prior_set_isotropic(10.0)
+    mu, Sig, Uv = ctx.posterior_v_stream(w, carry=False, fetch=True)
+    before = ctx.w_terms(mu, Uv)
+    ctx.theta_objective(mu, Uv, w, 1e-6)
+    assert ctx.w_terms(mu, Uv) == before            # same bits: sum_y2 still carries Var[y], nothing was re-swept
+    ctx.set_targets(y, yv)                          # invalidates the statistics: the theta step sweeps again, WITH the variances
+    ctx.theta_objective(mu, Uv, w, 1e-6)
+    after = ctx.w_terms(mu, Uv)
+    assert after == before
+
+
 def test_kin40k_golden_chain_on_gpu(ctx, kin40k):
     """K_*u mu_v over the 30000 test points with the reference's saved posterior reproduces the notebook's SMSE."""
     sp = kernels.softplus(kin40k["theta_raw"])
@@ -106,6 +147,13 @@ def test_banana_golden_chain_on_gpu(ctx, banana):
     m = ctx.predict_mean(x[4000:5300], banana["mu_v"])
     yt = (banana["label"][4000:5300] > 0).astype(float)
     assert int(np.sum(np.abs((m > 0).astype(float) - yt))) == 125
+    # the notebook's own prediction path (classification_banana.ipynb:289-317): Probit(:out) of the :out message, decision at p >= 0.5
+    from scipy.stats import norm
+    w_bar = 3.7
+    mf, var_f, prob = ctx.predict_probit(x[4000:5300], banana["mu_v"], w_bar)
+    assert np.array_equal(mf, m) and var_f == 1.0 / w_bar
+    assert np.max(np.abs(prob - norm.cdf(m / np.sqrt(1.0 + 1.0 / w_bar)))) < 1e-14
+    assert int(np.sum(np.abs((prob >= 0.5).astype(float) - yt))) == 125
 
 
 def test_streaming_prior_equals_one_full_sweep(ctx, kin40k):

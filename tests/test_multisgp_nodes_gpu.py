@@ -113,6 +113,13 @@ def test_unisgp_uncertain_v_rule_matches_per_node_fold():
         msg = nd.rule_v_uncertain(nd.PointMass(y[n]), nd.NormalMeanVariance(m[n], v[n]), nd.PointMass(w), nd.PointMass(theta), meta)
         marginal = nd.prod_uncertain(marginal, msg)
     assert fro(marginal.xi, left[0]) < 1e-10 and fro(marginal.Lam, left[1]) < 1e-10
+    # the N-th fold is the reference's `prod` (UniSGPnode.jl:62-73): it also delivers mean / covariance and refreshes meta.Uv
+    o_mu, o_Sig = unisgp.mean_cov(*left)
+    mu, Sig = nd.mean_cov(marginal)
+    cond = np.linalg.cond(left[1])
+    assert fro(mu, o_mu) < max(1e-9, 50 * cond * 2.2e-16) and fro(Sig, o_Sig) < max(1e-9, 50 * cond * 2.2e-16)
+    assert meta.Uv is not None and fro(meta.Uv.T @ meta.Uv, Sig + np.outer(mu, mu)) < 1e-12 and np.allclose(np.tril(meta.Uv, -1), 0.0)
+    assert fro(meta.Uv, ometa.Uv) < max(1e-8, 50 * cond * 2.2e-16)
 
 
 @pytest.mark.parametrize("method", [(cub.GAUSSHERMITE, 21), (cub.SRCUBATURE, 0), (cub.GENUT, 0)])
