@@ -430,6 +430,7 @@ def main():
                 ctx.set_kernel(1.0, elld); ctx.set_inducing(Zd); ctx.set_data(Xd_, yd_)
                 p0, p1, p2, sy = ctx.sweep_psi()
                 ctx.prior_set_isotropic(50.0)
+                ctx.kuu_factor(1e-8, fetch=False); ctx.posterior_v_stream(w, carry=False, fetch=True); ctx.w_terms(None, None)   # warm-up: allocations at this M
                 t_kuu = ctx.dense_timed(0, jitter=1e-8); t_pu = ctx.dense_timed(1, w=w); t_p = ctx.dense_timed(2, w=w); t_w = ctx.dense_timed(3)
                 Lp = pinned_empty((Md, Md), order="F"); Lp[...] = np.eye(Md) / 50.0
                 outp = (pinned_empty((Md,)), pinned_empty((Md, Md), order="F"), pinned_empty((Md, Md), order="F"))

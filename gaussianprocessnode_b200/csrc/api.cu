@@ -52,6 +52,14 @@ int check(sgp_ctx* ctx) { return ctx ? SGP_OK : SGP_ERR_ARG; }
 
 }  // namespace
 
+// like sgp_ensure, zero-filled when (re)allocated: the Cholesky writes only the lower triangle of the diagonal-block inverses
+int sgp_ensure_zero(sgp_ctx* ctx, double** p, size_t* cap, size_t need) {
+    if (*cap >= need && *p) return SGP_OK;
+    int rc = sgp_ensure(ctx, p, cap, need); if (rc) return rc;
+    SGP_CUDA(ctx, cudaMemsetAsync(*p, 0, need * sizeof(double), ctx->stream));
+    return SGP_OK;
+}
+
 int sgp_ensure(sgp_ctx* ctx, double** p, size_t* cap, size_t need) {
     if (*cap >= need && *p) return SGP_OK;
     if (*p) SGP_CUDA(ctx, cudaFree(*p));
@@ -412,7 +420,7 @@ int sgp_kuu_factor(sgp_ctx* ctx, double jitter, double* L) {
     // ONE cooperative launch: K_uu = kernelmatrix(Xu) + jitter I -> L (and the inverses of its diagonal blocks, which sgp_kuu_solve uses)
     // -> X = L^-1 -> K_uu^-1 = X' X, which the :w rule / energy / theta step contract with Psi2
     const size_t nd = (size_t)((M + 63) / 64) * 64 * 64, MM = (size_t)M * M;
-    int rc = sgp_ensure(ctx, &ctx->kuu_dinv_dev, &ctx->kuu_dinv_cap, nd); if (rc) return rc;
+    int rc = sgp_ensure_zero(ctx, &ctx->kuu_dinv_dev, &ctx->kuu_dinv_cap, nd); if (rc) return rc;
     double* d = ctx->dense_dev + 64;
     SgpDenseJob j;
     j.M = M; j.build = 2; j.jitter = jitter; j.A = ctx->KuuL_dev; j.Dinv = ctx->kuu_dinv_dev; j.X = d; j.Tmp = d + MM; j.S = ctx->Kinv_dev;
@@ -471,7 +479,7 @@ static int posterior_core(sgp_ctx* ctx, double w, bool carry, bool want_uv, doub
     double* d = ctx->dense_dev + 64;
     double *Lam = d, *X = d + MM, *T = d + 3 * MM, *xi = d + 4 * MM;
     double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM;
-    int rc = sgp_ensure(ctx, &ctx->dinv_dev, &ctx->dinv_cap, (size_t)((M + 63) / 64) * 64 * 64); if (rc) return rc;
+    int rc = sgp_ensure_zero(ctx, &ctx->dinv_dev, &ctx->dinv_cap, (size_t)((M + 63) / 64) * 64 * 64); if (rc) return rc;
     SgpDenseJob a;
     a.M = M; a.build = 1; a.S2 = psi2; a.s1 = psi1; a.P = post_LamP(ctx); a.xip = post_xiP(ctx); a.xi = xi; a.w = w; a.carry = carry ? 1 : 0;
     a.A = Lam; a.Dinv = ctx->dinv_dev; a.X = X; a.Tmp = T; a.S = post_Sig(ctx); a.mu = post_mu(ctx);

@@ -28,18 +28,18 @@ namespace {
 
 constexpr int TB = 64;        // panel width = diagonal block
 constexpr int CT = 256;       // threads per CTA (8 warps)
-constexpr int KC = 32;        // K chunk staged in shared memory
+constexpr int STAGE_A = TB * (32 + 4), STAGE_B = 64 * (TB + 4);          // staging of the largest tile configurations (Tile::LDA/LDB)
 constexpr int LDT = TB + 4;   // leading dimension of the 64 x 64 shared-memory blocks (= 4 mod 16: conflict-free DMMA fragment loads)
-constexpr int STAGE_A = TB * (KC + 4), STAGE_B = KC * (TB + 4);
-constexpr int SMEM_DOUBLES = 2 * TB * LDT + TB + STAGE_A + STAGE_B;     // T | Xi | rdiag | As | Bs
+constexpr int SMEM_DOUBLES = 2 * TB * LDT + TB + 2 + STAGE_A + STAGE_B;     // T | Xi | rdiag | progress word | As | Bs
 
 // ---- tile GEMM task: acc (+)= sum_{k < K} A(r, k) B(k, c) for a TR x TC tile, 8 warps arranged WR x (8 / WR) ------------------------
-template <int TR, int TC, int WR>
+template <int TR, int TC, int WR, int KCH>     // KCH = K chunk staged in shared memory per barrier pair
 struct Tile {
-    static constexpr int WC = 8 / WR, WTR = TR / WR, WTC = TC / WC, MI = WTR / 8, NJ = WTC / 8;
+    static constexpr int WC = 8 / WR, WTR = TR / WR, WTC = TC / WC, MI = WTR / 8, NJ = WTC / 8, KC = KCH;
     static constexpr int LDA = KC + 4, LDB = TC + 4;              // both = 4 (mod 16)
     static constexpr int AP = TR * KC / CT, BP = KC * TC / CT;   // staged elements per thread
     static_assert(WTR % 8 == 0 && WTC % 8 == 0 && AP >= 1 && BP >= 1, "tile shape");
+    static_assert(TR * LDA <= STAGE_A && KC * LDB <= STAGE_B, "staging area");
     struct Acc { double v[MI][NJ][2]; };
 };
 
@@ -51,28 +51,47 @@ __device__ __forceinline__ void acc_zero(typename TL::Acc& a) {
         for (int j = 0; j < TL::NJ; ++j) a.v[i][j][0] = a.v[i][j][1] = 0.0;
 }
 
+__device__ __forceinline__ double lds_f64(unsigned addr) {     // shared-memory load that keeps its place among the other ordered asm statements
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // A(r, k) = A[r * a_rs + k * a_ks] (r < rows), B(k, c) = B[k * b_ks + c * b_cs] (c < cols); out-of-range elements read as zero.
+// Staging map: a thread owns an (8 fast x 4 slow)-interleaved element so that both the global loads (64-byte runs along the fast
+// index) and the shared-memory stores (two-way bank conflicts at most, for either orientation) are efficient.
 // Global loads of chunk k+1 are in flight while chunk k is multiplied.  All 256 threads must call it.
 template <class TL>
 __device__ __forceinline__ void gemm_task(typename TL::Acc& acc, const double* __restrict__ A, size_t a_rs, size_t a_ks, int rows,
                                           const double* __restrict__ B, size_t b_ks, size_t b_cs, int cols, int K, double* __restrict__ As,
-                                          double* __restrict__ Bs) {
-    constexpr int TR = TL::WTR * (8 / TL::WC), TC = TL::WTC * TL::WC;
+                                          double* __restrict__ Bs, long long* __restrict__ tk = nullptr) {
+    constexpr int TR = TL::WTR * (8 / TL::WC), TC = TL::WTC * TL::WC, KC = TL::KC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp / TL::WC, wc = warp % TL::WC;
     double ra[TL::AP], rb[TL::BP];
     const bool a_rowfast = a_rs == 1, b_colfast = b_cs == 1;
+    // element e of the TR x KC (KC x TC) chunk -> (r, kk): 8 consecutive threads run along the operand's contiguous index, the next 4 along the other
+    auto dec_a = [&](int e, int& r, int& kk) {
+        const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
+        if (a_rowfast) { r = lo + 8 * (rest % (TR / 8)); kk = mid + 4 * (rest / (TR / 8)); }
+        else { kk = lo + 8 * (rest % (KC / 8)); r = mid + 4 * (rest / (KC / 8)); }
+    };
+    auto dec_b = [&](int e, int& c, int& kk) {
+        const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
+        if (b_colfast) { c = lo + 8 * (rest % (TC / 8)); kk = mid + 4 * (rest / (TC / 8)); }
+        else { kk = lo + 8 * (rest % (KC / 8)); c = mid + 4 * (rest / (KC / 8)); }
+    };
     auto gload = [&](int k0) {
 #pragma unroll
         for (int q = 0; q < TL::AP; ++q) {
             const int e = tid + q * CT;
-            const int r = a_rowfast ? e % TR : e / KC, kk = a_rowfast ? e / TR : e % KC;
+            int r, kk; dec_a(e, r, kk);
             ra[q] = (r < rows && k0 + kk < K) ? A[(size_t)r * a_rs + (size_t)(k0 + kk) * a_ks] : 0.0;
         }
 #pragma unroll
         for (int q = 0; q < TL::BP; ++q) {
             const int e = tid + q * CT;
-            const int c = b_colfast ? e % TC : e / KC, kk = b_colfast ? e / TC : e % KC;
+            int c, kk; dec_b(e, c, kk);
             rb[q] = (c < cols && k0 + kk < K) ? B[(size_t)(k0 + kk) * b_ks + (size_t)c * b_cs] : 0.0;
         }
     };
@@ -80,35 +99,86 @@ __device__ __forceinline__ void gemm_task(typename TL::Acc& acc, const double* _
 #pragma unroll
         for (int q = 0; q < TL::AP; ++q) {
             const int e = tid + q * CT;
-            const int r = a_rowfast ? e % TR : e / KC, kk = a_rowfast ? e / TR : e % KC;
+            int r, kk; dec_a(e, r, kk);
             As[r * TL::LDA + kk] = ra[q];
         }
 #pragma unroll
         for (int q = 0; q < TL::BP; ++q) {
             const int e = tid + q * CT;
-            const int c = b_colfast ? e % TC : e / KC, kk = b_colfast ? e / TC : e % KC;
+            int c, kk; dec_b(e, c, kk);
             Bs[kk * TL::LDB + c] = rb[q];
         }
     };
+    typename TL::Acc part[4];                              // (small warp tiles only)
+    if constexpr (TL::MI * TL::NJ <= 2) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc_zero<TL>(part[q]);
+    }
+    long long q0 = 0, q1;
+    if (tk) q0 = clock64();
+#define TCLK(i) do { if (tk) { q1 = clock64(); tk[i] += q1 - q0; q0 = q1; } } while (0)      /* tk: thread-local counters */
     gload(0);
     for (int k0 = 0; k0 < K; k0 += KC) {
         __syncthreads();                       // the previous chunk's fragments have been read
+        TCLK(0);                               // (tuning aid) barrier wait
         sstore();
         __syncthreads();
+        TCLK(1);                               // global-load wait + staging stores
         if (k0 + KC < K) gload(k0 + KC);
+        if constexpr (TL::MI * TL::NJ <= 2) {
+            // Small warp tiles are shared-memory bound (384 B of fragments per DMMA): groups of four k-steps, the loads of group g + 1 issued
+            // (ordered asm) before the DMMAs of group g, so that the warps' load and DMMA phases overlap instead of alternating in lock step.
+            constexpr int NG = KC / 16;
+            double fa[2][4][TL::MI], fb[2][4][TL::NJ];
+            const unsigned a0 = (unsigned)__cvta_generic_to_shared(As + (wr * TL::WTR + (lane >> 2)) * TL::LDA + (lane & 3));
+            const unsigned b0 = (unsigned)__cvta_generic_to_shared(Bs + (lane & 3) * TL::LDB + wc * TL::WTC + (lane >> 2));
+            auto lgroup = [&](int g, int buf) {
 #pragma unroll
-        for (int ks = 0; ks < KC / 4; ++ks) {
-            double a[TL::MI], b[TL::NJ];
+                for (int q = 0; q < 4; ++q) {
+                    const int ks = 4 * g + q;
 #pragma unroll
-            for (int i = 0; i < TL::MI; ++i) a[i] = As[(wr * TL::WTR + 8 * i + (lane >> 2)) * TL::LDA + ks * 4 + (lane & 3)];
+                    for (int i = 0; i < TL::MI; ++i) fa[buf][q][i] = lds_f64(a0 + 8u * (unsigned)(8 * i * TL::LDA + ks * 4));
 #pragma unroll
-            for (int j = 0; j < TL::NJ; ++j) b[j] = Bs[(ks * 4 + (lane & 3)) * TL::LDB + wc * TL::WTC + 8 * j + (lane >> 2)];
+                    for (int j = 0; j < TL::NJ; ++j) fb[buf][q][j] = lds_f64(b0 + 8u * (unsigned)(ks * 4 * TL::LDB + 8 * j));
+                }
+            };
+            lgroup(0, 0);
 #pragma unroll
-            for (int i = 0; i < TL::MI; ++i)
+            for (int g = 0; g < NG; ++g) {
+                if (g + 1 < NG) lgroup(g + 1, (g + 1) & 1);
+                // (four accumulator sets, k-steps mod 4: a dependent DMMA waits long when eight warps share the pipe)
 #pragma unroll
-                for (int j = 0; j < TL::NJ; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int i = 0; i < TL::MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < TL::NJ; ++j) dmma884(part[q].v[i][j][0], part[q].v[i][j][1], fa[g & 1][q][i], fb[g & 1][q][j]);
+            }
+        } else {
+#pragma unroll
+            for (int ks = 0; ks < KC / 4; ++ks) {
+                double a[TL::MI], b[TL::NJ];
+#pragma unroll
+                for (int i = 0; i < TL::MI; ++i) a[i] = As[(wr * TL::WTR + 8 * i + (lane >> 2)) * TL::LDA + ks * 4 + (lane & 3)];
+#pragma unroll
+                for (int j = 0; j < TL::NJ; ++j) b[j] = Bs[(ks * 4 + (lane & 3)) * TL::LDB + wc * TL::WTC + 8 * j + (lane >> 2)];
+#pragma unroll
+                for (int i = 0; i < TL::MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < TL::NJ; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+            }
         }
+        TCLK(2);                               // fragment loads + DMMA
     }
+    if constexpr (TL::MI * TL::NJ <= 2) {
+#pragma unroll
+        for (int i = 0; i < TL::MI; ++i)
+#pragma unroll
+            for (int j = 0; j < TL::NJ; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) acc.v[i][j][h] += (part[0].v[i][j][h] + part[1].v[i][j][h]) + (part[2].v[i][j][h] + part[3].v[i][j][h]);
+    }
+#undef TCLK
 }
 
 // C(r, c) = alpha acc + beta C(r, c), r < rows, c < cols; C column-major (ldc).  lower_only: only elements with grow0 + r >= gcol0 + c.
@@ -135,55 +205,149 @@ __device__ __forceinline__ void store_task(const typename TL::Acc& acc, double* 
             }
 }
 
-using T64 = Tile<64, 64, 4>;      // warp tile 16 x 32
-using T32 = Tile<32, 32, 4>;      // warp tile  8 x 16
-using T16 = Tile<16, 64, 2>;      // row strip: warp tile 8 x 16
+using T64 = Tile<64, 64, 4, 32>;      // warp tile 16 x 32
+using T32 = Tile<32, 32, 4, 64>;      // warp tile  8 x 16: little MMA work per chunk, so a long chunk per barrier pair
+using T16 = Tile<16, 64, 2, 64>;      // row strip: warp tile 8 x 16
 
-// ---- 32 x 32 pieces of the diagonal-block factorisation (shared memory, leading dimension LDT) -------------------------------------
-// In-place lower Cholesky of the 32 x 32 block at T[(off + i) * LDT + off + c] by ONE warp: lane i holds row i in registers; per pivot
-// one shuffle broadcasts the pivot, every lane scales its element, and the multipliers travel by shuffle for the rank-1 update.
+// The 32 x 32 sub-tile task every phase is made of, as ONE non-inlined routine (the kernel's instruction footprint decides its speed: each
+// phase runs its code only a few times per launch).  C = alpha A B + beta C with the masks of store_task.
+struct Task32 {
+    const double* A; size_t a_rs, a_ks; int rows;
+    const double* B; size_t b_ks, b_cs; int cols; int K;
+    double* C; int ldc; double alpha, beta; double* Ct; bool lower_only; int grow0, gcol0;
+    long long* tk;
+};
+__device__ __noinline__ void run_task32(const Task32& t, double* __restrict__ As, double* __restrict__ Bs) {
+    T32::Acc acc; acc_zero<T32>(acc);
+    gemm_task<T32>(acc, t.A, t.a_rs, t.a_ks, t.rows, t.B, t.b_ks, t.b_cs, t.cols, t.K, As, Bs, t.tk);
+    if (t.tk) { t.tk[3] += 1; t.tk[4] += (t.K + T32::KC - 1) / T32::KC; }
+    store_task<T32>(acc, t.C, t.ldc, t.rows, t.cols, t.alpha, t.beta, t.Ct, t.lower_only, t.grow0, t.gcol0);
+}
+
+// ---- the 64 x 64 diagonal block: factor + inverse in shared memory (leading dimension LDT), one CTA ------------------------------------
+// Measured on B200 (tools/lat_microbench.cu, tools/dense_clocks.py): a DFMA chain costs 8.7 clocks per link, rsqrt 66, a double shuffle 30
+// with an issue cost that makes 62 shuffles per pivot ~700 clocks, a shared-memory load ~4 issue clocks (29 latency), a dependent DMMA 26.
+// And: fully unrolled pivot loops (~50 KB of straight-line code per copy) run from instruction-cache misses at ~4 000 clocks per pivot.
+// Hence: ROLLED loops over the pivots, the not-yet-final part of a row / column in registers that ROTATE by one per pivot (all register
+// indices static), finished columns published through a column-major copy `Lc` in shared memory and read back as aligned 16-byte broadcasts
+// (no shuffles), and the next pivot's reciprocal square root issued before the current pivot's column updates.
+// NU = columns updated per pivot: 31 for the first 16 pivots, 15 for the last 16 (736 instead of 496 updates; loop bodies of ~80 / ~45
+// instructions).
+
+// Progress of the pivot loop, published by the factorising warp and polled by the warps that consume the finished columns one pivot behind
+// (forward substitution of the rows below, inverse): release / acquire at CTA scope on a shared-memory word.
+__device__ __forceinline__ void prog_publish(int* prog, int v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(prog)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prog_wait(const int* prog, int above) {      // until *prog > above
+    const unsigned a = (unsigned)__cvta_generic_to_shared(prog);
+    int v;
+    do { asm volatile("ld.acquire.cta.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory"); } while (v <= above);
+}
+
+constexpr int LCS = 64;                                          // stride of Lc: Lc[j * LCS + ((j + 1) & 1) + i] = L[i][j]
+__device__ __forceinline__ int lc_col(int j) { return j * LCS + ((j + 1) & 1); }      // ... so that &Lc[.. + j + 1] is 16-byte aligned
+
+// a[t - 1] = a[t] - l * colp[t - 1], t = 1 .. NU   (colp = &L[j + 1][j] in Lc; entries past row 31 are garbage that lands in dead slots)
+template <int NU>
+__device__ __forceinline__ void rot_update(double (&a)[32], double l, const double* __restrict__ colp) {
+#pragma unroll
+    for (int t = 1; t + 1 <= NU; t += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(colp + (t - 1));
+        a[t - 1] = fma(-l, v.x, a[t]);
+        a[t] = fma(-l, v.y, a[t + 1]);
+    }
+    if (NU & 1) a[NU - 1] = fma(-l, colp[NU - 1], a[NU]);
+}
+
+// 1 / sqrt(d) for a positive normal d, branch-free: MUFU.RSQ64H seed (2^-22) and one third-order correction -- 6 instructions that ptxas can
+// interleave with the column updates (the library rsqrt carries a slow-path branch that splits the basic block).
+__device__ __forceinline__ double rsqrt_pos(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);                      // 1 - d y^2
+    const double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);                               // y (1 + e / 2 + 3 e^2 / 8)
+}
+
+template <int NU>
+__device__ __forceinline__ void chol_pivot(double (&a)[32], double& dg, double& d, double& r, int& bad, int j, int lane, double* __restrict__ row,
+                                           double* __restrict__ Lc, double* __restrict__ rdiag_off, int* __restrict__ prog) {
+    double l = a[0] * r;
+    if (lane == j) { l = d * r; rdiag_off[j] = r; }
+    dg = fma(-l, l, dg);                                   // this lane's own diagonal element (meaningful for lanes > j)
+    double dn = __shfl_sync(0xffffffffu, dg, (j + 1) & 31);       // the next pivot
+    row[j] = (lane >= j) ? l : 0.0;                       // column j of L is final (in place in T)
+    const int cj = lc_col(j);
+    Lc[cj + lane] = l;
+    __syncwarp();
+    if (lane == 0) prog_publish(prog, j + 1);             // column j (and 1 / L_jj) are out: the lagging warps may use them
+    // one basic block from here: the next pivot's scale (a chain of ~60 clocks) is interleaved with the column updates
+    const bool neg = !(dn > 0.0) && j < 31;
+    bad = (neg && bad < 0) ? j + 1 : bad;                  // first non-positive pivot (recorded once, after the loop)
+    dn = neg ? 1.0 : dn;
+    const double rn = rsqrt_pos(dn);
+    rot_update<NU>(a, l, Lc + cj + j + 1);
+    d = dn; r = rn;
+}
+// In-place lower Cholesky of the 32 x 32 block of T at `off` by ONE warp (lane = row); Lc receives the factor column by column,
 // rdiag[off + j] = 1 / L_jj.  A non-positive pivot is recorded (rows below `nvalid` only) and replaced by 1.
-__device__ __forceinline__ void chol32_warp(double* __restrict__ T, int off, double* __restrict__ rdiag, int* __restrict__ info, int row0, int nvalid) {
+__device__ __noinline__ void chol32_warp(double* __restrict__ T, int off, double* __restrict__ Lc, double* __restrict__ rdiag, int* __restrict__ info,
+                                         int row0, int nvalid, int* __restrict__ prog) {
     const int lane = threadIdx.x & 31;
     double a[32];
     double* row = T + (off + lane) * LDT + off;
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = row[c];
-    double rmine = 1.0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0)) { if (lane == 0 && off + j < nvalid) atomicCAS(info, 0, row0 + off + j + 1); d = 1.0; }
-        const double r = rsqrt(d);
-        double l = a[j] * r;
-        if (lane == j) { l = d * r; rmine = r; }
-        a[j] = l;
-#pragma unroll
-        for (int t = j + 1; t < 32; ++t) {
-            const double v = __shfl_sync(0xffffffffu, l, t);      // L[t][j]
-            a[t] = fma(-l, v, a[t]);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 32; ++c) row[c] = (c <= lane) ? a[c] : 0.0;
-    rdiag[off + lane] = rmine;
+    double dg = row[lane];
+    double d = __shfl_sync(0xffffffffu, dg, 0);
+    int bad = -1;
+    if (!(d > 0.0)) { bad = 0; d = 1.0; }
+    double r = rsqrt_pos(d);
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) chol_pivot<31>(a, dg, d, r, bad, j, lane, row, Lc, rdiag + off, prog);
+#pragma unroll 1
+    for (int j = 16; j < 32; ++j) chol_pivot<15>(a, dg, d, r, bad, j, lane, row, Lc, rdiag + off, prog);
+    if (lane == 0 && bad >= 0 && off + bad < nvalid) atomicCAS(info, 0, row0 + off + bad + 1);
 }
 
-// Xi block = inverse of the lower-triangular 32 x 32 block of T at `off`, by ONE warp: lane c solves L x = e_c (right-looking, the
-// elements of L are broadcast reads).
-__device__ __forceinline__ void inv32_warp(const double* __restrict__ T, int off, const double* __restrict__ rdiag, double* __restrict__ Xi) {
+// Rows 32..63 of the panel: L21 = A21 L11^-T by ONE warp (lane = row; forward substitution with the rotating registers), in place in T.
+__device__ __noinline__ void trsm32_rows_warp(double* __restrict__ T, const double* __restrict__ Lc, const double* __restrict__ rdiag,
+                                              const int* __restrict__ prog) {
+    const int lane = threadIdx.x & 31;
+    double a[32];
+    double* row = T + (32 + lane) * LDT;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = row[c];
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) { prog_wait(prog, j); const double l = a[0] * rdiag[j]; row[j] = l; rot_update<31>(a, l, Lc + lc_col(j) + j + 1); }
+#pragma unroll 1
+    for (int j = 16; j < 32; ++j) { prog_wait(prog, j); const double l = a[0] * rdiag[j]; row[j] = l; rot_update<15>(a, l, Lc + lc_col(j) + j + 1); }
+}
+
+// Xi block at `off` = inverse of the lower-triangular 32 x 32 block whose columns are in Lc, by ONE warp: lane c solves L x = e_c.
+__device__ __noinline__ void inv32_warp(const double* __restrict__ Lc, int off, const double* __restrict__ rdiag, double* __restrict__ Xi,
+                                        const int* __restrict__ prog) {
     const int lane = threadIdx.x & 31;
     double x[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int l = 0; l < 32; ++l) {
-        x[l] *= rdiag[off + l];
-#pragma unroll
-        for (int i = l + 1; i < 32; ++i) x[i] = fma(-T[(off + i) * LDT + off + l], x[l], x[i]);
+    double* Xb = Xi + off * LDT + off;
+#pragma unroll 1
+    for (int l = 0; l < 16; ++l) {
+        prog_wait(prog, l);
+        const double xl = x[0] * rdiag[off + l];
+        Xb[l * LDT + lane] = (l >= lane) ? xl : 0.0;      // row l of the inverse is final
+        rot_update<31>(x, xl, Lc + lc_col(l) + l + 1);
     }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) Xi[(off + i) * LDT + off + lane] = (i >= lane) ? x[i] : 0.0;
+#pragma unroll 1
+    for (int l = 16; l < 32; ++l) {
+        prog_wait(prog, l);
+        const double xl = x[0] * rdiag[off + l];
+        Xb[l * LDT + lane] = (l >= lane) ? xl : 0.0;
+        rot_update<15>(x, xl, Lc + lc_col(l) + l + 1);
+    }
 }
 
 // 32 x 32 x 32 product on shared-memory operands by all 8 warps (warp tile 8 x 16): returns the warp's fragment of
@@ -192,18 +356,25 @@ struct Frag32 { double v[2][2]; };
 __device__ __forceinline__ Frag32 smem_mma32(const double* __restrict__ A, int a_rs, int a_ks, const double* __restrict__ B, int b_ks, int b_cs) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wr = warp >> 1, wc = warp & 1;
-    Frag32 f;
-    f.v[0][0] = f.v[0][1] = f.v[1][0] = f.v[1][1] = 0.0;
+    Frag32 f, g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q].v[0][0] = g[q].v[0][1] = g[q].v[1][0] = g[q].v[1][1] = 0.0;
+    double a[8], b[8][2];
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
         const int k = ks * 4 + (lane & 3);
-        const double a = A[(wr * 8 + (lane >> 2)) * a_rs + k * a_ks];
+        a[ks] = A[(wr * 8 + (lane >> 2)) * a_rs + k * a_ks];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const double b = B[k * b_ks + (wc * 16 + 8 * j + (lane >> 2)) * b_cs];
-            dmma884(f.v[j][0], f.v[j][1], a, b);
-        }
+        for (int j = 0; j < 2; ++j) b[ks][j] = B[k * b_ks + (wc * 16 + 8 * j + (lane >> 2)) * b_cs];
     }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)           // four accumulator sets: a dependent DMMA waits ~140 clocks when eight warps share the pipe
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma884(g[ks & 3].v[j][0], g[ks & 3].v[j][1], a[ks], b[ks][j]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) f.v[j][h] = (g[0].v[j][h] + g[1].v[j][h]) + (g[2].v[j][h] + g[3].v[j][h]);
     return f;
 }
 // C(r, c) = alpha f + beta C(r, c) for the warp's fragment; C[r * LDT + c]
@@ -220,55 +391,73 @@ __device__ __forceinline__ void smem_store32(const Frag32& f, double* __restrict
 }
 
 // Factor the nb x nb diagonal block held in T (lower part valid, identity-padded beyond nb, zeros above the diagonal), write L to A
-// (global, lower part) and its inverse to Dinv (64 x 64 column-major, identity-padded).  One CTA, all 256 threads.
-__device__ void factor_diag_smem(double* __restrict__ T, double* __restrict__ Xi, double* __restrict__ rdiag, double* __restrict__ A, int lda, int nb,
-                                 int row0, double* __restrict__ Dinv, int* __restrict__ info) {
+// (global, lower part) and its inverse to Dinv (64 x 64 column-major; only the lower triangle is written).  One CTA, all 256 threads.
+//   warp 0: Cholesky of the leading 32 x 32 block; one pivot behind it warp 1: L21 = A21 L11^-T (forward substitution), warp 2: X11 = L11^-1
+//   all: A22 -= L21 L21', W = L21 X11 (DMMA)  |  warp 0: Cholesky of A22, warp 1 one pivot behind: X22  |  all: X21 = -X22 W
+__device__ __noinline__ void factor_diag_smem(double* __restrict__ T, double* __restrict__ Xi, double* __restrict__ rdiag, double* __restrict__ Lc,
+                                              double* __restrict__ A, int lda, int nb, int row0, double* __restrict__ Dinv, int* __restrict__ info,
+                                              long long* __restrict__ st = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5;
     double* T21 = T + 32 * LDT; double* T22 = T + 32 * LDT + 32;
     double* X21 = Xi + 32 * LDT;
+    long long s0 = 0, s1;
+#define FCLK(i) do { if (st) { s1 = clock64(); st[i] += s1 - s0; s0 = s1; } } while (0)
+    int* prog = reinterpret_cast<int*>(rdiag + TB);        // progress word of the pivot loop (behind the 64 reciprocal diagonals)
+    if (tid == 0) *prog = 0;
     __syncthreads();
-    if (warp == 0) { chol32_warp(T, 0, rdiag, info, row0, nb); __syncwarp(); inv32_warp(T, 0, rdiag, Xi); }
+    if (st) s0 = clock64();
+    // leading block: warp 0 factorises; one pivot behind, warp 1 substitutes the rows below (L21) and warp 2 builds the inverse X11
+    if (warp == 0) chol32_warp(T, 0, Lc, rdiag, info, row0, nb, prog);
+    else if (warp == 1) trsm32_rows_warp(T, Lc, rdiag, prog);
+    else if (warp == 2) inv32_warp(Lc, 0, rdiag, Xi, prog);
     __syncthreads();
-    {   // L21 = A21 X11'  (in place: all reads before the writes)
-        const Frag32 f = smem_mma32(T21, LDT, 1, Xi, 1, LDT);
-        __syncthreads();
-        smem_store32(f, T21, 1.0, 0.0);
-    }
-    __syncthreads();
+    FCLK(0);
     {   // A22 -= L21 L21' ;  W = L21 X11 (kept in the X21 slot)
         const Frag32 f = smem_mma32(T21, LDT, 1, T21, 1, LDT);
         const Frag32 g = smem_mma32(T21, LDT, 1, Xi, LDT, 1);
         smem_store32(f, T22, -1.0, 1.0);
         smem_store32(g, X21, 1.0, 0.0);
+        if (tid == 0) *prog = 0;
     }
     __syncthreads();
-    if (warp == 0) { chol32_warp(T, 32, rdiag, info, row0, nb); __syncwarp(); inv32_warp(T, 32, rdiag, Xi); }
+    FCLK(2);
+    // trailing block: warp 0 factorises, warp 1 builds the inverse X22 one pivot behind
+    if (warp == 0) chol32_warp(T, 32, Lc, rdiag, info, row0, nb, prog);
+    else if (warp == 1) inv32_warp(Lc, 32, rdiag, Xi, prog);
     __syncthreads();
-    {   // X21 = -X22 W  (in place)
+    FCLK(0);
+    {   // X21 = -X22 W  (in place: all reads before the writes)
         const Frag32 f = smem_mma32(Xi + 32 * LDT + 32, LDT, 1, X21, LDT, 1);
         __syncthreads();
         smem_store32(f, X21, -1.0, 0.0);
     }
     __syncthreads();
-    for (int e = tid; e < nb * nb; e += CT) {
-        const int r = e % nb, c = e / nb;
-        if (c <= r) A[(size_t)r + (size_t)c * lda] = T[r * LDT + c];
+    FCLK(2);
+    for (int e = tid; e < TB * TB; e += CT) {           // (the strict upper triangle of every Dinv block is zero from its allocation;
+        const int r = e % TB, c = e / TB;               //  the grid barrier that follows publishes the stores)
+        if (c <= r) {
+            if (r < nb) A[(size_t)r + (size_t)c * lda] = T[r * LDT + c];
+            Dinv[(size_t)r + (size_t)c * TB] = Xi[r * LDT + c];
+        }
     }
-    for (int e = tid; e < TB * TB; e += CT) {
-        const int r = e % TB, c = e / TB;
-        Dinv[(size_t)r + (size_t)c * TB] = (c <= r) ? Xi[r * LDT + c] : 0.0;
-    }
-    __threadfence();
     __syncthreads();
+    FCLK(3);
+#undef FCLK
 }
 
-// T <- the nb x nb block at A (lower part), identity-padded to 64 x 64, zeros above the diagonal
+// T <- the nb x nb block at A (lower part), identity-padded to 64 x 64, zeros above the diagonal (all 16 loads of a thread in flight)
 __device__ __forceinline__ void load_diag_smem(double* __restrict__ T, const double* __restrict__ A, int lda, int nb) {
-    for (int e = threadIdx.x; e < TB * TB; e += CT) {
-        const int r = e % TB, c = e / TB;
-        double v = (r == c) ? 1.0 : 0.0;
-        if (r < nb && c < nb) v = (c <= r) ? A[(size_t)r + (size_t)c * lda] : 0.0;
-        T[r * LDT + c] = v;
+    double v[TB * TB / CT];
+#pragma unroll
+    for (int q = 0; q < TB * TB / CT; ++q) {
+        const int e = threadIdx.x + q * CT, r = e % TB, c = e / TB;
+        v[q] = (r == c) ? 1.0 : 0.0;
+        if (r < nb && c < nb) v[q] = (c <= r) ? A[(size_t)r + (size_t)c * lda] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < TB * TB / CT; ++q) {
+        const int e = threadIdx.x + q * CT;
+        T[(e % TB) * LDT + e / TB] = v[q];
     }
 }
 
@@ -284,17 +473,22 @@ struct DenseJob {
     double* X; double* Tmp; double* S;     // optional: X = L^-1 (lower), S = X' X = (L L')^-1 full symmetric; Tmp = M x M scratch
     double* mu;                            // optional (needs S and xi): mu = S xi
     double* Ut;                            // optional: Ut = L' (upper triangular, strict lower part zero)
-    long long* clk;                        // optional: CTA 0's clocks {build, factor, panel, trailing, barriers, inverse, S, tail}
+    long long* clk;                        // optional: CTA 0's clocks {build, factor, panel, trailing, barriers, inverse, S, tail | inside factor: chol32, inv32, 32^3 products, write-out}
 };
 
 __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant__ DenseJob j) {
     extern __shared__ double sm[];
-    double* T = sm; double* Xi = T + TB * LDT; double* rdiag = Xi + TB * LDT; double* As = rdiag + TB; double* Bs = As + STAGE_A;
+    double* T = sm; double* Xi = T + TB * LDT; double* rdiag = Xi + TB * LDT; double* As = rdiag + TB + 2; double* Bs = As + STAGE_A;
+    double* Lc = As;        // the factorisation's column-major scratch (32 x LCS) shares the GEMM staging area: never live together
     cg::grid_group grid = cg::this_grid();
     const int M = j.M, nblk = (M + TB - 1) / TB, ncta = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t MM = (size_t)M * M;
     double* __restrict__ A = j.A;
-    long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
+    long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fc[4] = {0, 0, 0, 0}, t0 = clock64(), t1;
+    long long* fst = (j.clk && threadIdx.x == 0) ? fc : nullptr;
+    long long tkl[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long* tk32 = j.clk ? tkl : nullptr;          // thread 0 of CTA 0 reports {barrier, load+stage, mma, tasks, chunks} of its 32 x 32 tasks
+    long long* tk64 = j.clk ? tkl + 8 : nullptr;      // ... and of its 64 x 64 diagonal-block updates
 #define DCLK(i) do { if (j.clk) { t1 = clock64(); tc[i] += t1 - t0; t0 = t1; } } while (0)
 
     // ---- build -------------------------------------------------------------------------------------------------------------------
@@ -325,13 +519,13 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
     } else if (j.build == 3) {
         for (size_t e = (size_t)cta * CT + tid; e < MM; e += (size_t)ncta * CT) A[e] = fma(j.mu_in[e % M], j.mu_in[e / M], j.Sig[e]);
     }
-    if (j.build) { __threadfence(); grid.sync(); }
+    if (j.build) grid.sync();        // (grid.sync orders every thread's earlier stores: no explicit fence in front of the barriers)
     DCLK(0);
 
     // ---- Cholesky ----------------------------------------------------------------------------------------------------------------
     if (cta == 0) {
         load_diag_smem(T, A, M, min(TB, M));
-        factor_diag_smem(T, Xi, rdiag, A, M, min(TB, M), 0, j.Dinv, j.info);
+        factor_diag_smem(T, Xi, rdiag, Lc, A, M, min(TB, M), 0, j.Dinv, j.info, fst);
     }
     DCLK(1);
     grid.sync();
@@ -349,16 +543,15 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
             gemm_task<T16>(acc, Ar, 1, (size_t)M, rows, Dk, (size_t)TB, 1, TB, TB, As, Bs);      // B(kk, c) = Dk(c, kk)
             store_task<T16>(acc, Ar, M, rows, TB, 1.0, 0.0);
         }
-        __threadfence();
         DCLK(2);
         grid.sync();
         DCLK(4);
         // trailing update A[i, c] -= sum_kk L[i, k0 + kk] L[c, k0 + kk] on the lower triangle of A[R0:, R0:]
         const int nbn = min(TB, M - R0);
         if (cta == 0) {     // next diagonal block: updated straight into shared memory and factorised there
-            T64::Acc acc; acc_zero<T64>(acc);
-            gemm_task<T64>(acc, A + (size_t)R0 + (size_t)k0 * M, 1, (size_t)M, nbn, A + (size_t)R0 + (size_t)k0 * M, (size_t)M, 1, nbn, TB, As, Bs);
             load_diag_smem(T, A + (size_t)R0 * ((size_t)M + 1), M, nbn);
+            T64::Acc acc; acc_zero<T64>(acc);
+            gemm_task<T64>(acc, A + (size_t)R0 + (size_t)k0 * M, 1, (size_t)M, nbn, A + (size_t)R0 + (size_t)k0 * M, (size_t)M, 1, nbn, TB, As, Bs, tk64);
             __syncthreads();
             {
                 const int wr = warp / T64::WC, wc = warp % T64::WC;
@@ -373,7 +566,7 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
                         }
             }
             DCLK(3);
-            factor_diag_smem(T, Xi, rdiag, A + (size_t)R0 * ((size_t)M + 1), M, nbn, R0, j.Dinv + (size_t)(k + 1) * TB * TB, j.info);
+            factor_diag_smem(T, Xi, rdiag, Lc, A + (size_t)R0 * ((size_t)M + 1), M, nbn, R0, j.Dinv + (size_t)(k + 1) * TB * TB, j.info, fst);
             DCLK(1);
         }
         if (cta > 0 || ncta == 1) {
@@ -385,12 +578,11 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
                 while ((a + 1) * (a + 2) / 2 <= tt) ++a;
                 const int b = tt - a * (a + 1) / 2;
                 const int r0 = R0 + 32 * a, c0 = R0 + 32 * b, rows = min(32, M - r0), cols = min(32, M - c0);
-                T32::Acc acc; acc_zero<T32>(acc);
-                gemm_task<T32>(acc, A + (size_t)r0 + (size_t)k0 * M, 1, (size_t)M, rows, A + (size_t)c0 + (size_t)k0 * M, (size_t)M, 1, cols, TB, As, Bs);
-                store_task<T32>(acc, A + (size_t)r0 + (size_t)c0 * M, M, rows, cols, -1.0, 1.0, nullptr, a == b, r0, c0);
+                const Task32 tk{A + (size_t)r0 + (size_t)k0 * M, 1, (size_t)M, rows, A + (size_t)c0 + (size_t)k0 * M, (size_t)M, 1, cols, TB,
+                                A + (size_t)r0 + (size_t)c0 * M, M, -1.0, 1.0, nullptr, a == b, r0, c0, tk32};
+                run_task32(tk, As, Bs);
             }
         }
-        __threadfence();
         DCLK(3);
         grid.sync();
         DCLK(4);
@@ -401,12 +593,15 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
         double* __restrict__ X = j.X;
         for (int b = cta; b < nblk; b += ncta) {
             const int nb = min(TB, M - b * TB);
-            for (int e = tid; e < nb * nb; e += CT) {
-                const int r = e % nb, c = e / nb;
-                X[(size_t)(b * TB + r) + (size_t)(b * TB + c) * M] = j.Dinv[(size_t)b * TB * TB + r + (size_t)c * TB];
+            double v[TB * TB / CT];
+#pragma unroll
+            for (int q = 0; q < TB * TB / CT; ++q) v[q] = j.Dinv[(size_t)b * TB * TB + tid + q * CT];
+#pragma unroll
+            for (int q = 0; q < TB * TB / CT; ++q) {
+                const int e = tid + q * CT, r = e % TB, c = e / TB;
+                if (r < nb && c < nb) X[(size_t)(b * TB + r) + (size_t)(b * TB + c) * M] = v[q];
             }
         }
-        __threadfence();
         grid.sync();
         for (int bs = 1; bs < nblk; bs *= 2) {                      // merge blocks of bs tiles into blocks of 2 bs tiles
             const int npairs = (nblk + 2 * bs - 1) / (2 * bs);
@@ -422,19 +617,17 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
                     for (int q = first; q < nr * ncol; q += ncta) {
                         const int r0 = mid + 32 * (q % nr), c0 = top + 32 * (q / nr);
                         const int rows = min(32, M - r0);
-                        T32::Acc acc; acc_zero<T32>(acc);
-                        if (phase == 0) {
-                            gemm_task<T32>(acc, A + (size_t)r0 + (size_t)c0 * M, 1, (size_t)M, rows, X + (size_t)c0 + (size_t)c0 * M, 1, (size_t)M, 32, mid - c0, As, Bs);
-                            store_task<T32>(acc, j.Tmp + (size_t)r0 + (size_t)c0 * M, M, rows, 32, 1.0, 0.0);
-                        } else {
-                            const int K = min(r0 + 32, M) - mid;
-                            gemm_task<T32>(acc, X + (size_t)r0 + (size_t)mid * M, 1, (size_t)M, rows, j.Tmp + (size_t)mid + (size_t)c0 * M, 1, (size_t)M, 32, K, As, Bs);
-                            store_task<T32>(acc, X + (size_t)r0 + (size_t)c0 * M, M, rows, 32, -1.0, 0.0);
-                        }
+                        Task32 tk;
+                        if (phase == 0)
+                            tk = Task32{A + (size_t)r0 + (size_t)c0 * M, 1, (size_t)M, rows, X + (size_t)c0 + (size_t)c0 * M, 1, (size_t)M, 32, mid - c0,
+                                        j.Tmp + (size_t)r0 + (size_t)c0 * M, M, 1.0, 0.0, nullptr, false, 0, 0, tk32};
+                        else
+                            tk = Task32{X + (size_t)r0 + (size_t)mid * M, 1, (size_t)M, rows, j.Tmp + (size_t)mid + (size_t)c0 * M, 1, (size_t)M, 32,
+                                        min(r0 + 32, M) - mid, X + (size_t)r0 + (size_t)c0 * M, M, -1.0, 0.0, nullptr, false, 0, 0, tk32};
+                        run_task32(tk, As, Bs);
                     }
                     task += nr * ncol;
                 }
-                __threadfence();
                 grid.sync();
             }
         }
@@ -446,12 +639,11 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
                 while ((a + 1) * (a + 2) / 2 <= t) ++a;
                 const int b = t - a * (a + 1) / 2;
                 const int r0 = 32 * a, c0 = 32 * b, rows = min(32, M - r0), cols = min(32, M - c0);
-                T32::Acc acc; acc_zero<T32>(acc);
-                gemm_task<T32>(acc, X + (size_t)r0 + (size_t)r0 * M, (size_t)M, 1, rows, X + (size_t)r0 + (size_t)c0 * M, 1, (size_t)M, cols, M - r0, As, Bs);
-                store_task<T32>(acc, j.S + (size_t)r0 + (size_t)c0 * M, M, rows, cols, 1.0, 0.0, j.S + (size_t)c0 + (size_t)r0 * M, a == b, r0, c0);
+                const Task32 tk{X + (size_t)r0 + (size_t)r0 * M, (size_t)M, 1, rows, X + (size_t)r0 + (size_t)c0 * M, 1, (size_t)M, cols, M - r0,
+                                j.S + (size_t)r0 + (size_t)c0 * M, M, 1.0, 0.0, j.S + (size_t)c0 + (size_t)r0 * M, a == b, r0, c0, tk32};
+                run_task32(tk, As, Bs);
             }
             if (j.mu) {
-                __threadfence();
                 grid.sync();
                 // mu = S xi: a warp per column of the symmetric S (fixed-shape tree: deterministic)
                 for (int i = cta * (CT / 32) + warp; i < M; i += ncta * (CT / 32)) {
@@ -494,8 +686,11 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
             if (e / M > e % M) A[e] = 0.0;
     }
     DCLK(7);
-    if (j.clk && cta == 0 && tid == 0)
+    if (j.clk && cta == 0 && tid == 0) {
         for (int i = 0; i < 8; ++i) j.clk[i] = tc[i];
+        for (int i = 0; i < 4; ++i) j.clk[8 + i] = fc[i];
+        for (int i = 0; i < 8; ++i) { j.clk[12 + i] = tkl[i]; j.clk[20 + i] = tkl[8 + i]; }
+    }
 #undef DCLK
 }
 
@@ -540,7 +735,7 @@ int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in) {
     SGP_CUDA(ctx, cudaFuncSetAttribute(dense_job_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const bool print_clocks = std::getenv("SGP_DENSE_CLOCKS") != nullptr;       // tuning aid: per-phase clocks of CTA 0 on stdout
     long long* clk_dev = nullptr;
-    if (print_clocks && !j.clk) { SGP_CUDA(ctx, cudaMalloc((void**)&clk_dev, 8 * sizeof(long long))); j.clk = clk_dev; }
+    if (print_clocks && !j.clk) { SGP_CUDA(ctx, cudaMalloc((void**)&clk_dev, 28 * sizeof(long long))); SGP_CUDA(ctx, cudaMemsetAsync(clk_dev, 0, 28 * sizeof(long long), ctx->stream)); j.clk = clk_dev; }
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_job_kernel, CT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     int want = std::max(1, n32 * (n32 + 1) / 2);                    // the widest phases: trailing sub-tiles of the first panel, S = X'X
@@ -551,12 +746,14 @@ int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in) {
     SGP_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)dense_job_kernel, dim3(grid), dim3(CT), args, smem, ctx->stream));
     SGP_CUDA(ctx, cudaGetLastError());
     if (clk_dev) {
-        long long c[8];
+        long long c[28];
         SGP_CUDA(ctx, cudaMemcpyAsync(c, clk_dev, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
         SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(clk_dev);
-        printf("dense job M=%d build=%d grid=%d: clocks build %lld | factor %lld | panel %lld | trailing %lld | barriers %lld | inverse %lld | S+mu %lld | tail %lld\n",
-               M, in.build, grid, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+        printf("dense job M=%d build=%d grid=%d: clocks build %lld | factor %lld | panel %lld | trailing %lld | barriers %lld | inverse %lld | S+mu %lld | tail %lld || factor: chol32 %lld | inv32 %lld | products %lld | write-out %lld\n",
+               M, in.build, grid, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10], c[11]);
+        printf("    CTA 0's 32x32 tasks: %lld tasks, %lld chunks: barrier %lld | load+stage %lld | mma %lld ;  64x64 diagonal updates: barrier %lld | load+stage %lld | mma %lld\n",
+               c[15], c[16], c[12], c[13], c[14], c[20], c[21], c[22]);
         fflush(stdout);
     }
     return SGP_OK;
@@ -579,7 +776,7 @@ int sgp_dense_info(sgp_ctx* ctx, const char* what) {
 // ctx->dinv_dev.  Non-positive pivot -> SGP_ERR_NOT_PD.
 int sgp_potrf_lower(sgp_ctx* ctx, double* A, int M) {
     const int nblk = (M + TB - 1) / TB;
-    int rc = sgp_ensure(ctx, &ctx->dinv_dev, &ctx->dinv_cap, (size_t)nblk * TB * TB); if (rc) return rc;
+    int rc = sgp_ensure_zero(ctx, &ctx->dinv_dev, &ctx->dinv_cap, (size_t)nblk * TB * TB); if (rc) return rc;
     SgpDenseJob j{};
     j.M = M; j.A = A; j.Dinv = ctx->dinv_dev; j.reset_info = 1;
     rc = sgp_dense_job(ctx, j); if (rc) return rc;
@@ -592,8 +789,13 @@ int sgp_gemm2(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha,
     Gemm2Args g{A, B, C, m, n, k, lda, ldb, ldc, opA, opB, lower_only, alpha, beta};
     const size_t smem = (size_t)(STAGE_A + STAGE_B) * sizeof(double);
     const int tiles64 = ((m + 63) / 64) * ((n + 63) / 64), tiles32 = ((m + 31) / 32) * ((n + 31) / 32);
-    if (tiles32 <= 2 * ctx->num_sms) gemm2_kernel<T32, 32><<<tiles32, CT, smem, ctx->stream>>>(g);
-    else gemm2_kernel<T64, 64><<<std::min(tiles64, 4 * ctx->num_sms), CT, smem, ctx->stream>>>(g);
+    if (tiles32 <= 2 * ctx->num_sms) {
+        SGP_CUDA(ctx, cudaFuncSetAttribute(gemm2_kernel<T32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm2_kernel<T32, 32><<<tiles32, CT, smem, ctx->stream>>>(g);
+    } else {
+        SGP_CUDA(ctx, cudaFuncSetAttribute(gemm2_kernel<T64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm2_kernel<T64, 64><<<std::min(tiles64, 4 * ctx->num_sms), CT, smem, ctx->stream>>>(g);
+    }
     SGP_CUDA(ctx, cudaGetLastError());
     return SGP_OK;
 }

@@ -111,6 +111,7 @@ struct SgpRange {
 #define SGP_FAIL(ctx, code, msg) do { (ctx)->err = (msg); return (code); } while (0)
 
 int sgp_ensure(sgp_ctx* ctx, double** p, size_t* cap, size_t need_doubles);
+int sgp_ensure_zero(sgp_ctx* ctx, double** p, size_t* cap, size_t need_doubles);      // zero-filled when (re)allocated
 
 // sweep.cu
 int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const double* yv, const double* w, int64_t N,
