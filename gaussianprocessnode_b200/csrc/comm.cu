@@ -63,8 +63,9 @@ void setup_p2p(sgp_ctx* ctx, SgpComm* c) {
     if (const char* e = std::getenv("SGP_COMM_P2P")) if (e[0] == '0') return;
     size_t maxM = 2048;
     if (const char* e = std::getenv("SGP_COMM_P2P_MAXM")) { long v = std::atol(e); if (v >= 1) maxM = (size_t)v; }
-    const size_t cap = maxM * maxM + maxM + 64;
-    const size_t bytes = kFlagBytes + 2 * cap * sizeof(double);
+    // one receive slot per rank: the packed statistics (lower triangle of Psi2 | Psi1 for up to 16 outputs | scalars), 16-byte aligned
+    const size_t cap = (maxM * (maxM + 1) / 2 + 16 * maxM + 64 + 1) & ~(size_t)1;
+    const size_t bytes = kFlagBytes + (size_t)c->nranks * cap * sizeof(double);
     bool ok = cudaMalloc((void**)&c->region, bytes) == cudaSuccess;
     if (ok) ok = cudaMemset(c->region, 0, bytes) == cudaSuccess;
     cudaIpcMemHandle_t mine;
@@ -183,23 +184,8 @@ bool sgp_comm_xchg(sgp_ctx* ctx, size_t need_doubles, SgpXchg* x) {
     if (!c || !c->p2p || need_doubles > c->cap_doubles) return false;
     x->nranks = c->nranks; x->rank = c->rank; x->epoch = ++c->epoch;
     for (int q = 0; q < 8; ++q) x->peers[q] = c->peers[q];
-    x->xin_off = kFlagBytes; x->xout_off = kFlagBytes + c->cap_doubles * sizeof(double);
-    x->count = (long long)need_doubles;
+    x->slot0_off = kFlagBytes; x->slot_bytes = c->cap_doubles * sizeof(double);
     return true;
-}
-
-int sgp_ensure_stats(sgp_ctx* ctx, size_t need) {
-    SgpComm* c = ctx->comm;
-    if (c && c->p2p && need <= c->cap_doubles) {
-        double* ext = reinterpret_cast<double*>(c->region + kFlagBytes + c->cap_doubles * sizeof(double));
-        if (ctx->stats_dev != ext) {
-            if (ctx->stats_dev && !ctx->stats_external) cudaFree(ctx->stats_dev);
-            ctx->stats_dev = ext; ctx->stats_cap = c->cap_doubles; ctx->stats_external = true; ctx->have_stats = false;
-        }
-        return SGP_OK;
-    }
-    if (ctx->stats_external) { ctx->stats_dev = nullptr; ctx->stats_cap = 0; ctx->stats_external = false; ctx->have_stats = false; }
-    return sgp_ensure(ctx, &ctx->stats_dev, &ctx->stats_cap, need);
 }
 
 void sgp_comm_destroy(sgp_ctx* ctx) {
@@ -207,7 +193,6 @@ void sgp_comm_destroy(sgp_ctx* ctx) {
         NcclApi& a = api();
         SgpComm* c = ctx->comm;
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-        if (ctx->stats_external) { ctx->stats_dev = nullptr; ctx->stats_cap = 0; ctx->stats_external = false; ctx->have_stats = false; }
         for (int q = 0; q < 8; ++q) if (q != c->rank && c->peers[q]) cudaIpcCloseMemHandle(c->peers[q]);
         if (c->region) cudaFree(c->region);
         if (a.ok && ctx->comm->comm) a.CommDestroy(ctx->comm->comm);

@@ -44,7 +44,6 @@ struct sgp_ctx {
     // statistics of the last sweep: stats_dev = [psi2 (M*M) | psi1 (M*Dout) | psi0 | sum_y2 | sum_w | n]
     double* stats_dev = nullptr;
     size_t stats_cap = 0;
-    bool stats_external = false;    // stats_dev lives in the peer-mapped exchange region of the communicator (comm.cu)
     int Dout = 1;
     bool have_stats = false;
     bool stats_of_data = false;     // ... and they are the statistics of the resident data set (not of a sigma-point cloud / theta scratch)
@@ -149,17 +148,16 @@ int sgp_sweep_resident(sgp_ctx* ctx, bool time_main);     // sweep of the reside
 int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count);          // xchg.cu: peer-memory kernel, or NCCL when the regions are not mapped
 int sgp_comm_allreduce_stats(sgp_ctx* ctx, int M, int D_out);               // ... of the resident statistics (packed lower triangle on the wire)
 void sgp_comm_destroy(sgp_ctx* ctx);
-// Peer-memory exchange fused into the sweep kernel (single node, <= 8 ranks): every rank owns a region
-// [flags A | flags B | xin (cap doubles) | xout (cap doubles)] that all peers map through CUDA IPC.
+// Peer-memory exchange (xchg.cuh; single node, <= 8 ranks): every rank owns a region [flags (256 B) | slot 0 | ... | slot R-1] that all
+// peers map through CUDA IPC; slot q of rank r receives rank q's contribution (PUSHED by rank q), cap doubles each.
 struct SgpXchg {
     int nranks = 1, rank = 0;
-    unsigned epoch = 0;            // barrier value of this sweep (flags are monotonic, never reset)
+    unsigned epoch = 0;            // barrier value of this exchange (flags are monotonic, never reset)
     char* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // region of rank q as mapped here
-    size_t xin_off = 0, xout_off = 0;   // byte offsets inside a region; flags A at 0, flags B at 64
-    long long count = 0;           // capacity check only: doubles of the unpacked statistics
+    size_t slot0_off = 0, slot_bytes = 0;   // byte offset of slot 0 inside a region, bytes per slot
 };
-bool sgp_comm_xchg(sgp_ctx* ctx, size_t need_doubles, SgpXchg* x);     // fills x (and bumps the epoch) if the fused exchange is available
-int sgp_ensure_stats(sgp_ctx* ctx, size_t need_doubles);               // stats_dev: exchange region when available, else an own buffer
+bool sgp_comm_xchg(sgp_ctx* ctx, size_t need_doubles, SgpXchg* x);     // fills x (and bumps the epoch) if the peer-memory exchange is available
+inline int sgp_ensure_stats(sgp_ctx* ctx, size_t need_doubles) { return sgp_ensure(ctx, &ctx->stats_dev, &ctx->stats_cap, need_doubles); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // device helpers

@@ -50,10 +50,18 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     const long long chunks = (N + NB - 1) / NB;
     // slab: as many chunks as keep the panel (nblk x 32 x (TM + 4) doubles per chunk) inside the L2 budget
     double slab_mb = 20.0;        // per panel; the ring holds three: 60 MB is what stays in the L2 (persisting window) without DRAM re-reads
-    if (const char* e = std::getenv("SGP_SWEEP_SLAB_MB")) { double v = std::atof(e); if (v > 0.0) slab_mb = v; }
+    if (const char* e = std::getenv("SGP_SWEEP_SLAB_MB")) { double v = std::atof(e); if (v > 0.0) slab_mb = v; }      // (forces the panel size)
     const size_t chunk_doubles = (size_t)nblk * NB * (TM + 4);
     long long max_slab = (long long)(slab_mb * 1048576.0 / (chunk_doubles * sizeof(double)));
     if (max_slab < 8) max_slab = 8;
+    if (!std::getenv("SGP_SWEEP_SLAB_MB")) {
+        // Small problems: when ALL of K_uf fits the L2 next to everything else (<= 64 MB: one slab; <= 96 MB: two), every panel is written once
+        // and read once without any ring turnover -- one generator phase instead of several short ones (kin40k shape, 42 MB: 0.134 -> 0.119 ms;
+        // N = 20 000: 0.246 -> 0.218 ms; tools/sweep_knobs.sh).  Larger problems keep the 3 x 20 MB ring that stays L2-resident.
+        const double total_mb = (double)chunks * chunk_doubles * sizeof(double) / 1048576.0;
+        if (total_mb <= 64.0) max_slab = chunks;
+        else if (total_mb <= 96.0) max_slab = (chunks + 1) / 2;
+    }
     const int nslabs = (int)((chunks + max_slab - 1) / max_slab);
     const long long slab_chunks = (chunks + nslabs - 1) / nslabs;
     int w_diag = 5, w_off = 8, w_fixed = 64;          // per k-step (4 points) / per segment, from the per-segment clock fit (tools/profile_sweep.py)
@@ -93,14 +101,11 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     p.slab_doubles = (long long)(slab_chunks * chunk_doubles); p.nring = nring;
     p.partial = ctx->work_dev; p.psi1_partial = p.partial + (size_t)nslots * TM * TM; p.scal_partial = p.psi1_partial + (size_t)ncta * TM;
     p.psi2 = ctx->stats_dev; p.psi1 = p.psi2 + (size_t)M * M; p.scal = p.psi1 + M;
-    // multi-GPU: phase 2 writes this rank's statistics into its exchange region (Psi2 as the packed lower triangle) and the kernel sums them
-    // over the ranks through peer memory (one-shot pull: every rank reads all contributions and adds them in rank order, xchg.cuh)
+    // multi-GPU: phase 2 pushes this rank's statistics (Psi2 as the packed lower triangle) into its slot on every rank, and the kernel's tail adds
+    // the slots in rank order once all ranks have published (xchg.cuh)
     ctx->last_sweep_exchanged = false;
-    if (ctx->want_exchange && sgp_comm_xchg(ctx, (size_t)M * M + M + 4, &p.xr)) {
-        p.psi2 = reinterpret_cast<double*>(p.xr.peers[p.xr.rank] + p.xr.xin_off); p.psi1 = p.psi2 + (size_t)M * (M + 1) / 2; p.scal = p.psi1 + M;
-        p.stats_out = ctx->stats_dev;
-        ctx->last_sweep_exchanged = true;
-    }
+    p.stats_out = ctx->stats_dev;
+    if (ctx->want_exchange && sgp_comm_xchg(ctx, (size_t)M * (M + 1) / 2 + M + 4, &p.xr)) ctx->last_sweep_exchanged = true;
 
     // the panel ring is the only buffer worth keeping in L2: mark it persisting, everything else streams through the rest of the cache
     if (ctx->kbuf_window != (void*)ctx->kbuf_dev || ctx->kbuf_window_bytes != (size_t)nring * slab_chunks * chunk_doubles * sizeof(double)) {

@@ -65,8 +65,8 @@ struct Params {
     double center[SGP_MAX_D];
     double log_var_s;
     double variance;
-    SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none): psi2 / psi1 / scal then point into this rank's xin, Psi2 as the PACKED lower triangle
-    double* stats_out;            // ... and the sums over the ranks land here (full symmetric Psi2 | Psi1 | scalars)
+    SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none): phase 2 then pushes [packed lower triangle of Psi2 | Psi1 | scalars] to every rank
+    double* stats_out;            // ... and the sums over the ranks land here (full symmetric Psi2 | Psi1 | scalars); = psi2 without exchange
 };
 
 __device__ __forceinline__ void mbar_wait_(unsigned long long* bar, unsigned parity) {
@@ -578,6 +578,7 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nitems = p.ntiles * STRIPES;
     const bool packed = p.xr.nranks > 1;
+    const long long tri = (long long)p.M * (p.M + 1) / 2;
     const int it0 = (int)((long long)nitems * blockIdx.x / gridDim.x), it1 = (int)((long long)nitems * (blockIdx.x + 1) / gridDim.x);
     int* slots = ibuf + NWARPS;
     int it = it0;
@@ -640,10 +641,12 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                 const int r0 = (sb + q) * SR;
                 const double* Sq = S_ + (size_t)q * SR * LDS_;
                 for (int e = tid; e < SR * TM; e += NT) {
-                    {   // psi2[gi + gj*M]: SR consecutive rows = one 32-byte sector per column (multi-GPU: column gj of the packed lower triangle)
+                    {   // psi2[gi + gj*M]: SR consecutive rows = one 32-byte sector per column (multi-GPU: column gj of the packed lower triangle, to every rank)
                         const int rl = e % SR, c = e / SR, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
-                        if (gi < p.M && gj < p.M && (!diag || c <= r))
-                            p.psi2[packed ? (size_t)(sgp_xchg::tri_col(gj, p.M) + gi - gj) : (size_t)gi + (size_t)gj * p.M] = Sq[rl * LDS_ + c];
+                        if (gi < p.M && gj < p.M && (!diag || c <= r)) {
+                            if (packed) sgp_xchg::push1(p.xr, sgp_xchg::tri_col(gj, p.M) + gi - gj, Sq[rl * LDS_ + c]);
+                            else p.psi2[(size_t)gi + (size_t)gj * p.M] = Sq[rl * LDS_ + c];
+                        }
                     }
                     if (!packed) {   // mirror psi2[gj + gi*M]: consecutive threads -> consecutive columns (multi-GPU: the pull writes both halves)
                         const int rl = e / TM, c = e % TM, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
@@ -657,7 +660,10 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                     for (int qq = lo + lane; qq < hi; qq += 32) v += __ldcg(p.psi1_partial + (size_t)qq * TM + r);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == 0 && gi < p.M) p.psi1[gi] = v;
+                    if (lane == 0 && gi < p.M) {
+                        if (packed) sgp_xchg::push1(p.xr, tri + gi, v);
+                        else p.psi1[gi] = v;
+                    }
                 }
             }
             __syncthreads();                                 // S_ is reused by the next batch
@@ -669,10 +675,12 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { sw += __shfl_xor_sync(0xffffffffu, sw, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
             if (lane == 0) {
-                p.scal[0] = p.variance * sw;   // Psi0 = sum_n w_n k(x_n, x_n)
-                p.scal[1] = sy;                // sum_n w_n (ybar^2 + yvar)
-                p.scal[2] = sw;
-                p.scal[3] = (double)p.N;
+                const double sc[4] = {p.variance * sw /* Psi0 = sum_n w_n k(x_n, x_n) */, sy /* sum_n w_n (ybar^2 + yvar) */, sw, (double)p.N};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (packed) sgp_xchg::push1(p.xr, tri + p.M + q, sc[q]);
+                    else p.scal[q] = sc[q];
+                }
             }
         }
         it += s_hi - s_lo;
@@ -868,10 +876,10 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     // the dependency counters are dead after the last grid barrier: leave them zeroed for the next launch (no memset per sweep on the host)
     if (bcta == 0)
         for (int i = tid; i < p.nring * (p.nblk + 1); i += NT) p.flags[i] = 0u;
-    if (p.xr.nranks > 1) {      // sum over the ranks (xchg.cuh): publish, wait for all contributions, one-shot pull, signal "done reading"
+    if (p.xr.nranks > 1) {      // sum over the ranks (xchg.cuh): publish the pushed contribution, wait for all ranks, add the local slots, signal "done reading"
         sgp_xchg::publish(p.xr, p.ncta);
         sgp_xchg::gather_wait(p.xr);
-        sgp_xchg::pull_stats(p.xr, p.stats_out, p.M, p.M + 4, bcta, p.ncta);
+        sgp_xchg::sum_stats(p.xr, p.stats_out, p.M, p.M + 4, bcta, p.ncta);
         sgp_xchg::done(p.xr, p.ncta);
     }
     if (p.dbg && tid == 0) {   // timeline of this CTA: {setup clocks, slab-loop clocks, 4, cta}, {final barrier clocks, phase-2 (+ exchange) clocks, 5, cta}

@@ -7,30 +7,30 @@
 namespace {
 
 // mode 0: dst[e] = sum over ranks of src[e], e < count.
-// mode 1: src = dst = statistics buffer [Psi2 (M x M, full symmetric) | tail (ntail)]: contributed as the packed lower triangle + tail.
+// mode 1: src = dst = statistics buffer [Psi2 (M x M, full symmetric) | tail (ntail)]: contributed as the packed lower triangle + tail
+//         (in place: every CTA has pushed its part before any CTA passes gather_wait, which needs this rank's own flag too).
 __global__ void __launch_bounds__(256) xchg_kernel(const SgpXchg x, const double* __restrict__ src, double* __restrict__ dst, long long count, int M,
                                                    int ntail, int mode) {
     const int cta = blockIdx.x, ncta = gridDim.x, tid = threadIdx.x, nt = blockDim.x;
     sgp_xchg::wait_free(x);
-    double* xin = sgp_xchg::xin_of(x, x.rank);
     if (mode == 0) {
-        for (long long e = (long long)cta * nt + tid; e < count; e += (long long)ncta * nt) xin[e] = src[e];
+        for (long long e = (long long)cta * nt + tid; e < count; e += (long long)ncta * nt) sgp_xchg::push1(x, e, src[e]);
     } else {
         for (int j = cta; j < M; j += ncta) {
             const long long off = sgp_xchg::tri_col(j, M) - j;
-            for (int i = j + tid; i < M; i += nt) xin[off + i] = src[(size_t)i + (size_t)j * M];
+            for (int i = j + tid; i < M; i += nt) sgp_xchg::push1(x, off + i, src[(size_t)i + (size_t)j * M]);
         }
         if (cta == ncta - 1) {
             const long long tri = (long long)M * (M + 1) / 2;
-            for (int e = tid; e < ntail; e += nt) xin[tri + e] = src[(size_t)M * M + e];
+            for (int e = tid; e < ntail; e += nt) sgp_xchg::push1(x, tri + e, src[(size_t)M * M + e]);
         }
     }
     sgp_xchg::publish(x, ncta);
     sgp_xchg::gather_wait(x);
     if (mode == 0) {
-        for (long long e = (long long)cta * nt + tid; e < count; e += (long long)ncta * nt) dst[e] = sgp_xchg::pull1(x, e);
+        for (long long e = (long long)cta * nt + tid; e < count; e += (long long)ncta * nt) dst[e] = sgp_xchg::sum1(x, e);
     } else {
-        sgp_xchg::pull_stats(x, dst, M, ntail, cta, ncta);
+        sgp_xchg::sum_stats(x, dst, M, ntail, cta, ncta);
     }
     sgp_xchg::done(x, ncta);
 }
@@ -63,6 +63,6 @@ int sgp_comm_allreduce_stats(sgp_ctx* ctx, int M, int D_out) {
     const int ntail = M * D_out + 4;
     const size_t full = (size_t)M * M + (size_t)ntail;
     SgpXchg x;
-    if (sgp_comm_xchg(ctx, full, &x)) return launch(ctx, x, ctx->stats_dev, ctx->stats_dev, 0, M, ntail, 1);
+    if (sgp_comm_xchg(ctx, (size_t)M * (M + 1) / 2 + (size_t)ntail, &x)) return launch(ctx, x, ctx->stats_dev, ctx->stats_dev, 0, M, ntail, 1);
     return sgp_comm_allreduce_nccl(ctx, ctx->stats_dev, full);
 }
