@@ -16,7 +16,7 @@
 // equally heavy slice of the (tile, chunk) sequence -- at most a few "segments" (tile, chunk range) per CTA.
 //
 // Per segment, software-pipelined over chunks (one __syncthreads per chunk):
-//     1. cp.async.bulk (TMA, 1-D, SASS UBLKCP) stages the raw x / y / w blocks, 4 stages deep, mbarrier-tracked
+//     1. cp.async.bulk (TMA, 1-D, SASS UBLKCP) stages the raw x / y / w blocks in a multi-stage ring (kStages in sweep_kernel.cuh), mbarrier-tracked
 //     2. raw block -> scaled records  x~ = sqrt(s) (x - c)/ell,  a = -|x~|^2/2                (s = 2048/ln 2)
 //     3. every thread owns one inducing row and generates K_uf values of chunk c+1 into the other half of a
 //        double-buffered shared-memory tile:   k = exp(a_n + b_m + x~_n . z~_m)   (16 FP64-pipe instructions per value
@@ -25,8 +25,8 @@
 //        consumption of chunk c into a 64x32 register accumulator per warp.  DFMA and DMMA share one pipe
 //        (tools/fp64_microbench.cu), so the only way to keep it full is to feed it both streams at once: the DMMAs
 //        hide the dependent-issue latency of the generator chains and vice versa.
-//   After its last chunk a segment's partial tile goes to the workspace; a second kernel adds the partials of each
-//   tile in a fixed order (deterministic, no FP64 atomics), mirrors the triangle and finishes Psi1.
+//   After its last chunk a segment's partial tile goes to the workspace; after a grid barrier the same (cooperative) launch adds the
+//   partials of each tile in a fixed order (deterministic, no FP64 atomics), mirrors the triangle and finishes Psi1.
 //
 // Roofline: FP64 DMMA pipe (measured 37.0 TFLOP/s on this pool's B200; cuBLAS DGEMM 35.5).  The generator's 16
 // instructions per value are paid from the same budget: (TI+TJ)*16 / (TI*TJ) = 25 % on top of the MMA work for a 128x128

@@ -3,7 +3,12 @@
 * ``srcubature`` / ``ghcubature``: ReactiveMP.jl (NOT under /root/reference, unpinned; **parity unpinned**,
   restated from ReactiveMP's published definitions; call sites GPnode/MultiSGPnode.jl:15-35,
   GPnode/UniSGPnode.jl:11-33, GPtest.jl:14-15).  GPtest.jl:380 asserts the spherical-radial weights sum to one
-  exactly for a constant integrand.
+  exactly for a constant integrand (tests/test_oracle_rules.py checks that).
+  Searched for a stronger pin (round 2): every code cell of experiments/*.ipynb that touches srcubature / ghcubature /
+  approximate_kernel_expectation / GenUnscented (Pendulum_Wishart_2d cells 13, 36, 39; GPLVM cell 14) either prints nothing or
+  depends on Julia's MersenneTwister stream (`Random.seed!(124)` data, `rand` initialisations), and GPtest.jl draws its inputs
+  with unseeded `rand`: the reference holds NO RNG-free cubature output, so node placement and order stay pinned only to the
+  Monte-Carlo tolerances of GPtest.jl:141-143, 380-382 and to the published definitions.  Nothing further can be pinned here.
 * ``gen_unscented_*``: helper_functions/ut_approx.jl:116-151, quirks reproduced as written.
 All rules return (points [S x d], weights [S]) in the reference's enumeration order.
 """
