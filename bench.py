@@ -354,7 +354,7 @@ def main():
         "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "kin40k-shape VSGP sweep (BASELINE.json configs[1]): N=10000 points per GPU, D=8, M=512, SE-ARD, Float64; "
-                               "Psi0/Psi1/Psi2 per step" + ("; statistics summed over the ranks inside the sweep kernel (NVLink peer memory, one-shot pull of the packed lower triangle)" if world > 1 else ""),
+                               "Psi0/Psi1/Psi2 per step" + ("; statistics summed over the ranks inside the sweep kernel (NVLink peer memory, two-shot all-reduce of the packed lower triangle); ranks aligned by a flag barrier after every L2 flush, before the timed interval" if world > 1 else ""),
                    "l2": "256 MB buffer rewritten on the stream before every timed step (inputs are smaller than L2); flush outside the timed intervals",
                    "parallelism": "N sharded over %d GPU(s)" % world, "wall_s_timed_region": t_wall},
         "e2e": {"value": e2e_val, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

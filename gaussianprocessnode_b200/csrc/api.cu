@@ -342,6 +342,9 @@ int sgp_sweep_timed_flushed(sgp_ctx* ctx, int reps, int flush_mb, float* ms_per_
     int rc = SGP_OK;
     for (int r = 0; r < reps && rc == SGP_OK; ++r) {
         if (fbytes && cudaMemsetAsync(ctx->flush_dev, r & 0xff, fbytes, ctx->stream) != cudaSuccess) { rc = SGP_ERR_CUDA; break; }
+        // the flush takes a few microseconds more on one GPU than on another: align the ranks again BEFORE the timed interval starts (a flag
+        // barrier over peer memory on the stream), otherwise that skew is waited out inside the timed sweep's exchange
+        if (ctx->comm && sgp_comm_barrier(ctx) != SGP_OK) { rc = SGP_ERR_CUDA; break; }
         if (cudaEventRecord(ev[4 * r], ctx->stream) != cudaSuccess) { rc = SGP_ERR_CUDA; break; }
         ctx->ev[2] = ev[4 * r + 2]; ctx->ev[3] = ev[4 * r + 3];       // the launcher brackets the main kernel with ev[2] / ev[3]
         rc = sgp_sweep_resident(ctx, true);

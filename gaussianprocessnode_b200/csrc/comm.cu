@@ -50,6 +50,7 @@ struct SgpComm {
     size_t cap_doubles = 0;
     char* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned epoch = 0;
+    unsigned epoch_bar = 0;        // epoch of the stand-alone rank barrier (sgp_comm_barrier)
 };
 
 namespace {
@@ -63,9 +64,9 @@ void setup_p2p(sgp_ctx* ctx, SgpComm* c) {
     if (const char* e = std::getenv("SGP_COMM_P2P")) if (e[0] == '0') return;
     size_t maxM = 2048;
     if (const char* e = std::getenv("SGP_COMM_P2P_MAXM")) { long v = std::atol(e); if (v >= 1) maxM = (size_t)v; }
-    // one receive slot per rank: the packed statistics (lower triangle of Psi2 | Psi1 for up to 16 outputs | scalars), 16-byte aligned
+    // two buffers (contribution, result) of the packed statistics (lower triangle of Psi2 | Psi1 for up to 16 outputs | scalars), 16-byte aligned
     const size_t cap = (maxM * (maxM + 1) / 2 + 16 * maxM + 64 + 1) & ~(size_t)1;
-    const size_t bytes = kFlagBytes + (size_t)c->nranks * cap * sizeof(double);
+    const size_t bytes = kFlagBytes + 2 * cap * sizeof(double);
     bool ok = cudaMalloc((void**)&c->region, bytes) == cudaSuccess;
     if (ok) ok = cudaMemset(c->region, 0, bytes) == cudaSuccess;
     cudaIpcMemHandle_t mine;
@@ -185,6 +186,14 @@ bool sgp_comm_xchg(sgp_ctx* ctx, size_t need_doubles, SgpXchg* x) {
     x->nranks = c->nranks; x->rank = c->rank; x->epoch = ++c->epoch;
     for (int q = 0; q < 8; ++q) x->peers[q] = c->peers[q];
     x->slot0_off = kFlagBytes; x->slot_bytes = c->cap_doubles * sizeof(double);
+    return true;
+}
+
+bool sgp_comm_xchg_barrier(sgp_ctx* ctx, SgpXchg* x) {
+    SgpComm* c = ctx->comm;
+    if (!c || !c->p2p) return false;
+    x->nranks = c->nranks; x->rank = c->rank; x->epoch = ++c->epoch_bar;
+    for (int q = 0; q < 8; ++q) x->peers[q] = c->peers[q];
     return true;
 }
 

@@ -146,15 +146,16 @@ const double* sgp_resident_sigma(sgp_ctx* ctx);
 int sgp_sweep_resident(sgp_ctx* ctx, bool time_main);     // sweep of the resident data, statistics summed over the ranks
 // comm.cu
 int sgp_comm_allreduce(sgp_ctx* ctx, double* buf, size_t count);          // xchg.cu: peer-memory kernel, or NCCL when the regions are not mapped
-int sgp_comm_allreduce_stats(sgp_ctx* ctx, int M, int D_out);               // ... of the resident statistics (packed lower triangle on the wire)
+int sgp_comm_allreduce_stats(sgp_ctx* ctx, int M, int D_out);
+int sgp_comm_barrier(sgp_ctx* ctx);                                         // flag barrier over the ranks on the ctx stream (peer-memory exchange only)               // ... of the resident statistics (packed lower triangle on the wire)
 void sgp_comm_destroy(sgp_ctx* ctx);
-// Peer-memory exchange (xchg.cuh; single node, <= 8 ranks): every rank owns a region [flags (256 B) | slot 0 | ... | slot R-1] that all
-// peers map through CUDA IPC; slot q of rank r receives rank q's contribution (PUSHED by rank q), cap doubles each.
+// Peer-memory exchange (xchg.cuh; single node, <= 8 ranks): every rank owns a region [flags (256 B) | contribution | result] (cap doubles
+// each) that all peers map through CUDA IPC.
 struct SgpXchg {
     int nranks = 1, rank = 0;
     unsigned epoch = 0;            // barrier value of this exchange (flags are monotonic, never reset)
     char* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // region of rank q as mapped here
-    size_t slot0_off = 0, slot_bytes = 0;   // byte offset of slot 0 inside a region, bytes per slot
+    size_t slot0_off = 0, slot_bytes = 0;   // byte offset of the contribution buffer inside a region; the result buffer follows after slot_bytes
 };
 bool sgp_comm_xchg(sgp_ctx* ctx, size_t need_doubles, SgpXchg* x);     // fills x (and bumps the epoch) if the peer-memory exchange is available
 inline int sgp_ensure_stats(sgp_ctx* ctx, size_t need_doubles) { return sgp_ensure(ctx, &ctx->stats_dev, &ctx->stats_cap, need_doubles); }

@@ -92,8 +92,8 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     s4::Params p{};
     p.X = X; p.y = y; p.yv = yv; p.w = w; p.N = N; p.chunks = chunks; p.slab_chunks = slab_chunks; p.slab_units = slab_units; p.nslabs = nslabs;
     p.M = M; p.D = D; p.ntiles = ntiles; p.nblk = nblk; p.ncta = ncta;
-    p.total_cost = total_cost; p.w_diag = w_diag; p.w_off = w_off; p.w_fixed = w_fixed; p.dbg = (nslots + 6 * ncta <= 8192) ? ctx->sweep_dbg_dev : nullptr;
-    if (p.dbg) { SGP_CUDA(ctx, cudaMemsetAsync(p.dbg, 0xff, (size_t)(nslots + 6 * ncta) * 4 * sizeof(long long), ctx->stream)); ctx->sweep_dbg_slots = nslots + 6 * ncta; }
+    p.total_cost = total_cost; p.w_diag = w_diag; p.w_off = w_off; p.w_fixed = w_fixed; p.dbg = (nslots + 8 * ncta <= 8192) ? ctx->sweep_dbg_dev : nullptr;
+    if (p.dbg) { SGP_CUDA(ctx, cudaMemsetAsync(p.dbg, 0xff, (size_t)(nslots + 8 * ncta) * 4 * sizeof(long long), ctx->stream)); ctx->sweep_dbg_slots = nslots + 8 * ncta; }
     const double sq = std::sqrt(SGP_EXP_SCALE);
     for (int d = 0; d < SGP_MAX_D; ++d) { p.inv_ell_s[d] = d < D ? sq / ctx->ell[d] : 0.0; p.center[d] = d < D ? ctx->center[d] : 0.0; }
     p.log_var_s = SGP_EXP_SCALE * std::log(ctx->variance); p.variance = ctx->variance;

@@ -65,7 +65,7 @@ struct Params {
     double center[SGP_MAX_D];
     double log_var_s;
     double variance;
-    SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none): phase 2 then pushes [packed lower triangle of Psi2 | Psi1 | scalars] to every rank
+    SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none): phase 2 then writes [packed lower triangle of Psi2 | Psi1 | scalars] into this rank's contribution buffer
     double* stats_out;            // ... and the sums over the ranks land here (full symmetric Psi2 | Psi1 | scalars); = psi2 without exchange
 };
 
@@ -644,7 +644,7 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                     {   // psi2[gi + gj*M]: SR consecutive rows = one 32-byte sector per column (multi-GPU: column gj of the packed lower triangle, to every rank)
                         const int rl = e % SR, c = e / SR, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
                         if (gi < p.M && gj < p.M && (!diag || c <= r)) {
-                            if (packed) sgp_xchg::push1(p.xr, sgp_xchg::tri_col(gj, p.M) + gi - gj, Sq[rl * LDS_ + c]);
+                            if (packed) sgp_xchg::put1(p.xr, sgp_xchg::tri_col(gj, p.M) + gi - gj, Sq[rl * LDS_ + c]);
                             else p.psi2[(size_t)gi + (size_t)gj * p.M] = Sq[rl * LDS_ + c];
                         }
                     }
@@ -661,7 +661,7 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     if (lane == 0 && gi < p.M) {
-                        if (packed) sgp_xchg::push1(p.xr, tri + gi, v);
+                        if (packed) sgp_xchg::put1(p.xr, tri + gi, v);
                         else p.psi1[gi] = v;
                     }
                 }
@@ -678,7 +678,7 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                 const double sc[4] = {p.variance * sw /* Psi0 = sum_n w_n k(x_n, x_n) */, sy /* sum_n w_n (ybar^2 + yvar) */, sw, (double)p.N};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (packed) sgp_xchg::push1(p.xr, tri + p.M + q, sc[q]);
+                    if (packed) sgp_xchg::put1(p.xr, tri + p.M + q, sc[q]);
                     else p.scal[q] = sc[q];
                 }
             }
@@ -870,17 +870,21 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     __threadfence();
     grid.sync();
     if (p.dbg) t_k3 = clock64();
-    if (p.xr.nranks > 1) sgp_xchg::wait_free(p.xr);       // every peer has read this rank's previous contribution
     long long tr[3] = {0, 0, 0};
     reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)), tr);
     // the dependency counters are dead after the last grid barrier: leave them zeroed for the next launch (no memset per sweep on the host)
     if (bcta == 0)
         for (int i = tid; i < p.nring * (p.nblk + 1); i += NT) p.flags[i] = 0u;
-    if (p.xr.nranks > 1) {      // sum over the ranks (xchg.cuh): publish the pushed contribution, wait for all ranks, add the local slots, signal "done reading"
-        sgp_xchg::publish(p.xr, p.ncta);
-        sgp_xchg::gather_wait(p.xr);
-        sgp_xchg::sum_stats(p.xr, p.stats_out, p.M, p.M + 4, bcta, p.ncta);
-        sgp_xchg::done(p.xr, p.ncta);
+    if (p.xr.nranks > 1) {      // sum over the ranks (xchg.cuh): two-shot all-reduce of the packed statistics over NVLink peer memory
+        if (bcta == 0 && tid == 0 && ((p.M + 4 + (long long)p.M * (p.M + 1) / 2) & 1)) sgp_xchg::put1(p.xr, (long long)p.M * (p.M + 1) / 2 + p.M + 4, 0.0);
+        long long tx[5];
+        const long long tx0 = clock64();
+        sgp_xchg::allreduce_stats(p.xr, p.stats_out, p.M, p.M + 4, bcta, p.ncta, p.dbg ? tx : nullptr);
+        if (p.dbg && tid == 0) {   // {publish A, wait A, 8, reduce-scatter}, {publish B + wait B, expand, 9, phase 2 before the exchange}
+            long long* d4 = p.dbg + 4 * (size_t)(p.ncta + p.ntiles) + 24 * (size_t)p.ncta;
+            d4[8 * bcta + 0] = tx[0] - tx0; d4[8 * bcta + 1] = tx[1] - tx[0]; d4[8 * bcta + 2] = 8; d4[8 * bcta + 3] = tx[2] - tx[1];
+            d4[8 * bcta + 4] = tx[3] - tx[2]; d4[8 * bcta + 5] = tx[4] - tx[3]; d4[8 * bcta + 6] = 9; d4[8 * bcta + 7] = tx0 - t_k3;
+        }
     }
     if (p.dbg && tid == 0) {   // timeline of this CTA: {setup clocks, slab-loop clocks, 4, cta}, {final barrier clocks, phase-2 (+ exchange) clocks, 5, cta}
         long long* d = p.dbg + 4 * (size_t)(p.ncta + p.ntiles) + 8 * (size_t)p.ncta;
