@@ -521,11 +521,12 @@ def main():
         best = 1e30
         for _ in range(3):
             t0 = time.perf_counter(); port.sweep(Xc, yc, Zk, KIN["variance"], ellk, 1.0e4, threads=threads); best = min(best, time.perf_counter() - t0)
+        used = int(port.sweep.last_threads)
         t0 = time.perf_counter(); port.sweep(Xc[:2000], yc[:2000], Zk, KIN["variance"], ellk, 1.0e4, threads=1); r1 = 2000 / (time.perf_counter() - t0)
-        line["cpu_baseline"] = {"value": KIN["N"] / best, "unit": "points/s", "cores": int(port.sweep.last_threads if threads != 1 else 1), "kind": "port",
+        line["cpu_baseline"] = {"value": KIN["N"] / best, "unit": "points/s", "cores": used, "kind": "port",
                                 "sample": "all 10000 kin40k-shape points, best of 3 passes (%.2f s each); C port of the reference's per-point rule + prod "
                                           "schedule (oracle/sweep_port.c), OpenMP over the column / rank-1 `mul!` / M x M add with %d thread(s) (fastest of a probe; "
-                                          "1 thread: %.0f points/s); Julia not installed" % (best, threads, r1)}
+                                          "1 thread: %.0f points/s); Julia not installed" % (best, used, r1)}
         try:
             dt, c1, c2 = cpu_best_effort(KIN, Xc, yc, Zk, ellk)
             dt = min(dt, cpu_best_effort(KIN, Xc, yc, Zk, ellk)[0])
