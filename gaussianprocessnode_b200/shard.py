@@ -36,6 +36,39 @@ def unpack_stats(buf, M, D_out=1):
     return psi0, (psi1[:, 0] if D_out == 1 else psi1), psi2, sum_y2, sum_w, int(round(n))
 
 
+def tri_col(j, M):
+    """Offset of column j in the packed lower triangle (column by column) -- csrc/xchg.cuh: tri_col."""
+    return j * M - j * (j - 1) // 2
+
+
+def pack_stats_lower(psi0, psi1, psi2, sum_y2, sum_w, n):
+    """What crosses NVLink (csrc/xchg.cuh): the lower triangle of Psi2 column by column (M (M + 1) / 2 doubles), then Psi1 (M x D_out,
+    column-major) and the four scalars; padded with one zero to an even length (the reduce-scatter works on 16-byte pairs)."""
+    psi2 = np.asarray(psi2, dtype=np.float64); M = psi2.shape[0]
+    cols = [psi2[j:, j] for j in range(M)]
+    buf = np.concatenate(cols + [np.asarray(psi1, dtype=np.float64).ravel(order="F"), np.array([psi0, sum_y2, sum_w, float(n)])])
+    return np.concatenate([buf, [0.0]]) if buf.size % 2 else buf
+
+
+def unpack_stats_lower(buf, M, D_out=1):
+    """Step 5 of the exchange: packed result -> full symmetric Psi2, Psi1, scalars."""
+    buf = np.asarray(buf, dtype=np.float64)
+    psi2 = np.empty((M, M))
+    for j in range(M):
+        c = buf[tri_col(j, M):tri_col(j + 1, M)]
+        psi2[j:, j] = c; psi2[j, j:] = c
+    tri = M * (M + 1) // 2
+    psi1 = buf[tri:tri + M * D_out].reshape(M, D_out, order="F")
+    psi0, sum_y2, sum_w, n = buf[tri + M * D_out:tri + M * D_out + 4]
+    return psi0, (psi1[:, 0] if D_out == 1 else psi1), psi2, sum_y2, sum_w, int(round(n))
+
+
+def two_shot_share(n, world, rank):
+    """Rank `rank`'s share [lo, hi) of the n packed doubles in the reduce-scatter (pairs of doubles, csrc/xchg.cuh: reduce_scatter)."""
+    pairs = (n + 1) // 2
+    return 2 * (pairs * rank // world), min(2 * (pairs * (rank + 1) // world), 2 * pairs)
+
+
 class ShardedSweep:
     """One rank's view of a sharded sweep: owns an SGPContext on `device`, keeps its slice of the data resident and
     attaches the NCCL communicator (the unique id travels over the host's own process group, e.g. torch.distributed)."""
