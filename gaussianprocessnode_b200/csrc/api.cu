@@ -132,7 +132,7 @@ int sgp_set_kernel(sgp_ctx* ctx, int kind, int D, double variance, const double*
     if (kind < 0 || kind > 2 || D < 1 || D > SGP_MAX_D || !lengthscale || !(variance > 0.0)) SGP_FAIL(ctx, SGP_ERR_ARG, "set_kernel: bad kind / D (1..16) / variance");
     for (int d = 0; d < D; ++d) if (!(lengthscale[d] > 0.0)) SGP_FAIL(ctx, SGP_ERR_ARG, "set_kernel: lengthscale must be positive");
     if (ctx->have_Z && D != ctx->D) { ctx->have_Z = false; }
-    if (ctx->N > 0 && D != ctx->D) { ctx->N = 0; }
+    if (ctx->have_data && D != ctx->D) { ctx->N = 0; ctx->have_data = false; }
     ctx->kind = kind; ctx->D = D; ctx->variance = variance;
     for (int d = 0; d < D; ++d) ctx->ell[d] = lengthscale[d];
     ctx->have_kernel = true; ctx->have_kuu = false; ctx->have_stats = false;
@@ -204,7 +204,7 @@ static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* y
     else SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, cap * sizeof(double), ctx->stream));
     if (yvar && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->yv_dev, yvar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (wts && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->w_dev, wts, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->N = N; ctx->have_yv = yvar != nullptr; ctx->have_w = wts != nullptr; ctx->have_stats = false;
+    ctx->N = N; ctx->have_yv = yvar != nullptr; ctx->have_w = wts != nullptr; ctx->have_stats = false; ctx->have_data = true;
     return SGP_OK;
 }
 
@@ -231,7 +231,7 @@ int sgp_set_data_dev(sgp_ctx* ctx, int64_t N, const double* X_dev, const double*
     if (ctx->own_data) { cudaFree(ctx->X_dev); cudaFree(ctx->y_dev); cudaFree(ctx->yv_dev); cudaFree(ctx->w_dev); ctx->own_data = false; }
     ctx->X_dev = const_cast<double*>(X_dev); ctx->y_dev = const_cast<double*>(ybar_dev);
     ctx->yv_dev = const_cast<double*>(yvar_dev); ctx->w_dev = const_cast<double*>(wts_dev);
-    ctx->N = N; ctx->Ncap = N; ctx->have_yv = yvar_dev != nullptr; ctx->have_w = wts_dev != nullptr; ctx->have_stats = false;
+    ctx->N = N; ctx->Ncap = N; ctx->have_yv = yvar_dev != nullptr; ctx->have_w = wts_dev != nullptr; ctx->have_stats = false; ctx->have_data = true;
     return SGP_OK;
 }
 
@@ -260,9 +260,20 @@ static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, d
 
 }  // extern "C"
 int sgp_sweep_resident(sgp_ctx* ctx, bool time_main) {
-    if (ctx->N <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: no data (sgp_set_data)");
+    if (!ctx->have_data) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: no data (sgp_set_data)");
     SGP_RANGE("sgp_sweep");
     ctx->stats_of_data = false;
+    if (ctx->N == 0) {
+        // an empty data set (e.g. a rank whose shard is empty): all statistics are zero; under sharding the rank still takes part in the sum
+        if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: set_kernel and set_inducing first");
+        const size_t cnt = (size_t)ctx->M * ctx->M + (size_t)ctx->M + 4;
+        int rc0 = sgp_ensure_stats(ctx, cnt + 4); if (rc0) return rc0;
+        SGP_CUDA(ctx, cudaMemsetAsync(ctx->stats_dev, 0, cnt * sizeof(double), ctx->stream));
+        ctx->Dout = 1; ctx->have_stats = true; ctx->last_launches = 0; ctx->last_sweep_exchanged = false;
+        if (ctx->comm) { rc0 = sgp_comm_allreduce_stats(ctx, ctx->M, 1); if (rc0) return rc0; ctx->last_launches = 1; }
+        ctx->stats_of_data = true;
+        return SGP_OK;
+    }
     ctx->want_exchange = true;
     int rc = sgp_sweep_launch(ctx, ctx->X_dev, ctx->y_dev, ctx->have_yv ? ctx->yv_dev : nullptr, ctx->have_w ? ctx->w_dev : nullptr, ctx->N,
                               ctx->Ncap, time_main);

@@ -1,8 +1,8 @@
 // M x M factorisations of the path as ONE cooperative kernel per job (M = 20 ... 2048: latency-bound, so the design minimises the
 // critical path, not the FLOP count):
 //
-//   dense_job_kernel   [build A] -> blocked right-looking Cholesky -> [X = L^-1 by recursive doubling, S = X'X] -> [mu = S xi]
-//                      -> [transposed copy of L]
+//   dense_job_kernel   [build A] -> blocked right-looking Cholesky, with [X = L^-1 and S = X'X built row block by row block by the CTAs that
+//                      would otherwise wait for the diagonal-block factorisation] -> [mu = S xi] -> [transposed copy of L]
 //       build:  A = Lambda_prior + w Psi2 (the N-th `prod`), A = K_uu(Z) + jitter I, A = Sigma + mu mu', or A as given
 //       Cholesky, per 64-wide panel:  panel L21 = A21 Dinv'  (16 x 64 row strips, one per CTA)  | grid barrier |
 //                      trailing update in 32 x 32 sub-tiles over all CTAs, while CTA 0 updates the next diagonal block straight into
@@ -28,7 +28,7 @@ namespace {
 
 constexpr int TB = 64;        // panel width = diagonal block
 constexpr int CT = 256;       // threads per CTA (8 warps)
-constexpr int STAGE_A = TB * (32 + 4), STAGE_B = 64 * (TB + 4);          // staging of the largest tile configurations (Tile::LDA/LDB)
+constexpr int STAGE_A = TB * (64 + 4), STAGE_B = 64 * (TB + 4);          // staging of the largest tile configurations (Tile::LDA/LDB)
 constexpr int LDT = TB + 4;   // leading dimension of the 64 x 64 shared-memory blocks (= 4 mod 16: conflict-free DMMA fragment loads)
 constexpr int SMEM_DOUBLES = 2 * TB * LDT + TB + 2 + STAGE_A + STAGE_B;     // T | Xi | rdiag | progress word | As | Bs
 
@@ -208,6 +208,7 @@ __device__ __forceinline__ void store_task(const typename TL::Acc& acc, double* 
 using T64 = Tile<64, 64, 4, 32>;      // warp tile 16 x 32
 using T32 = Tile<32, 32, 4, 64>;      // warp tile  8 x 16: little MMA work per chunk, so a long chunk per barrier pair
 using T16 = Tile<16, 64, 2, 64>;      // row strip: warp tile 8 x 16
+using TX = Tile<64, 16, 8, 64>;       // column slice of a row block of X: warp tile 8 x 16
 
 // The 32 x 32 sub-tile task every phase is made of, as ONE non-inlined routine (the kernel's instruction footprint decides its speed: each
 // phase runs its code only a few times per launch).  C = alpha A B + beta C with the masks of store_task.
@@ -473,7 +474,7 @@ struct DenseJob {
     double* X; double* Tmp; double* S;     // optional: X = L^-1 (lower), S = X' X = (L L')^-1 full symmetric; Tmp = M x M scratch
     double* mu;                            // optional (needs S and xi): mu = S xi
     double* Ut;                            // optional: Ut = L' (upper triangular, strict lower part zero)
-    long long* clk;                        // optional: CTA 0's clocks {build, factor, panel, trailing, barriers, inverse, S, tail | inside factor: chol32, inv32, 32^3 products, write-out}
+    long long* clk;                        // optional: CTA 0's clocks {build, factor, panel, trailing (+ X rows / S updates on the last step), barriers, mu, last S update, tail | inside factor: ...}
 };
 
 __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant__ DenseJob j) {
@@ -530,25 +531,89 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
     DCLK(1);
     grid.sync();
     DCLK(4);
-    const int nwork = ncta > 1 ? ncta - 1 : 1, wid = ncta > 1 ? cta - 1 : 0;      // CTAs that take the trailing sub-tiles (CTA 0 factorises)
-    for (int k = 0; k + 1 < nblk; ++k) {
+    // The inverse rides along: while CTA 0 factorises diagonal block k + 1 (the critical path, ~24 k clocks), the other CTAs -- after the trailing
+    // update of step k -- build ROW BLOCK k of X = L^-1 and add row block k - 1 of X to S = X'X.  Right-looking, so that every task is short
+    // (K = 64): with P(i, j) = sum_{l <= k-2} L(i, l) X(l, j) kept up to date in `Tmp` for the rows below,
+    //     X(k, j) = -Dinv_k [ P(k, j) + L(k, k-1) X(k-1, j) ],   X(k, k) = Dinv_k,     then   P(i, j) += L(i, k-1) X(k-1, j)  for i > k.
+    // Everything read in a step was finished in an earlier one: no separate inverse phases, no extra grid barriers, and the workers stay inside
+    // CTA 0's factorisation window.
+    double* __restrict__ X = j.X;
+    auto x_row_tasks = [&](int k, int w, int nw) {            // row block k of X: 64 x 16 column slices, dealt over the workers w, w + nw, ...
+        const int kb = k * TB, nbk = min(TB, M - kb);
+        const double* Dk = j.Dinv + (size_t)k * TB * TB;
+        const int nsl = 4 * k;                                 // 16-column slices of the strictly lower part
+        for (int t = w; t <= nsl; t += nw) {
+            if (t == nsl) {                                    // the diagonal block: X(k, k) = Dinv_k
+                double v[TB * TB / CT];
+#pragma unroll
+                for (int q = 0; q < TB * TB / CT; ++q) v[q] = Dk[tid + q * CT];
+#pragma unroll
+                for (int q = 0; q < TB * TB / CT; ++q) {
+                    const int e = tid + q * CT, r = e % TB, c = e / TB;
+                    if (r < nbk && c < nbk) X[(size_t)(kb + r) + (size_t)(kb + c) * M] = v[q];
+                }
+                continue;
+            }
+            const int c0 = 16 * t;
+            double* Tt = j.Tmp + (size_t)kb + (size_t)c0 * M;  // P(k, slice), completed in place with the l = k - 1 term
+            TX::Acc acc; acc_zero<TX>(acc);
+            gemm_task<TX>(acc, A + (size_t)kb + (size_t)(kb - TB) * M, 1, (size_t)M, nbk, X + (size_t)(kb - TB) + (size_t)c0 * M, 1, (size_t)M, 16, TB, As, Bs);
+            store_task<TX>(acc, Tt, M, nbk, 16, 1.0, (c0 / TB == k - 1) ? 0.0 : 1.0);
+            __syncthreads();                                   // (the block reads back its own global stores)
+            TX::Acc acc2; acc_zero<TX>(acc2);
+            gemm_task<TX>(acc2, Dk, 1, (size_t)TB, nbk, Tt, 1, (size_t)M, 16, nbk, As, Bs);
+            store_task<TX>(acc2, X + (size_t)kb + (size_t)c0 * M, M, nbk, 16, -1.0, 0.0);
+        }
+    };
+    auto p_update_tasks = [&](int k, int w, int nw) {         // P(i, j) (+)= L(i, k-1) X(k-1, j) for the rows below block k, columns left of block k
+        if (k < 1) return;
+        const int R1 = (k + 1) * TB, kb1 = (k - 1) * TB;
+        if (R1 >= M) return;
+        const int nr = (M - R1 + 31) / 32, nc = 2 * k;
+        for (int t = w; t < nr * nc; t += nw) {
+            const int r0 = R1 + 32 * (t % nr), c0 = 32 * (t / nr), rows = min(32, M - r0);
+            const Task32 tk{A + (size_t)r0 + (size_t)kb1 * M, 1, (size_t)M, rows, X + (size_t)kb1 + (size_t)c0 * M, 1, (size_t)M, 32, TB,
+                            j.Tmp + (size_t)r0 + (size_t)c0 * M, M, 1.0, (c0 / TB == k - 1) ? 0.0 : 1.0, nullptr, false, 0, 0, tk32};
+            run_task32(tk, As, Bs);
+        }
+    };
+    auto s_update_tasks = [&](int kk, int w, int nw, bool last) {     // S(a, b) (+)= X(kk, a)' X(kk, b) over the 32 x 32 sub-tiles b <= a of the first kk + 1 blocks
+        const int kb = kk * TB, nbk = min(TB, M - kb);
+        const int n32 = (min(M, kb + TB) + 31) / 32, ntask = n32 * (n32 + 1) / 2;
+        for (int t = w; t < ntask; t += nw) {
+            int a = 0;
+            while ((a + 1) * (a + 2) / 2 <= t) ++a;
+            const int b = t - a * (a + 1) / 2;
+            const int r0 = 32 * a, c0 = 32 * b, rows = min(32, M - r0), cols = min(32, M - c0);
+            const bool first = (r0 / TB) == kk;                // row block kk is the first one with a non-zero X(kk, column block of a)
+            const Task32 tk{X + (size_t)kb + (size_t)r0 * M, (size_t)M, 1, rows, X + (size_t)kb + (size_t)c0 * M, 1, (size_t)M, cols, nbk,
+                            j.S + (size_t)r0 + (size_t)c0 * M, M, 1.0, first ? 0.0 : 1.0, last ? j.S + (size_t)c0 + (size_t)r0 * M : nullptr, a == b, r0, c0, tk32};
+            run_task32(tk, As, Bs);
+        }
+    };
+    for (int k = 0; k < nblk; ++k) {
+        const bool has_next = k + 1 < nblk;
         const int k0 = k * TB, R0 = k0 + TB;                   // trailing matrix starts at row / column R0
         const double* Dk = j.Dinv + (size_t)k * TB * TB;
-        // panel: 16-row strips of A[R0:, k0:k0+64] <- strip * Dk'   (in place: a strip is private to its CTA)
-        const int nstrips = (M - R0 + 15) / 16;
-        for (int s = cta; s < nstrips; s += ncta) {
-            const int r0 = R0 + 16 * s, rows = min(16, M - r0);
-            double* Ar = A + (size_t)r0 + (size_t)k0 * M;
-            T16::Acc acc; acc_zero<T16>(acc);
-            gemm_task<T16>(acc, Ar, 1, (size_t)M, rows, Dk, (size_t)TB, 1, TB, TB, As, Bs);      // B(kk, c) = Dk(c, kk)
-            store_task<T16>(acc, Ar, M, rows, TB, 1.0, 0.0);
+        if (has_next) {
+            // panel: 16-row strips of A[R0:, k0:k0+64] <- strip * Dk'   (in place: a strip is private to its CTA)
+            const int nstrips = (M - R0 + 15) / 16;
+            for (int s = cta; s < nstrips; s += ncta) {
+                const int r0 = R0 + 16 * s, rows = min(16, M - r0);
+                double* Ar = A + (size_t)r0 + (size_t)k0 * M;
+                T16::Acc acc; acc_zero<T16>(acc);
+                gemm_task<T16>(acc, Ar, 1, (size_t)M, rows, Dk, (size_t)TB, 1, TB, TB, As, Bs);      // B(kk, c) = Dk(c, kk)
+                store_task<T16>(acc, Ar, M, rows, TB, 1.0, 0.0);
+            }
+            DCLK(2);
+            grid.sync();
+            DCLK(4);
         }
-        DCLK(2);
-        grid.sync();
-        DCLK(4);
-        // trailing update A[i, c] -= sum_kk L[i, k0 + kk] L[c, k0 + kk] on the lower triangle of A[R0:, R0:]
-        const int nbn = min(TB, M - R0);
-        if (cta == 0) {     // next diagonal block: updated straight into shared memory and factorised there
+        // CTA 0 factorises the next diagonal block; everybody else: trailing update, row block k of X, row block k - 1 of X into S
+        const bool factoring = has_next && cta == 0 && ncta > 1;
+        const int nwork = (has_next && ncta > 1) ? ncta - 1 : ncta, wid = (has_next && ncta > 1) ? cta - 1 : cta;
+        if (has_next && cta == 0) {     // next diagonal block: A[i, c] -= sum_kk L[i, k0 + kk] L[c, k0 + kk], straight into shared memory, factorised there
+            const int nbn = min(TB, M - R0);
             load_diag_smem(T, A + (size_t)R0 * ((size_t)M + 1), M, nbn);
             T64::Acc acc; acc_zero<T64>(acc);
             gemm_task<T64>(acc, A + (size_t)R0 + (size_t)k0 * M, 1, (size_t)M, nbn, A + (size_t)R0 + (size_t)k0 * M, (size_t)M, 1, nbn, TB, As, Bs, tk64);
@@ -569,94 +634,48 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
             factor_diag_smem(T, Xi, rdiag, Lc, A + (size_t)R0 * ((size_t)M + 1), M, nbn, R0, j.Dinv + (size_t)(k + 1) * TB * TB, j.info, fst);
             DCLK(1);
         }
-        if (cta > 0 || ncta == 1) {
-            const int n32 = (M - R0 + 31) / 32;
-            const int ntask = n32 * (n32 + 1) / 2 - (n32 >= 2 ? 3 : 1);            // the sub-tiles of the first 64 x 64 block belong to CTA 0
-            for (int t = wid; t < ntask; t += nwork) {
-                const int tt = t + 3;
-                int a = 0;
-                while ((a + 1) * (a + 2) / 2 <= tt) ++a;
-                const int b = tt - a * (a + 1) / 2;
-                const int r0 = R0 + 32 * a, c0 = R0 + 32 * b, rows = min(32, M - r0), cols = min(32, M - c0);
-                const Task32 tk{A + (size_t)r0 + (size_t)k0 * M, 1, (size_t)M, rows, A + (size_t)c0 + (size_t)k0 * M, (size_t)M, 1, cols, TB,
-                                A + (size_t)r0 + (size_t)c0 * M, M, -1.0, 1.0, nullptr, a == b, r0, c0, tk32};
-                run_task32(tk, As, Bs);
+        if (!factoring) {
+            if (has_next) {         // trailing update on the lower triangle of A[R0:, R0:] (the sub-tiles of its first 64 x 64 block belong to CTA 0)
+                const int n32 = (M - R0 + 31) / 32;
+                const int ntask = n32 * (n32 + 1) / 2 - (n32 >= 2 ? 3 : 1);
+                for (int t = wid; t < ntask; t += nwork) {
+                    const int tt = t + 3;
+                    int a = 0;
+                    while ((a + 1) * (a + 2) / 2 <= tt) ++a;
+                    const int b = tt - a * (a + 1) / 2;
+                    const int r0 = R0 + 32 * a, c0 = R0 + 32 * b, rows = min(32, M - r0), cols = min(32, M - c0);
+                    const Task32 tk{A + (size_t)r0 + (size_t)k0 * M, 1, (size_t)M, rows, A + (size_t)c0 + (size_t)k0 * M, (size_t)M, 1, cols, TB,
+                                    A + (size_t)r0 + (size_t)c0 * M, M, -1.0, 1.0, nullptr, a == b, r0, c0, tk32};
+                    run_task32(tk, As, Bs);
+                }
+            }
+            if (X) {
+                // (workers are dealt from the far end for the X rows so that the CTAs that got the last trailing sub-tiles are not the first here)
+                x_row_tasks(k, nwork - 1 - wid, nwork);
+                p_update_tasks(k, wid, nwork);
+                if (j.S && k > 0) s_update_tasks(k - 1, wid, nwork, false);
             }
         }
         DCLK(3);
         grid.sync();
         DCLK(4);
     }
-
-    // ---- X = L^-1 (recursive doubling from the diagonal-block inverses), S = X' X ----------------------------------------------------
-    if (j.X) {
-        double* __restrict__ X = j.X;
-        for (int b = cta; b < nblk; b += ncta) {
-            const int nb = min(TB, M - b * TB);
-            double v[TB * TB / CT];
+    if (X && j.S) {       // the last row block of X into S (every tile receives its last contribution here: mirrored on the way out), then mu = S xi
+        s_update_tasks(nblk - 1, cta, ncta, true);
+        DCLK(6);
+        if (j.mu) {
+            grid.sync();
+            // mu = S xi: a warp per column of the symmetric S (fixed-shape tree: deterministic)
+            for (int i = cta * (CT / 32) + warp; i < M; i += ncta * (CT / 32)) {
+                const double* col = j.S + (size_t)i * M;
+                double v = 0.0;
+                for (int r = lane; r < M; r += 32) v = fma(col[r], j.xi[r], v);
 #pragma unroll
-            for (int q = 0; q < TB * TB / CT; ++q) v[q] = j.Dinv[(size_t)b * TB * TB + tid + q * CT];
-#pragma unroll
-            for (int q = 0; q < TB * TB / CT; ++q) {
-                const int e = tid + q * CT, r = e % TB, c = e / TB;
-                if (r < nb && c < nb) X[(size_t)(b * TB + r) + (size_t)(b * TB + c) * M] = v[q];
-            }
-        }
-        grid.sync();
-        for (int bs = 1; bs < nblk; bs *= 2) {                      // merge blocks of bs tiles into blocks of 2 bs tiles
-            const int npairs = (nblk + 2 * bs - 1) / (2 * bs);
-            // phase 0: Tmp21 = L21 X11  (K from the column sub-block's first row to the end of the top half)
-            // phase 1: X21 = -X22 Tmp21 (K from the start of the bottom half to the row sub-block's last row)
-            for (int phase = 0; phase < 2; ++phase) {
-                int task = 0;
-                for (int pr = 0; pr < npairs; ++pr) {
-                    const int top = pr * 2 * bs * TB, mid = top + bs * TB, bot = min(top + 2 * bs * TB, M);
-                    if (mid >= M) continue;
-                    const int nr = (bot - mid + 31) / 32, ncol = (mid - top) / 32;
-                    const int first = ((cta - task) % ncta + ncta) % ncta;         // this CTA's first sub-tile of the pair
-                    for (int q = first; q < nr * ncol; q += ncta) {
-                        const int r0 = mid + 32 * (q % nr), c0 = top + 32 * (q / nr);
-                        const int rows = min(32, M - r0);
-                        Task32 tk;
-                        if (phase == 0)
-                            tk = Task32{A + (size_t)r0 + (size_t)c0 * M, 1, (size_t)M, rows, X + (size_t)c0 + (size_t)c0 * M, 1, (size_t)M, 32, mid - c0,
-                                        j.Tmp + (size_t)r0 + (size_t)c0 * M, M, 1.0, 0.0, nullptr, false, 0, 0, tk32};
-                        else
-                            tk = Task32{X + (size_t)r0 + (size_t)mid * M, 1, (size_t)M, rows, j.Tmp + (size_t)mid + (size_t)c0 * M, 1, (size_t)M, 32,
-                                        min(r0 + 32, M) - mid, X + (size_t)r0 + (size_t)c0 * M, M, -1.0, 0.0, nullptr, false, 0, 0, tk32};
-                        run_task32(tk, As, Bs);
-                    }
-                    task += nr * ncol;
-                }
-                grid.sync();
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) j.mu[i] = v;
             }
         }
         DCLK(5);
-        if (j.S) {        // S[i, c] = sum_{k >= i} X[k, i] X[k, c] for c <= i (32 x 32 sub-tiles, longest K first), mirrored
-            const int n32 = (M + 31) / 32, ntask = n32 * (n32 + 1) / 2;
-            for (int t = cta; t < ntask; t += ncta) {
-                int a = 0;
-                while ((a + 1) * (a + 2) / 2 <= t) ++a;
-                const int b = t - a * (a + 1) / 2;
-                const int r0 = 32 * a, c0 = 32 * b, rows = min(32, M - r0), cols = min(32, M - c0);
-                const Task32 tk{X + (size_t)r0 + (size_t)r0 * M, (size_t)M, 1, rows, X + (size_t)r0 + (size_t)c0 * M, 1, (size_t)M, cols, M - r0,
-                                j.S + (size_t)r0 + (size_t)c0 * M, M, 1.0, 0.0, j.S + (size_t)c0 + (size_t)r0 * M, a == b, r0, c0, tk32};
-                run_task32(tk, As, Bs);
-            }
-            if (j.mu) {
-                grid.sync();
-                // mu = S xi: a warp per column of the symmetric S (fixed-shape tree: deterministic)
-                for (int i = cta * (CT / 32) + warp; i < M; i += ncta * (CT / 32)) {
-                    const double* col = j.S + (size_t)i * M;
-                    double v = 0.0;
-                    for (int r = lane; r < M; r += 32) v = fma(col[r], j.xi[r], v);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == 0) j.mu[i] = v;
-                }
-            }
-        }
-        DCLK(6);
     }
 
     // ---- tail: zero the strict upper triangle of L; Ut = L' -----------------------------------------------------------------------------
@@ -750,7 +769,7 @@ int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in) {
         SGP_CUDA(ctx, cudaMemcpyAsync(c, clk_dev, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
         SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(clk_dev);
-        printf("dense job M=%d build=%d grid=%d: clocks build %lld | factor %lld | panel %lld | trailing %lld | barriers %lld | inverse %lld | S+mu %lld | tail %lld || factor: chol32 %lld | inv32 %lld | products %lld | write-out %lld\n",
+        printf("dense job M=%d build=%d grid=%d: clocks build %lld | factor %lld | panel %lld | trailing %lld | barriers %lld | mu %lld | last S update %lld | tail %lld || factor: chol32 %lld | inv32 %lld | products %lld | write-out %lld\n",
                M, in.build, grid, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10], c[11]);
         printf("    CTA 0's 32x32 tasks: %lld tasks, %lld chunks: barrier %lld | load+stage %lld | mma %lld ;  64x64 diagonal updates: barrier %lld | load+stage %lld | mma %lld\n",
                c[15], c[16], c[12], c[13], c[14], c[20], c[21], c[22]);

@@ -39,7 +39,7 @@ struct sgp_ctx {
     int64_t N = 0, Ncap = 0;        // Ncap: allocated points (multiple of the chunk size, zero padded)
     int Dcap = 0;                   // input dimension the owned X buffer was allocated for
     double *X_dev = nullptr, *y_dev = nullptr, *yv_dev = nullptr, *w_dev = nullptr;
-    bool own_data = false, have_yv = false, have_w = false;
+    bool own_data = false, have_yv = false, have_w = false, have_data = false;     // have_data: sgp_set_data[_dev] was called (N may be 0)
 
     // statistics of the last sweep: stats_dev = [psi2 (M*M) | psi1 (M*Dout) | psi0 | sum_y2 | sum_w | n]
     double* stats_dev = nullptr;
@@ -55,6 +55,7 @@ struct sgp_ctx {
     double* kbuf_dev = nullptr;  size_t kbuf_cap = 0;      // L2-resident K_uf panel of one slab (generate-once sweep)
     double* fetch_host = nullptr; size_t fetch_cap = 0;    // pinned staging of the small results (Psi1 | scalars)
     void* flush_dev = nullptr; size_t flush_cap = 0;       // L2 flush buffer of sgp_sweep_timed_flushed
+    unsigned sweep_bar_epoch = 0;                          // launch counter of the plain-launch grid barrier (SGP_SWEEP_COOP=0)
     unsigned* sweep_flags_dev = nullptr;                   // generation / consumption counters of the generate-once sweep
     double* exptab_dev = nullptr;
     double* dense_dev = nullptr; size_t dense_cap = 0;     // M x M scratch for factorisations

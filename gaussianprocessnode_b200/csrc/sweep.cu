@@ -80,7 +80,7 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     int rc = sgp_ensure(ctx, &ctx->work_dev, &ctx->work_cap, need_work); if (rc) return rc;
     const int nring = nslabs > 2 ? 3 : nslabs;
     rc = sgp_ensure(ctx, &ctx->kbuf_dev, &ctx->kbuf_cap, (size_t)nring * slab_chunks * chunk_doubles); if (rc) return rc;
-    if (3 * (nblk + 1) > 1024) return 1;
+    if (3 * (nblk + 1) > 1000) return 1;
     if (!ctx->sweep_flags_dev) {      // zeroed once; every sweep kernel leaves the counters zeroed when it ends
         SGP_CUDA(ctx, cudaMalloc((void**)&ctx->sweep_flags_dev, 1024 * sizeof(unsigned)));
         SGP_CUDA(ctx, cudaMemsetAsync(ctx->sweep_flags_dev, 0, 1024 * sizeof(unsigned), ctx->stream));
@@ -99,6 +99,14 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     p.log_var_s = SGP_EXP_SCALE * std::log(ctx->variance); p.variance = ctx->variance;
     p.Z = ctx->Z_dev; p.exptab = ctx->exptab_dev; p.Kbuf = ctx->kbuf_dev; p.flags = ctx->sweep_flags_dev;
     p.slab_doubles = (long long)(slab_chunks * chunk_doubles); p.nring = nring;
+    // launch form: cooperative (co-residency of the persistent CTAs guaranteed by the driver) unless SGP_SWEEP_COOP=0 asks for a plain launch
+    // with the kernel's own ticket barrier (the grid is one CTA per SM: resident as long as nothing else occupies the device)
+    {
+        const char* e = std::getenv("SGP_SWEEP_COOP");
+        p.coop = (e && e[0] == '0') ? 0 : 1;
+        p.gbar = ctx->sweep_flags_dev + 1000;          // (the dependency counters use the first 3 (nblk + 1) <= 1000 words)
+        p.bar_epoch = ++ctx->sweep_bar_epoch;
+    }
     p.partial = ctx->work_dev; p.psi1_partial = p.partial + (size_t)nslots * TM * TM; p.scal_partial = p.psi1_partial + (size_t)ncta * TM;
     p.psi2 = ctx->stats_dev; p.psi1 = p.psi2 + (size_t)M * M; p.scal = p.psi1 + M;
     // multi-GPU: phase 2 pushes this rank's statistics (Psi2 as the packed lower triangle) into its slot on every rank, and the kernel's tail adds

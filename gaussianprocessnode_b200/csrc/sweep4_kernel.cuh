@@ -65,6 +65,9 @@ struct Params {
     double center[SGP_MAX_D];
     double log_var_s;
     double variance;
+    unsigned* gbar;               // {ticket, go} words of the hand-rolled grid barrier (plain launch: SGP_SWEEP_COOP=0)
+    unsigned bar_epoch;           // ... value of `go` that releases this launch
+    int coop;                     // 1: cooperative launch (grid.sync), 0: plain launch + ticket barrier
     SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none): phase 2 then writes [packed lower triangle of Psi2 | Psi1 | scalars] into this rank's contribution buffer
     double* stats_out;            // ... and the sums over the ranks land here (full symmetric Psi2 | Psi1 | scalars); = psi2 without exchange
 };
@@ -868,7 +871,21 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
             if (lane < 4) p.psi1_partial[(size_t)bcta * TM + warp * (8 * RB) + rb * 8 + 2 * lane + v] = x;
         }
     __threadfence();
-    grid.sync();
+    if (p.coop) grid.sync();
+    else {   // plain launch (one CTA per SM, all resident): the last CTA to take a ticket releases everybody; a lost CTA traps after the time-out
+        __syncthreads();
+        if (tid == 0) {
+            if (atomicAdd(p.gbar, 1u) == (unsigned)p.ncta - 1u) {
+                p.gbar[0] = 0u;
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p.gbar + 1), "r"(p.bar_epoch) : "memory");
+            } else {
+                const long long t0 = clock64();
+                while (ld_acquire(p.gbar + 1) != p.bar_epoch) { if (clock64() - t0 > (1ll << 33)) __trap(); }
+            }
+        }
+        __syncthreads();
+    }
     if (p.dbg) t_k3 = clock64();
     long long tr[3] = {0, 0, 0};
     reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)), tr);
@@ -903,7 +920,8 @@ int launch4_t(sgp_ctx* ctx, const Params& p, bool weighted, int grid) {
     auto kern = weighted ? sweep4_kernel<TM, NB, DPAD, NT, KIND, true> : sweep4_kernel<TM, NB, DPAD, NT, KIND, false>;
     SGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
     void* args[] = {const_cast<Params*>(&p)};
-    SGP_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NT), args, S::bytes, ctx->stream));
+    if (p.coop) SGP_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NT), args, S::bytes, ctx->stream));
+    else SGP_CUDA(ctx, cudaLaunchKernel((const void*)kern, dim3(grid), dim3(NT), args, S::bytes, ctx->stream));
     ctx->last_grid = grid; ctx->last_block = NT; ctx->last_smem = (int)S::bytes;
     SGP_CUDA(ctx, cudaGetLastError());
     return SGP_OK;

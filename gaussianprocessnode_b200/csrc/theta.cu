@@ -160,7 +160,7 @@ __global__ void amat_kernel(double* __restrict__ A, double* __restrict__ Rv, con
 extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const double* Uv, double w, double jitter, double* value,
                                    double* dvariance, double* dlengthscale) {
     if (!ctx) return SGP_ERR_ARG;
-    if (!ctx->have_kernel || !ctx->have_Z || ctx->N <= 0) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: set_kernel, set_inducing and set_data first");
+    if (!ctx->have_kernel || !ctx->have_Z || !ctx->have_data) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: set_kernel, set_inducing and set_data first");
     if ((mu_v == nullptr) != (Uv == nullptr)) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: pass both mu_v and Uv, or neither (resident posterior)");
     if (!mu_v && !(sgp_resident_mu(ctx) && sgp_resident_sigma(ctx))) SGP_FAIL(ctx, SGP_ERR_ARG, "theta_objective: no resident posterior (sgp_posterior_v first)");
     if (ctx->have_w) SGP_FAIL(ctx, SGP_ERR_UNSUPPORTED, "theta_objective: per-point weights are not part of the reference objective");

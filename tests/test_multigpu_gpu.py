@@ -143,3 +143,46 @@ def test_four_gpu_sharded_sweep_matches_single_gpu():
     for r in res.values():
         assert max(r[:4]) <= 1e-12 and r[4] and r[6] == 1, res
     assert len({r[5] for r in res.values()}) == 1, "every rank must hold bitwise identical statistics"
+
+
+def _worker_uneven(rank, world, port, out):
+    """Ragged and EMPTY shards: 33 points over two ranks, then a single point (rank 1 owns nothing and still takes part in the sum)."""
+    import torch
+    import torch.distributed as dist
+    from gaussianprocessnode_b200 import SGPContext, shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    uid = [SGPContext.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    rng = np.random.default_rng(2)
+    errs = []
+    ctx = SGPContext(rank); single = SGPContext(rank)
+    first = True
+    for M in (600, 40):
+        for N in (33, 1):
+            D = 3
+            X = rng.normal(size=(N, D)); y = rng.normal(size=N); Z = rng.normal(size=(M, D)); ell = np.full(D, 1.3)
+            ctx.set_kernel(1.0, ell); ctx.set_inducing(Z)
+            if first:
+                sw = shard.ShardedSweep(ctx, world, rank, uid[0]); first = False
+            sw.set_data(X, y)
+            p0, p1, p2, sy = sw.sweep_psi()
+            single.set_kernel(1.0, ell); single.set_inducing(Z); single.set_data(X, y)
+            f0, f1, f2, fy = single.sweep_psi()
+            errs += [float(np.linalg.norm(p2 - f2) / np.linalg.norm(f2)), float(np.linalg.norm(p1 - f1) / max(np.linalg.norm(f1), 1e-300)), abs(p0 - f0), abs(sy - fy) / max(abs(fy), 1e-300)]
+    ctx.close(); single.close()
+    out[rank] = max(errs)
+    dist.destroy_process_group()
+
+
+def test_two_gpu_ragged_and_empty_shards():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_uneven, args=(2, _free_port(), out), nprocs=2, join=True)
+        res = dict(out)
+    assert set(res) == {0, 1} and max(res.values()) <= 1e-12, res

@@ -228,3 +228,32 @@ def test_first_fused_kernel_still_matches(ctx, monkeypatch):
     rng = np.random.default_rng(77)
     X = rng.normal(size=(5000, 8)); Z = rng.normal(size=(300, 8)); y = rng.normal(size=5000)
     _check(ctx, X, y, Z, 1.1, np.full(8, 1.7))
+
+
+@pytest.mark.parametrize("M", [48, 512])
+def test_empty_data_set_gives_zero_statistics(ctx, M):
+    # a rank whose shard is empty still calls the sweep: zeros, not an error (and the following M x M calls see zero statistics)
+    rng = np.random.default_rng(0)
+    Z = rng.normal(size=(M, 3))
+    ctx.set_kernel(1.0, np.full(3, 1.0)); ctx.set_inducing(Z); ctx.set_data(np.zeros((0, 3)), np.zeros(0))
+    p0, p1, p2, sy = ctx.sweep_psi()
+    assert p0 == 0.0 and sy == 0.0 and not p1.any() and not p2.any()
+    mu, Sig, Uv = ctx.posterior_v(np.zeros(M), np.eye(M) / 4.0, 10.0)
+    assert np.allclose(mu, 0.0) and np.allclose(Sig, 4.0 * np.eye(M), rtol=1e-13, atol=1e-13)
+
+
+def test_single_and_double_slab_policy_matches_forced_ring(ctx, monkeypatch):
+    # small sweeps run as one (<= 64 MB of K_uf) or two (<= 96 MB) slabs; the same numbers as the forced 3-panel ring of small panels
+    rng = np.random.default_rng(4)
+    D, M = 8, 512
+    Z = rng.normal(size=(M, D))
+    for N in (9000, 19000):                        # 38 MB -> one slab, 80 MB -> two slabs
+        X = rng.normal(size=(N, D)); y = np.sin(X[:, 1])
+        ctx.set_kernel(1.0, np.full(D, 2.0)); ctx.set_inducing(Z); ctx.set_data(X, y)
+        a = ctx.sweep_psi()
+        monkeypatch.setenv("SGP_SWEEP_SLAB_MB", "7")
+        b = ctx.sweep_psi()
+        monkeypatch.delenv("SGP_SWEEP_SLAB_MB")
+        assert fro(a[2], b[2]) < 1e-14 and fro(a[1], b[1]) < 1e-14 and a[0] == b[0]
+        o = batched.psi_stats_point(X, y, Z, 1.0, np.full(D, 2.0))
+        assert fro(a[2], o[2]) < 1e-13 and fro(a[1], o[1]) < 1e-13
