@@ -3,6 +3,7 @@
 #include "sgp_internal.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -486,19 +487,26 @@ __global__ void isotropic_kernel(double* __restrict__ A, int M, double diag) {
 
 // The N-th prod on the resident prior: Lambda = Lambda_p + w Psi2, xi = xi_p + w Psi1 -> Sigma, mu (and, when the host wants it, Uv).
 // carry: the posterior's natural parameters become the resident prior (the streaming schedule of regression_kin40k.ipynb:200-213).
-// Two cooperative launches at most: [Lambda -> L -> L^-1 -> Sigma = L^-T L^-1 -> mu] and [Sigma + mu mu' -> its Cholesky factor -> Uv];
-// the device-to-host copies of Sigma / mu run on the second stream while the second launch factorises.
+// ONE cooperative launch: [J Lambda J -> L -> X = L^-1 -> Sigma = J X'X J -> mu -> Uv = G (J X J)] (dense_coop.cu).  The older two-launch
+// form [Lambda -> ... -> mu] + [Sigma + mu mu' -> its Cholesky factor -> Uv] remains for M > SGP_FLIP_UV_MAX_M and as a cross-check
+// (SGP_DENSE_UV2=1); there the device-to-host copies of Sigma / mu run on the second stream while the second launch factorises.
 static int posterior_core(sgp_ctx* ctx, double w, bool carry, bool want_uv, double* mu_v, double* Sigma_v, double* Uv_host) {
     const int M = ctx->M; const size_t MM = (size_t)M * M;
     double* d = ctx->dense_dev + 64;
     double *Lam = d, *X = d + MM, *T = d + 3 * MM, *xi = d + 4 * MM;
     double* psi2 = ctx->stats_dev; double* psi1 = psi2 + MM;
     int rc = sgp_ensure_zero(ctx, &ctx->dinv_dev, &ctx->dinv_cap, (size_t)((M + 63) / 64) * 64 * 64); if (rc) return rc;
+    // Reversed-order factorisation (default): the inverse of that factor IS the Cholesky factor of Sigma, and Uv follows from it by the
+    // closed-form rank-one update inside the same launch.  SGP_DENSE_UV2=1 (or M > SGP_FLIP_UV_MAX_M) keeps the second factorisation.
+    static const bool two_jobs = std::getenv("SGP_DENSE_UV2") != nullptr && std::atoi(std::getenv("SGP_DENSE_UV2")) != 0;
+    const bool flip = !two_jobs && M <= SGP_FLIP_UV_MAX_M;
     SgpDenseJob a;
     a.M = M; a.build = 1; a.S2 = psi2; a.s1 = psi1; a.P = post_LamP(ctx); a.xip = post_xiP(ctx); a.xi = xi; a.w = w; a.carry = carry ? 1 : 0;
     a.A = Lam; a.Dinv = ctx->dinv_dev; a.X = X; a.Tmp = T; a.S = post_Sig(ctx); a.mu = post_mu(ctx);
+    if (flip) { a.flip = 1; a.S = d + 2 * MM; a.Sout = post_Sig(ctx); if (want_uv) a.Uv = post_Uv(ctx); }
     rc = sgp_dense_job(ctx, a); if (rc) return rc;
-    ctx->have_post = true; ctx->have_post_uv = false;
+    ctx->have_post = true; ctx->have_post_uv = flip && want_uv;
+    if (flip) want_uv = false;                                  // (done)
     const bool early = (Sigma_v || mu_v) && want_uv;            // something to copy while the second factorisation runs
     if (early) {
         SGP_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));

@@ -30,6 +30,8 @@ constexpr int TB = 64;        // panel width = diagonal block
 constexpr int CT = 256;       // threads per CTA (8 warps)
 constexpr int STAGE_A = TB * (64 + 4), STAGE_B = 64 * (TB + 4);          // staging of the largest tile configurations (Tile::LDA/LDB)
 constexpr int LDT = TB + 4;   // leading dimension of the 64 x 64 shared-memory blocks (= 4 mod 16: conflict-free DMMA fragment loads)
+static_assert(4 * SGP_FLIP_UV_MAX_M <= 2 * 64 * 68 + 66 + 2 * 64 * 68, "p, G and the scan buffers in shared memory");
+constexpr int kPParts = 4;    // partial sums per row strip of p = X xi (more CTAs on a memory-latency-bound pass)
 constexpr int SMEM_DOUBLES = 2 * TB * LDT + TB + 2 + STAGE_A + STAGE_B;     // T | Xi | rdiag | progress word | As | Bs
 
 // ---- tile GEMM task: acc (+)= sum_{k < K} A(r, k) B(k, c) for a TR x TC tile, 8 warps arranged WR x (8 / WR) ------------------------
@@ -218,6 +220,13 @@ struct Task32 {
     double* C; int ldc; double alpha, beta; double* Ct; bool lower_only; int grow0, gcol0;
     long long* tk;
 };
+// ... and the 64 x 64 tile form (a quarter of the operand traffic per flop: what the worker CTAs run beside CTA 0's factorisations)
+__device__ __noinline__ void run_task64(const Task32& t, double* __restrict__ As, double* __restrict__ Bs) {
+    T64::Acc acc; acc_zero<T64>(acc);
+    gemm_task<T64>(acc, t.A, t.a_rs, t.a_ks, t.rows, t.B, t.b_ks, t.b_cs, t.cols, t.K, As, Bs, t.tk);
+    if (t.tk) { t.tk[3] += 1; t.tk[4] += (t.K + T64::KC - 1) / T64::KC; }
+    store_task<T64>(acc, t.C, t.ldc, t.rows, t.cols, t.alpha, t.beta, t.Ct, t.lower_only, t.grow0, t.gcol0);
+}
 __device__ __noinline__ void run_task32(const Task32& t, double* __restrict__ As, double* __restrict__ Bs) {
     T32::Acc acc; acc_zero<T32>(acc);
     gemm_task<T32>(acc, t.A, t.a_rs, t.a_ks, t.rows, t.B, t.b_ks, t.b_cs, t.cols, t.K, As, Bs, t.tk);
@@ -474,6 +483,9 @@ struct DenseJob {
     double* X; double* Tmp; double* S;     // optional: X = L^-1 (lower), S = X' X = (L L')^-1 full symmetric; Tmp = M x M scratch
     double* mu;                            // optional (needs S and xi): mu = S xi
     double* Ut;                            // optional: Ut = L' (upper triangular, strict lower part zero)
+    int flip;                              // build 1 only: factorise J A J (J = index reversal); S is then scratch and Sout / mu / Uv are delivered un-reversed
+    double* Sout;                          // flip: A^-1 (full symmetric)
+    double* Uv;                            // flip, optional (needs mu, M <= kFlipUvMaxM): upper Cholesky factor of A^-1 + mu mu'
     long long* clk;                        // optional: CTA 0's clocks {build, factor, panel, trailing (+ X rows / S updates on the last step), barriers, mu, last S update, tail | inside factor: ...}
 };
 
@@ -494,10 +506,23 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
 
     // ---- build -------------------------------------------------------------------------------------------------------------------
     if (j.build == 1) {
-        for (size_t e = (size_t)cta * CT + tid; e < MM; e += (size_t)ncta * CT) {
-            const double a = fma(j.w, j.S2[e], j.P[e]);
-            A[e] = a;
-            if (j.carry) j.P[e] = a;
+        const size_t stride = (size_t)ncta * CT;
+        for (size_t e0 = (size_t)cta * CT + tid; e0 < MM; e0 += 4 * stride) {        // (four independent loads in flight per thread)
+            double s2[4], pr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const size_t e = e0 + u * stride, src = j.flip ? MM - 1 - e : e;     // (reversing rows and columns reverses the column-major index)
+                if (e < MM) { s2[u] = j.S2[src]; pr[u] = j.P[src]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const size_t e = e0 + u * stride, src = j.flip ? MM - 1 - e : e;
+                if (e < MM) {
+                    const double a = fma(j.w, s2[u], pr[u]);
+                    A[e] = a;
+                    if (j.carry) j.P[src] = a;
+                }
+            }
         }
         if (cta == ncta - 1)
             for (int e = tid; e < M; e += CT) {
@@ -506,6 +531,7 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
                 if (j.carry) j.xip[e] = x;
             }
     } else if (j.build == 2) {
+#pragma unroll 2
         for (size_t e = (size_t)cta * CT + tid; e < MM; e += (size_t)ncta * CT) {
             const int r = (int)(e % M), c = (int)(e / M);
             double r2 = 0.0;
@@ -538,57 +564,78 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
     // Everything read in a step was finished in an earlier one: no separate inverse phases, no extra grid barriers, and the workers stay inside
     // CTA 0's factorisation window.
     double* __restrict__ X = j.X;
-    auto x_row_tasks = [&](int k, int w, int nw) {            // row block k of X: 64 x 16 column slices, dealt over the workers w, w + nw, ...
+    auto x_slice = [&](int k, int t) {                        // slice t of row block k of X (64 x 16 columns; t == 4 k: the diagonal block)
         const int kb = k * TB, nbk = min(TB, M - kb);
         const double* Dk = j.Dinv + (size_t)k * TB * TB;
-        const int nsl = 4 * k;                                 // 16-column slices of the strictly lower part
-        for (int t = w; t <= nsl; t += nw) {
-            if (t == nsl) {                                    // the diagonal block: X(k, k) = Dinv_k
-                double v[TB * TB / CT];
+        if (t == 4 * k) {                                      // X(k, k) = Dinv_k
+            double v[TB * TB / CT];
 #pragma unroll
-                for (int q = 0; q < TB * TB / CT; ++q) v[q] = Dk[tid + q * CT];
+            for (int q = 0; q < TB * TB / CT; ++q) v[q] = Dk[tid + q * CT];
 #pragma unroll
-                for (int q = 0; q < TB * TB / CT; ++q) {
-                    const int e = tid + q * CT, r = e % TB, c = e / TB;
-                    if (r < nbk && c < nbk) X[(size_t)(kb + r) + (size_t)(kb + c) * M] = v[q];
-                }
-                continue;
+            for (int q = 0; q < TB * TB / CT; ++q) {
+                const int e = tid + q * CT, r = e % TB, c = e / TB;
+                if (r < nbk && c < nbk) X[(size_t)(kb + r) + (size_t)(kb + c) * M] = v[q];
             }
-            const int c0 = 16 * t;
-            double* Tt = j.Tmp + (size_t)kb + (size_t)c0 * M;  // P(k, slice), completed in place with the l = k - 1 term
-            TX::Acc acc; acc_zero<TX>(acc);
-            gemm_task<TX>(acc, A + (size_t)kb + (size_t)(kb - TB) * M, 1, (size_t)M, nbk, X + (size_t)(kb - TB) + (size_t)c0 * M, 1, (size_t)M, 16, TB, As, Bs);
-            store_task<TX>(acc, Tt, M, nbk, 16, 1.0, (c0 / TB == k - 1) ? 0.0 : 1.0);
-            __syncthreads();                                   // (the block reads back its own global stores)
-            TX::Acc acc2; acc_zero<TX>(acc2);
-            gemm_task<TX>(acc2, Dk, 1, (size_t)TB, nbk, Tt, 1, (size_t)M, 16, nbk, As, Bs);
-            store_task<TX>(acc2, X + (size_t)kb + (size_t)c0 * M, M, nbk, 16, -1.0, 0.0);
+            return;
         }
+        const int c0 = 16 * t;
+        double* Tt = j.Tmp + (size_t)kb + (size_t)c0 * M;      // P(k, slice), completed in place with the l = k - 1 term
+        TX::Acc acc; acc_zero<TX>(acc);
+        gemm_task<TX>(acc, A + (size_t)kb + (size_t)(kb - TB) * M, 1, (size_t)M, nbk, X + (size_t)(kb - TB) + (size_t)c0 * M, 1, (size_t)M, 16, TB, As, Bs);
+        store_task<TX>(acc, Tt, M, nbk, 16, 1.0, (c0 / TB == k - 1) ? 0.0 : 1.0);
+        __syncthreads();                                       // (the block reads back its own global stores)
+        TX::Acc acc2; acc_zero<TX>(acc2);
+        gemm_task<TX>(acc2, Dk, 1, (size_t)TB, nbk, Tt, 1, (size_t)M, 16, nbk, As, Bs);
+        store_task<TX>(acc2, X + (size_t)kb + (size_t)c0 * M, M, nbk, 16, -1.0, 0.0);
     };
-    auto p_update_tasks = [&](int k, int w, int nw) {         // P(i, j) (+)= L(i, k-1) X(k-1, j) for the rows below block k, columns left of block k
-        if (k < 1) return;
-        const int R1 = (k + 1) * TB, kb1 = (k - 1) * TB;
-        if (R1 >= M) return;
-        const int nr = (M - R1 + 31) / 32, nc = 2 * k;
-        for (int t = w; t < nr * nc; t += nw) {
-            const int r0 = R1 + 32 * (t % nr), c0 = 32 * (t / nr), rows = min(32, M - r0);
-            const Task32 tk{A + (size_t)r0 + (size_t)kb1 * M, 1, (size_t)M, rows, X + (size_t)kb1 + (size_t)c0 * M, 1, (size_t)M, 32, TB,
-                            j.Tmp + (size_t)r0 + (size_t)c0 * M, M, 1.0, (c0 / TB == k - 1) ? 0.0 : 1.0, nullptr, false, 0, 0, tk32};
-            run_task32(tk, As, Bs);
-        }
+    auto tri_ab = [](int t, int& a, int& b) { a = 0; while ((a + 1) * (a + 2) / 2 <= t) ++a; b = t - a * (a + 1) / 2; };
+    auto trailing_tile = [&](int k, int t) {                  // 64 x 64 tile t + 1 of the lower triangle of A[R0:, R0:] (tile 0 belongs to CTA 0)
+        const int k0 = k * TB, R0 = k0 + TB;
+        int a, b; tri_ab(t + 1, a, b);
+        const int r0 = R0 + TB * a, c0 = R0 + TB * b;
+        const Task32 tk{A + (size_t)r0 + (size_t)k0 * M, 1, (size_t)M, min(TB, M - r0), A + (size_t)c0 + (size_t)k0 * M, (size_t)M, 1, min(TB, M - c0), TB,
+                        A + (size_t)r0 + (size_t)c0 * M, M, -1.0, 1.0, nullptr, a == b, r0, c0, tk32};
+        run_task64(tk, As, Bs);
     };
-    auto s_update_tasks = [&](int kk, int w, int nw, bool last) {     // S(a, b) (+)= X(kk, a)' X(kk, b) over the 32 x 32 sub-tiles b <= a of the first kk + 1 blocks
+    auto p_tile = [&](int k, int t) {                          // P(i, jb) (+)= L(i, k-1) X(k-1, jb), row blocks i > k, column blocks jb < k
+        const int nr = nblk - k - 1, kb1 = (k - 1) * TB;
+        const int r0 = (k + 1 + t % nr) * TB, jb = t / nr, c0 = jb * TB;
+        const Task32 tk{A + (size_t)r0 + (size_t)kb1 * M, 1, (size_t)M, min(TB, M - r0), X + (size_t)kb1 + (size_t)c0 * M, 1, (size_t)M, TB, TB,
+                        j.Tmp + (size_t)r0 + (size_t)c0 * M, M, 1.0, jb == k - 1 ? 0.0 : 1.0, nullptr, false, 0, 0, tk32};
+        run_task64(tk, As, Bs);
+    };
+    auto s_tile = [&](int kk, int t, bool last) {              // S(a, b) (+)= X(kk, a)' X(kk, b), blocks b <= a <= kk
         const int kb = kk * TB, nbk = min(TB, M - kb);
-        const int n32 = (min(M, kb + TB) + 31) / 32, ntask = n32 * (n32 + 1) / 2;
-        for (int t = w; t < ntask; t += nw) {
-            int a = 0;
-            while ((a + 1) * (a + 2) / 2 <= t) ++a;
-            const int b = t - a * (a + 1) / 2;
-            const int r0 = 32 * a, c0 = 32 * b, rows = min(32, M - r0), cols = min(32, M - c0);
-            const bool first = (r0 / TB) == kk;                // row block kk is the first one with a non-zero X(kk, column block of a)
-            const Task32 tk{X + (size_t)kb + (size_t)r0 * M, (size_t)M, 1, rows, X + (size_t)kb + (size_t)c0 * M, 1, (size_t)M, cols, nbk,
-                            j.S + (size_t)r0 + (size_t)c0 * M, M, 1.0, first ? 0.0 : 1.0, last ? j.S + (size_t)c0 + (size_t)r0 * M : nullptr, a == b, r0, c0, tk32};
-            run_task32(tk, As, Bs);
+        int a, b; tri_ab(t, a, b);
+        const int r0 = TB * a, c0 = TB * b;
+        const Task32 tk{X + (size_t)kb + (size_t)r0 * M, (size_t)M, 1, min(TB, M - r0), X + (size_t)kb + (size_t)c0 * M, 1, (size_t)M, min(TB, M - c0), nbk,
+                        j.S + (size_t)r0 + (size_t)c0 * M, M, 1.0, a == kk ? 0.0 : 1.0, last ? j.S + (size_t)c0 + (size_t)r0 * M : nullptr, a == b, r0, c0, tk32};
+        run_task64(tk, As, Bs);
+    };
+    auto s_tile32 = [&](int kk, int t, bool last) {            // the same in 32 x 32 sub-tiles: for the phases everybody waits for, when they are small
+        const int kb = kk * TB, nbk = min(TB, M - kb);
+        int a, b; tri_ab(t, a, b);
+        const int r0 = 32 * a, c0 = 32 * b;
+        const Task32 tk{X + (size_t)kb + (size_t)r0 * M, (size_t)M, 1, min(32, M - r0), X + (size_t)kb + (size_t)c0 * M, 1, (size_t)M, min(32, M - c0), nbk,
+                        j.S + (size_t)r0 + (size_t)c0 * M, M, 1.0, r0 / TB == kk ? 0.0 : 1.0, last ? j.S + (size_t)c0 + (size_t)r0 * M : nullptr, a == b, r0, c0, tk32};
+        run_task32(tk, As, Bs);
+    };
+    // All of a step's worker tasks in ONE list dealt round-robin (tiles first, the lighter X slices last): nobody reads what another task of the
+    // same step writes.
+    auto step_tasks = [&](int k, int w, int nw) {
+        const bool has_next = k + 1 < nblk;
+        const int nb = has_next ? nblk - k - 1 : 0;
+        const int n_tr = has_next ? nb * (nb + 1) / 2 - 1 : 0;
+        const int n_p = (X && k >= 1) ? nb * k : 0;
+        int n_s = (X && j.S && k >= 1) ? k * (k + 1) / 2 : 0;
+        const int n_x = X ? 4 * k + 1 : 0;
+        const bool s32 = !has_next && n_s > 0 && 3 * n_s <= nw;           // last step (nobody factorises meanwhile): finer tasks when they fit one round
+        if (s32) n_s = k * (2 * k + 1);
+        for (int t = w; t < n_tr + n_p + n_s + n_x; t += nw) {
+            if (t < n_tr) trailing_tile(k, t);
+            else if (t < n_tr + n_p) p_tile(k, t - n_tr);
+            else if (t < n_tr + n_p + n_s) { if (s32) s_tile32(k - 1, t - n_tr - n_p, false); else s_tile(k - 1, t - n_tr - n_p, false); }
+            else x_slice(k, t - n_tr - n_p - n_s);
         }
     };
     for (int k = 0; k < nblk; ++k) {
@@ -634,45 +681,126 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
             factor_diag_smem(T, Xi, rdiag, Lc, A + (size_t)R0 * ((size_t)M + 1), M, nbn, R0, j.Dinv + (size_t)(k + 1) * TB * TB, j.info, fst);
             DCLK(1);
         }
-        if (!factoring) {
-            if (has_next) {         // trailing update on the lower triangle of A[R0:, R0:] (the sub-tiles of its first 64 x 64 block belong to CTA 0)
-                const int n32 = (M - R0 + 31) / 32;
-                const int ntask = n32 * (n32 + 1) / 2 - (n32 >= 2 ? 3 : 1);
-                for (int t = wid; t < ntask; t += nwork) {
-                    const int tt = t + 3;
-                    int a = 0;
-                    while ((a + 1) * (a + 2) / 2 <= tt) ++a;
-                    const int b = tt - a * (a + 1) / 2;
-                    const int r0 = R0 + 32 * a, c0 = R0 + 32 * b, rows = min(32, M - r0), cols = min(32, M - c0);
-                    const Task32 tk{A + (size_t)r0 + (size_t)k0 * M, 1, (size_t)M, rows, A + (size_t)c0 + (size_t)k0 * M, (size_t)M, 1, cols, TB,
-                                    A + (size_t)r0 + (size_t)c0 * M, M, -1.0, 1.0, nullptr, a == b, r0, c0, tk32};
-                    run_task32(tk, As, Bs);
-                }
-            }
-            if (X) {
-                // (workers are dealt from the far end for the X rows so that the CTAs that got the last trailing sub-tiles are not the first here)
-                x_row_tasks(k, nwork - 1 - wid, nwork);
-                p_update_tasks(k, wid, nwork);
-                if (j.S && k > 0) s_update_tasks(k - 1, wid, nwork, false);
-            }
-        }
+        if (!factoring) step_tasks(k, wid, nwork);
         DCLK(3);
         grid.sync();
         DCLK(4);
     }
-    if (X && j.S) {       // the last row block of X into S (every tile receives its last contribution here: mirrored on the way out), then mu = S xi
-        s_update_tasks(nblk - 1, cta, ncta, true);
-        DCLK(6);
-        if (j.mu) {
-            grid.sync();
-            // mu = S xi: a warp per column of the symmetric S (fixed-shape tree: deterministic)
-            for (int i = cta * (CT / 32) + warp; i < M; i += ncta * (CT / 32)) {
-                const double* col = j.S + (size_t)i * M;
+    if (X && j.S) {       // the last row block of X into S (every tile receives its last contribution here: mirrored on the way out), then mu
+        if (3 * nblk * (nblk + 1) / 2 <= ncta) {
+            const int n32 = (M + 31) / 32;
+            for (int t = cta; t < n32 * (n32 + 1) / 2; t += ncta) s_tile32(nblk - 1, t, true);
+        } else {
+            for (int t = cta; t < nblk * (nblk + 1) / 2; t += ncta) s_tile(nblk - 1, t, true);
+        }
+        if (j.flip && j.mu) {
+            // p = X xi (reversed indices) in kPParts partial sums per 32-row strip: rows = lanes, a warp per column, fixed-order reduction.
+            // Needs X only: dealt from the far end of the grid, beside the S tiles.
+            const int nstrip = (M + 31) / 32;
+            double* red = sm;                                  // 8 warps x 32 rows
+            for (int t = ncta - 1 - cta; t < nstrip * kPParts; t += ncta) {
+                const int st = t / kPParts, q = t % kPParts, row = 32 * st + lane;
+                const int ncol = min(M, 32 * st + 32), cb = (int)((long long)ncol * q / kPParts), ce = (int)((long long)ncol * (q + 1) / kPParts);
                 double v = 0.0;
-                for (int r = lane; r < M; r += 32) v = fma(col[r], j.xi[r], v);
+                if (row < M)
+#pragma unroll 4
+                    for (int c = cb + warp; c < ce; c += CT / 32)
+                        if (c <= row) v = fma(X[(size_t)row + (size_t)c * M], j.xi[M - 1 - c], v);
+                __syncthreads();
+                red[warp * 32 + lane] = v;
+                __syncthreads();
+                if (warp == 0 && row < M) {
+                    double a = red[lane];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) j.mu[i] = v;
+                    for (int w8 = 1; w8 < CT / 32; ++w8) a += red[w8 * 32 + lane];
+                    j.Tmp[(size_t)q * M + row] = a;
+                }
+            }
+        }
+        DCLK(6);
+        if (j.mu || j.flip) grid.sync();
+        if (!j.flip) {
+            if (j.mu)          // mu = S xi: a warp per column of the symmetric S (fixed-shape tree: deterministic)
+                for (int i = cta * (CT / 32) + warp; i < M; i += ncta * (CT / 32)) {
+                    const double* col = j.S + (size_t)i * M;
+                    double v = 0.0;
+                    for (int r = lane; r < M; r += 32) v = fma(col[r], j.xi[r], v);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) j.mu[i] = v;
+                }
+        } else {
+            // A^-1 = U0' U0 with U0 = J X J upper triangular: the Cholesky factor of the inverse is the inverse of the REVERSED-order factor.
+            //   mu = U0' p, p = U0 xi (two triangular products, as a Cholesky solve would do), and
+            //   A^-1 + mu mu' = U0' (I + p p') U0, where the factor G of I + p p' is closed-form:
+            //     G[k, k] = s_{k+1} / s_k,   G[k, i] = p_k p_i / (s_k s_{k+1})  (i > k),   s_k^2 = 1 + sum_{i < k} p_i^2,
+            // so Uv = G U0 costs a running sum down every column of X instead of a second M^3 / 3 factorisation:
+            //     Uv[k, c] = (s_{k+1} / s_k) U0[k, c] + p_k / (s_k s_{k+1}) sum_{k < i <= c} p_i U0[i, c].
+            double* pp = sm; double* ga = sm + M; double* b0 = sm + 2 * M; double* b1 = sm + 3 * M;     // (in reversed indices throughout)
+            const double* gb = nullptr;
+            if (j.mu) {
+                for (int i = tid; i < M; i += CT) {
+                    double v = j.Tmp[i];
+#pragma unroll
+                    for (int q = 1; q < kPParts; ++q) v += j.Tmp[(size_t)q * M + i];
+                    pp[i] = v; b0[i] = v * v;
+                }
+                __syncthreads();
+            }
+            if (j.Uv) {
+                double* cur = b0; double* nxt = b1;                 // inclusive suffix sums of p^2 (positive terms: no cancellation)
+                for (int off = 1; off < M; off <<= 1) {
+                    for (int i = tid; i < M; i += CT) nxt[i] = cur[i] + (i + off < M ? cur[i + off] : 0.0);
+                    __syncthreads();
+                    double* sw = cur; cur = nxt; nxt = sw;
+                }
+                for (int i = tid; i < M; i += CT) {                 // s_k^2 = 1 + (sum over reversed indices above i), s_{k+1}^2 = s_k^2 + p_i^2
+                    const double lo = 1.0 + (i + 1 < M ? cur[i + 1] : 0.0), hi = 1.0 + cur[i];
+                    ga[i] = sqrt(hi / lo);
+                    nxt[i] = pp[i] / sqrt(hi * lo);
+                }
+                __syncthreads();
+                gb = nxt;
+            }
+            // a warp per column c of X (column M - 1 - c of Uv), from the diagonal down (Uv: from the diagonal up), 128 rows at a time:
+            // mu[M - 1 - c] = sum_r X[r, c] p[r] and the column of Uv in the same pass
+            if (j.mu)
+                for (int c = cta + ncta * warp; c < M; c += ncta * (CT / 32)) {
+                    const double* xc = X + (size_t)c * M;
+                    double* uc = j.Uv ? j.Uv + (size_t)(M - 1 - c) * M : nullptr;
+                    if (uc) for (int r = lane; r < c; r += 32) uc[M - 1 - r] = 0.0;       // strictly below the diagonal of Uv
+                    double carry = 0.0, dot = 0.0;
+                    for (int r0 = c; r0 < M; r0 += 128) {
+                        double x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { const int r = r0 + 32 * u + lane; x[u] = r < M ? xc[r] : 0.0; }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int r = r0 + 32 * u + lane;
+                            const double t = r < M ? pp[r] * x[u] : 0.0;
+                            dot += t;
+                            if (uc) {
+                                double inc = t;
+#pragma unroll
+                                for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+                                if (r < M) uc[M - 1 - r] = fma(gb[r], carry + (inc - t), ga[r] * x[u]);
+                                carry += __shfl_sync(0xffffffffu, inc, 31);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                    if (lane == 0) j.mu[M - 1 - c] = dot;
+                }
+            {
+                const size_t stride = (size_t)ncta * CT;
+                for (size_t e0 = (size_t)cta * CT + tid; e0 < MM; e0 += 8 * stride) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const size_t e = e0 + u * stride; if (e < MM) v[u] = j.S[MM - 1 - e]; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const size_t e = e0 + u * stride; if (e < MM) j.Sout[e] = v[u]; }
+                }
             }
         }
         DCLK(5);
@@ -700,7 +828,7 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
                 }
             }
         }
-    } else {
+    } else if (!j.flip) {                                              // (nobody reads the factor of a reversed-order job)
         for (size_t e = (size_t)cta * CT + tid; e < MM; e += (size_t)ncta * CT)
             if (e / M > e % M) A[e] = 0.0;
     }
@@ -748,7 +876,10 @@ int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in) {
     j.Z = ctx->Z_dev; j.D = ctx->D; j.kind = ctx->kind; j.variance = ctx->variance; j.jitter = in.jitter;
     for (int d = 0; d < SGP_MAX_D; ++d) j.ell_inv[d] = d < ctx->D ? 1.0 / ctx->ell[d] : 0.0;
     j.Sig = in.Sig; j.mu_in = in.mu_in; j.X = in.X; j.Tmp = in.Tmp; j.S = in.S; j.mu = in.mu; j.Ut = in.Ut; j.clk = in.clk;
+    j.flip = in.flip; j.Sout = in.Sout; j.Uv = in.Uv;
     if (j.mu && !(j.S && j.xi)) SGP_FAIL(ctx, SGP_ERR_ARG, "dense job: mu needs S and xi");
+    if (j.flip && !(j.build == 1 && j.X && j.S && j.Sout)) SGP_FAIL(ctx, SGP_ERR_ARG, "dense job: the reversed order is for build 1 with X, S and Sout");
+    if (j.Uv && !(j.flip && j.mu && j.M <= SGP_FLIP_UV_MAX_M)) SGP_FAIL(ctx, SGP_ERR_ARG, "dense job: Uv needs the reversed order, mu and M <= 4096");
     const int M = in.M, nblk = (M + TB - 1) / TB, n32 = (M + 31) / 32;
     const size_t smem = SMEM_DOUBLES * sizeof(double);
     SGP_CUDA(ctx, cudaFuncSetAttribute(dense_job_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

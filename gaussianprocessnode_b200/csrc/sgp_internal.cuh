@@ -117,6 +117,7 @@ int sgp_ensure_zero(sgp_ctx* ctx, double** p, size_t* cap, size_t need_doubles);
 int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const double* yv, const double* w, int64_t N,
                      int64_t Ncap, bool time_main);
 // dense_coop.cu: one cooperative kernel per M x M job: [build A] -> Cholesky -> [X = L^-1, S = X'X] -> [mu = S xi] -> [Ut = L']
+constexpr int SGP_FLIP_UV_MAX_M = 4096;      // four M-vectors of the closed-form rank-one factor live in shared memory
 struct SgpDenseJob {
     int M = 0;
     int build = 0;             // 0: A as given | 1: A = P + w S2, xi = xip + w s1 (carry: P <- A, xip <- xi) | 2: A = K_uu(Z) + jitter I | 3: A = Sig + mu_in mu_in'
@@ -128,6 +129,9 @@ struct SgpDenseJob {
     double* X = nullptr; double* Tmp = nullptr; double* S = nullptr;    // optional inverse: X = L^-1, S = (L L')^-1 (full symmetric), Tmp = M x M scratch
     double* mu = nullptr;      // optional: mu = S xi
     double* Ut = nullptr;      // optional: Ut = L' (upper)
+    int flip = 0;              // build 1 with X and S: factorise the index-reversed matrix; S is scratch, Sout / mu / Uv come out un-reversed
+    double* Sout = nullptr;    // flip: A^-1 (full symmetric)
+    double* Uv = nullptr;      // flip, optional (needs mu, M <= SGP_FLIP_UV_MAX_M): chol(A^-1 + mu mu').U from a running sum down the columns of X
     long long* clk = nullptr;  // optional: 8 phase clocks of CTA 0
     int reset_info = 1;        // zero ctx->info_dev before the launch
 };

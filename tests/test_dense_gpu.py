@@ -66,9 +66,14 @@ def test_posterior_and_w_terms(ctx, N, D, M, w):
     nL = np.linalg.norm(o_Lam, 2)
     assert np.linalg.norm(o_Lam @ Sigma - np.eye(M)) / (nL * np.linalg.norm(Sigma, 2) * M) < 1e-13
     assert np.linalg.norm(o_Lam @ mu - o_xi) / (nL * np.linalg.norm(mu) + np.linalg.norm(o_xi)) < 1e-11
-    assert fro(Uv.T @ Uv, Sigma + np.outer(mu, mu)) < 1e-12
-    assert np.allclose(np.tril(Uv, -1), 0.0)
     cond = np.linalg.cond(o_Lam)
+    # Uv comes from the factor of Sigma and p = U0 xi, not from the rounded Sigma and mu: its residual against THEM carries mu's own
+    # conditioning-limited error (mu = Sigma xi, |Sigma| |xi| >> |mu|)
+    assert fro(Uv.T @ Uv, Sigma + np.outer(mu, mu)) < max(1e-12, 20 * cond * 2.2e-16)
+    assert np.allclose(np.tril(Uv, -1), 0.0)
+    assert np.all(np.diag(Uv) > 0.0)
+    Rv = o_Sig + np.outer(o_mu, o_mu)
+    assert fro(Uv, o_Uv) < max(1e-10, 50 * np.linalg.cond(Rv) * 2.2e-16)   # the factor is unique: forward error bounded by conditioning
     assert fro(Sigma, o_Sig) < max(1e-10, 50 * cond * 2.2e-16)        # forward error bounded by conditioning
     assert fro(mu, o_mu) < max(1e-10, 50 * cond * 2.2e-16)
     # :w terms with the posterior as input
@@ -181,3 +186,32 @@ def test_streaming_prior_equals_one_full_sweep(ctx, kin40k):
     assert abs(a[0] - b_[0]) <= 1e-12 * abs(b_[0]) and abs(a[1] - b_[1]) <= 1e-10 * abs(b_[1])
     f1 = ctx.theta_objective(None, None, w, 1e-8); f2 = ctx.theta_objective(mu_s, Uv_s, w, 1e-8)
     assert abs(f1[0] - f2[0]) <= 1e-10 * abs(f2[0]) and np.linalg.norm(f1[2] - f2[2]) <= 1e-9 * np.linalg.norm(f2[2])
+
+
+_UV2_SCRIPT = """
+import sys, numpy as np
+from gaussianprocessnode_b200 import SGPContext
+M = int(sys.argv[1]); rng = np.random.default_rng(7 + M)
+X = rng.normal(size=(4000, 4)); y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=4000)
+Z = X[rng.choice(4000, M, replace=False)]
+c = SGPContext(0); c.set_kernel(1.1, np.full(4, 1.4), D=4); c.set_inducing(Z); c.set_data(X, y); c.sweep_psi()
+mu, Sig, Uv = c.posterior_v(np.zeros(M), np.eye(M) / 50.0, 40.0)
+np.savez(sys.argv[2], mu=mu, Sig=Sig, Uv=Uv); c.close()
+"""
+
+
+@pytest.mark.parametrize("M", [50, 130, 512])
+def test_one_launch_posterior_agrees_with_the_two_factorisation_form(tmp_path, M):
+    # default: reversed-order factorisation + closed-form rank-one update inside one launch; SGP_DENSE_UV2=1: Cholesky of Sigma + mu mu'
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for tag, val in (("one", "0"), ("two", "1")):
+        f = str(tmp_path / f"{tag}.npz")
+        env = dict(os.environ, SGP_DENSE_UV2=val, PYTHONPATH=root)
+        subprocess.run([sys.executable, "-c", _UV2_SCRIPT, str(M), f], check=True, env=env, cwd=root, timeout=300)
+        out[tag] = np.load(f)
+    tol = max(1e-10, 50 * np.linalg.cond(out["two"]["Sig"]) * 2.2e-16)       # two backward-stable solvers: forward difference ~ cond * eps
+    errs = [fro(out["one"][k], out["two"][k]) for k in ("Sig", "mu", "Uv")]
+    assert max(errs) < tol, (errs, tol)
+    assert np.allclose(np.tril(out["one"]["Uv"], -1), 0.0)
