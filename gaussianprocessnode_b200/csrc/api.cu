@@ -417,11 +417,10 @@ int sgp_stats_dev(sgp_ctx* ctx, double** psi2_dev, double** psi1_dev, double** s
 }
 
 // ---- M x M factorisations ---------------------------------------------------------------------------------------
-int sgp_kuu_factor(sgp_ctx* ctx, double jitter, double* L) {
-    if (check(ctx)) return SGP_ERR_ARG;
-    if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "kuu_factor: set_kernel and set_inducing first");
-    SGP_RANGE("sgp_kuu_factor");
-    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+}  // extern "C"
+// Enqueues the K_uu job without synchronising: the caller checks the pivot record (sgp_dense_info, or its own read of ctx->info_dev) when it
+// next synchronises, and clears ctx->have_kuu if that fails.
+int sgp_kuu_factor_enqueue(sgp_ctx* ctx, double jitter) {
     const int M = ctx->M;
     if (ctx->KuuL_M != M) {
         if (ctx->KuuL_dev) SGP_CUDA(ctx, cudaFree(ctx->KuuL_dev));
@@ -440,10 +439,21 @@ int sgp_kuu_factor(sgp_ctx* ctx, double jitter, double* L) {
     SgpDenseJob j;
     j.M = M; j.build = 2; j.jitter = jitter; j.A = ctx->KuuL_dev; j.Dinv = ctx->kuu_dinv_dev; j.X = d; j.Tmp = d + MM; j.S = ctx->Kinv_dev;
     rc = sgp_dense_job(ctx, j); if (rc) return rc;
-    if (ctx->dense_timing) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (L) SGP_CUDA(ctx, cudaMemcpyAsync(L, ctx->KuuL_dev, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    rc = sgp_dense_info(ctx, "kuu_factor"); if (rc) return rc;
     ctx->have_kuu = true; ctx->kuu_jitter = jitter;
+    return SGP_OK;
+}
+extern "C" {
+
+int sgp_kuu_factor(sgp_ctx* ctx, double jitter, double* L) {
+    if (check(ctx)) return SGP_ERR_ARG;
+    if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "kuu_factor: set_kernel and set_inducing first");
+    SGP_RANGE("sgp_kuu_factor");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    int rc = sgp_kuu_factor_enqueue(ctx, jitter); if (rc) return rc;
+    if (ctx->dense_timing) SGP_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (L) SGP_CUDA(ctx, cudaMemcpyAsync(L, ctx->KuuL_dev, (size_t)ctx->M * ctx->M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = sgp_dense_info(ctx, "kuu_factor");
+    if (rc) { ctx->have_kuu = false; return rc; }
     return SGP_OK;
 }
 

@@ -210,6 +210,7 @@ __device__ __forceinline__ void store_task(const typename TL::Acc& acc, double* 
 using T64 = Tile<64, 64, 4, 32>;      // warp tile 16 x 32
 using T32 = Tile<32, 32, 4, 64>;      // warp tile  8 x 16: little MMA work per chunk, so a long chunk per barrier pair
 using T16 = Tile<16, 64, 2, 64>;      // row strip: warp tile 8 x 16
+using T63 = Tile<64, 32, 4, 32>;      // 64 x 32: warp tile 16 x 16
 using TX = Tile<64, 16, 8, 64>;       // column slice of a row block of X: warp tile 8 x 16
 
 // The 32 x 32 sub-tile task every phase is made of, as ONE non-inlined routine (the kernel's instruction footprint decides its speed: each
@@ -400,6 +401,13 @@ __device__ __forceinline__ void smem_store32(const Frag32& f, double* __restrict
         }
 }
 
+// Element e of a 64 x 64 block that is column-major in global memory and row-major (LDT) in shared memory -> (r, c): 8 consecutive threads
+// along a column (64-byte runs in global memory), the next 4 along the row: two-way bank conflicts at most on the shared-memory side
+// (a plain r = e % 64 map is eight-way conflicted there).
+__device__ __forceinline__ void blk_rc(int e, int& r, int& c) {
+    const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
+    r = lo + 8 * (rest & 7); c = mid + 4 * (rest >> 3);
+}
 // Factor the nb x nb diagonal block held in T (lower part valid, identity-padded beyond nb, zeros above the diagonal), write L to A
 // (global, lower part) and its inverse to Dinv (64 x 64 column-major; only the lower triangle is written).  One CTA, all 256 threads.
 //   warp 0: Cholesky of the leading 32 x 32 block; one pivot behind it warp 1: L21 = A21 L11^-T (forward substitution), warp 2: X11 = L11^-1
@@ -444,7 +452,7 @@ __device__ __noinline__ void factor_diag_smem(double* __restrict__ T, double* __
     __syncthreads();
     FCLK(2);
     for (int e = tid; e < TB * TB; e += CT) {           // (the strict upper triangle of every Dinv block is zero from its allocation;
-        const int r = e % TB, c = e / TB;               //  the grid barrier that follows publishes the stores)
+        int r, c; blk_rc(e, r, c);                      //  the grid barrier that follows publishes the stores)
         if (c <= r) {
             if (r < nb) A[(size_t)r + (size_t)c * lda] = T[r * LDT + c];
             Dinv[(size_t)r + (size_t)c * TB] = Xi[r * LDT + c];
@@ -460,15 +468,55 @@ __device__ __forceinline__ void load_diag_smem(double* __restrict__ T, const dou
     double v[TB * TB / CT];
 #pragma unroll
     for (int q = 0; q < TB * TB / CT; ++q) {
-        const int e = threadIdx.x + q * CT, r = e % TB, c = e / TB;
+        int r, c; blk_rc(threadIdx.x + q * CT, r, c);
         v[q] = (r == c) ? 1.0 : 0.0;
         if (r < nb && c < nb) v[q] = (c <= r) ? A[(size_t)r + (size_t)c * lda] : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < TB * TB / CT; ++q) {
-        const int e = threadIdx.x + q * CT;
-        T[(e % TB) * LDT + e / TB] = v[q];
+        int r, c; blk_rc(threadIdx.x + q * CT, r, c);
+        T[r * LDT + c] = v[q];
     }
+}
+
+// T <- A_diag - P P' for the next diagonal block: A_diag (nb x nb, lower part) and the panel block P = L(k+1, k) (nb x 64) both straight from
+// global memory into shared memory (all 32 loads of a thread in flight), the product on the shared-memory copy of P -- which is both
+// operands -- for the three 32 x 32 blocks of the lower triangle only.  T comes out as load_diag_smem leaves it (identity-padded, zeros above).
+__device__ __forceinline__ void update_diag_smem(double* __restrict__ T, double* __restrict__ Pm, const double* __restrict__ Adiag,
+                                                 const double* __restrict__ Ppanel, int lda, int nb) {
+    double v[TB * TB / CT], q_[TB * TB / CT];
+#pragma unroll
+    for (int q = 0; q < TB * TB / CT; ++q) {
+        int r, c; blk_rc(threadIdx.x + q * CT, r, c);
+        v[q] = (r == c) ? 1.0 : 0.0;
+        if (r < nb && c < nb) v[q] = (c <= r) ? Adiag[(size_t)r + (size_t)c * lda] : 0.0;
+        q_[q] = r < nb ? Ppanel[(size_t)r + (size_t)c * lda] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < TB * TB / CT; ++q) {
+        int r, c; blk_rc(threadIdx.x + q * CT, r, c);
+        T[r * LDT + c] = v[q];
+        Pm[r * LDT + c] = q_[q];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = warp >> 1, wc = warp & 1;
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
+        const int bi = blk == 0 ? 0 : 1, bj = blk == 2 ? 1 : 0;          // (0,0), (1,0), (1,1)
+        const double* Pa = Pm + 32 * bi * LDT; const double* Pb = Pm + 32 * bj * LDT;
+        const Frag32 f0 = smem_mma32(Pa, LDT, 1, Pb, 1, LDT);
+        const Frag32 f1 = smem_mma32(Pa + 32, LDT, 1, Pb + 32, 1, LDT);
+        double* C = T + 32 * bi * LDT + 32 * bj;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = wr * 8 + (lane >> 2), c = wc * 16 + 8 * jj + 2 * (lane & 3) + h;
+                if (bi != bj || c <= r) C[r * LDT + c] -= f0.v[jj][h] + f1.v[jj][h];
+            }
+    }
+    __syncthreads();
 }
 
 struct DenseJob {
@@ -661,22 +709,7 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
         const int nwork = (has_next && ncta > 1) ? ncta - 1 : ncta, wid = (has_next && ncta > 1) ? cta - 1 : cta;
         if (has_next && cta == 0) {     // next diagonal block: A[i, c] -= sum_kk L[i, k0 + kk] L[c, k0 + kk], straight into shared memory, factorised there
             const int nbn = min(TB, M - R0);
-            load_diag_smem(T, A + (size_t)R0 * ((size_t)M + 1), M, nbn);
-            T64::Acc acc; acc_zero<T64>(acc);
-            gemm_task<T64>(acc, A + (size_t)R0 + (size_t)k0 * M, 1, (size_t)M, nbn, A + (size_t)R0 + (size_t)k0 * M, (size_t)M, 1, nbn, TB, As, Bs, tk64);
-            __syncthreads();
-            {
-                const int wr = warp / T64::WC, wc = warp % T64::WC;
-#pragma unroll
-                for (int i = 0; i < T64::MI; ++i)
-#pragma unroll
-                    for (int jj = 0; jj < T64::NJ; ++jj)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int r = wr * T64::WTR + 8 * i + (lane >> 2), c = wc * T64::WTC + 8 * jj + 2 * (lane & 3) + h;
-                            if (r < nbn && c <= r) T[r * LDT + c] -= acc.v[i][jj][h];
-                        }
-            }
+            update_diag_smem(T, Xi, A + (size_t)R0 * ((size_t)M + 1), A + (size_t)R0 + (size_t)k0 * M, M, nbn);
             DCLK(3);
             factor_diag_smem(T, Xi, rdiag, Lc, A + (size_t)R0 * ((size_t)M + 1), M, nbn, R0, j.Dinv + (size_t)(k + 1) * TB * TB, j.info, fst);
             DCLK(1);
@@ -847,23 +880,31 @@ struct Gemm2Args {
     int m, n, k, lda, ldb, ldc, opA, opB, lower_only;
     double alpha, beta;
 };
-template <class TL, int TS>
+template <class TL, int TSR, int TSC>
 __global__ void __launch_bounds__(CT) gemm2_kernel(const Gemm2Args g) {
     extern __shared__ double sm[];
     double* As = sm; double* Bs = sm + STAGE_A;
-    const int tm = (g.m + TS - 1) / TS, tn = (g.n + TS - 1) / TS;
+    const int tm = (g.m + TSR - 1) / TSR, tn = (g.n + TSC - 1) / TSC;
     for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
         const int ti = t % tm, tj = t / tm;
-        if (g.lower_only && tj > ti) continue;
-        const int rows = min(TS, g.m - ti * TS), cols = min(TS, g.n - tj * TS);
-        // A(r, k): opA == 0 -> A[(ti*TS + r) + k*lda], else A[k + (ti*TS + r)*lda];  B(k, c): opB == 0 -> B[k + (tj*TS + c)*ldb], else B[(tj*TS + c) + k*ldb]
-        const double* Ab = g.opA == 0 ? g.A + (size_t)ti * TS : g.A + (size_t)ti * TS * g.lda;
-        const double* Bb = g.opB == 0 ? g.B + (size_t)tj * TS * g.ldb : g.B + (size_t)tj * TS;
+        if (g.lower_only && tj * TSC > ti * TSR + TSR - 1) continue;      // tile entirely above the diagonal
+        const int rows = min(TSR, g.m - ti * TSR), cols = min(TSC, g.n - tj * TSC);
+        // A(r, k): opA == 0 -> A[(ti*TSR + r) + k*lda], else A[k + (ti*TSR + r)*lda];  B(k, c): opB == 0 -> B[k + (tj*TSC + c)*ldb], else B[(tj*TSC + c) + k*ldb]
+        const double* Ab = g.opA == 0 ? g.A + (size_t)ti * TSR : g.A + (size_t)ti * TSR * g.lda;
+        const double* Bb = g.opB == 0 ? g.B + (size_t)tj * TSC * g.ldb : g.B + (size_t)tj * TSC;
         typename TL::Acc acc; acc_zero<TL>(acc);
         gemm_task<TL>(acc, Ab, g.opA == 0 ? 1 : (size_t)g.lda, g.opA == 0 ? (size_t)g.lda : 1, rows, Bb, g.opB == 0 ? 1 : (size_t)g.ldb,
                       g.opB == 0 ? (size_t)g.ldb : 1, cols, g.k, As, Bs);
-        store_task<TL>(acc, g.C + (size_t)ti * TS + (size_t)tj * TS * g.ldc, g.ldc, rows, cols, g.alpha, g.beta);
+        store_task<TL>(acc, g.C + (size_t)ti * TSR + (size_t)tj * TSC * g.ldc, g.ldc, rows, cols, g.alpha, g.beta);
     }
+}
+template <class TL, int TSR, int TSC>
+int launch_gemm2(sgp_ctx* ctx, const Gemm2Args& g, int grid) {
+    const size_t smem = (size_t)(STAGE_A + STAGE_B) * sizeof(double);
+    SGP_CUDA(ctx, cudaFuncSetAttribute(gemm2_kernel<TL, TSR, TSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm2_kernel<TL, TSR, TSC><<<grid, CT, smem, ctx->stream>>>(g);
+    SGP_CUDA(ctx, cudaGetLastError());
+    return SGP_OK;
 }
 
 }  // namespace
@@ -937,17 +978,14 @@ int sgp_gemm2(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha,
               double* C, int ldc, int lower_only) {
     if (m <= 0 || n <= 0) return SGP_OK;
     Gemm2Args g{A, B, C, m, n, k, lda, ldb, ldc, opA, opB, lower_only, alpha, beta};
-    const size_t smem = (size_t)(STAGE_A + STAGE_B) * sizeof(double);
-    const int tiles64 = ((m + 63) / 64) * ((n + 63) / 64), tiles32 = ((m + 31) / 32) * ((n + 31) / 32);
-    if (tiles32 <= 2 * ctx->num_sms) {
-        SGP_CUDA(ctx, cudaFuncSetAttribute(gemm2_kernel<T32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm2_kernel<T32, 32><<<tiles32, CT, smem, ctx->stream>>>(g);
-    } else {
-        SGP_CUDA(ctx, cudaFuncSetAttribute(gemm2_kernel<T64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm2_kernel<T64, 64><<<std::min(tiles64, 4 * ctx->num_sms), CT, smem, ctx->stream>>>(g);
-    }
-    SGP_CUDA(ctx, cudaGetLastError());
-    return SGP_OK;
+    // Tile shape by the fewest (waves over the SMs) x (measured relative cost of a tile: 32 x 32 = 1, 64 x 32 = 1.5, 64 x 64 = 2.6 -- the
+    // larger tiles move less operand traffic per flop, the smaller ones fill the machine when the matrix is small)
+    const int sms = ctx->num_sms;
+    const int t32 = ((m + 31) / 32) * ((n + 31) / 32), t63 = ((m + 63) / 64) * ((n + 31) / 32), t64 = ((m + 63) / 64) * ((n + 63) / 64);
+    const double c32 = 1.0 * ((t32 + sms - 1) / sms), c63 = 1.5 * ((t63 + sms - 1) / sms), c64 = 2.6 * ((t64 + sms - 1) / sms);
+    if (c32 <= c63 && c32 <= c64) return launch_gemm2<T32, 32, 32>(ctx, g, t32);
+    if (c63 <= c64) return launch_gemm2<T63, 64, 32>(ctx, g, t63);
+    return launch_gemm2<T64, 64, 64>(ctx, g, std::min(t64, 4 * sms));
 }
 
 // B (M x nrhs, ld M) <- L^-1 B (trans = false) or L^-T B (trans = true) with the diagonal-block inverses `dinv` of L

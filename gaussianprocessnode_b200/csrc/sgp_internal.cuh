@@ -136,6 +136,7 @@ struct SgpDenseJob {
     int reset_info = 1;        // zero ctx->info_dev before the launch
 };
 int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& job);                          // enqueues; no host synchronisation
+int sgp_kuu_factor_enqueue(sgp_ctx* ctx, double jitter);                         // api.cu: K_uu job without the host synchronisation
 int sgp_dense_info(sgp_ctx* ctx, const char* what);                               // synchronises; non-positive pivot -> SGP_ERR_NOT_PD
 int sgp_potrf_lower(sgp_ctx* ctx, double* A, int M);                              // in place, column-major, lower (synchronises)
 int sgp_trsm_lower_dinv(sgp_ctx* ctx, const double* L, const double* dinv, double* B, double* tmp, int M, int nrhs, bool trans);

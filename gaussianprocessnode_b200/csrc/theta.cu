@@ -59,13 +59,56 @@ __global__ void kuf_chunk_kernel(const double* __restrict__ X, const double* __r
     K[e] = k_of(kp, r2_of(X + (n0 + j) * kp.D, Z + (size_t)m * kp.D, kp, c));
 }
 
-// partial[block][d] = sum over the block's (m, j) of h_mj c_mjd (w G_mj - w y_j v_m)
+// Block reduction of acc[0 .. SGP_MAX_D] (slot SGP_MAX_D: an extra scalar) into partial[block][.]; the LAST block to arrive (ticket) adds the
+// partials of all blocks in fixed order -- deterministic -- and accumulates total[d] += scale * sum (extra: *extra_out += sum, if given).
+constexpr int kPS = SGP_MAX_D + 1;
+__device__ __forceinline__ void reduce_and_finish(const double (&acc)[kPS], double* __restrict__ partial, unsigned* __restrict__ ticket, double scale,
+                                                  double* __restrict__ total, double* __restrict__ extra_out) {
+    __shared__ double s[8][kPS];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < kPS; ++d) {
+        double a = acc[d];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) s[wp][d] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < kPS) {
+        double a = 0.0;
+        for (int q = 0; q < 8; ++q) a += s[q][threadIdx.x];
+        partial[(size_t)blockIdx.x * kPS + threadIdx.x] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bool last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (last) *ticket = 0u;
+        s_last = last ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int d = wp; d < kPS; d += 8) {
+        double a = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) a += __ldcg(partial + (size_t)b * kPS + d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            if (d < SGP_MAX_D) total[d] += scale * a;
+            else if (extra_out) *extra_out += a;
+        }
+    }
+}
+
+// total[d] += sum over the chunk's (m, j) of h_mj c_mjd (w G_mj - w y_j v_m)
 __global__ void __launch_bounds__(256) grad_contract_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ Z,
                                                             const double* __restrict__ G, const double* __restrict__ v, double w, long long n0,
-                                                            int nc, KParams kp, double* __restrict__ partial) {
-    double acc[SGP_MAX_D];
+                                                            int nc, KParams kp, double* __restrict__ partial, unsigned* __restrict__ ticket,
+                                                            double* __restrict__ total_out) {
+    double acc[kPS];
 #pragma unroll
-    for (int d = 0; d < SGP_MAX_D; ++d) acc[d] = 0.0;
+    for (int d = 0; d < kPS; ++d) acc[d] = 0.0;
     const size_t total = (size_t)kp.M * nc;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(e % kp.M); const long long j = (long long)(e / kp.M);
@@ -76,71 +119,35 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const double* __rest
         for (int d = 0; d < SGP_MAX_D; ++d)
             if (d < kp.D) acc[d] = fma(f, c[d], acc[d]);
     }
-    __shared__ double s[8][SGP_MAX_D];
-    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 0; d < SGP_MAX_D; ++d) {
-        double a = acc[d];
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) s[wp][d] = a;
-    }
-    __syncthreads();
-    if (threadIdx.x < SGP_MAX_D) {
-        double a = 0.0;
-        for (int q = 0; q < 8; ++q) a += s[q][threadIdx.x];
-        partial[(size_t)blockIdx.x * SGP_MAX_D + threadIdx.x] = a;
-    }
+    reduce_and_finish(acc, partial, ticket, 1.0, total_out, nullptr);
 }
 
-// partial[block][d] = sum over the block's (m, m') of B_mm' h_mm' c_mm'd   (K_uu part of the gradient)
-__global__ void __launch_bounds__(256) kuu_contract_kernel(const double* __restrict__ Z, const double* __restrict__ B, KParams kp, double* __restrict__ partial) {
-    double acc[SGP_MAX_D];
+// total[d] += scale * sum over (m, m') of B_mm' h_mm' c_mm'd   (K_uu part of the gradient);  *trace_out += tr B
+__global__ void __launch_bounds__(256) kuu_contract_kernel(const double* __restrict__ Z, const double* __restrict__ B, KParams kp, double* __restrict__ partial,
+                                                           unsigned* __restrict__ ticket, double scale, double* __restrict__ total_out,
+                                                           double* __restrict__ trace_out) {
+    double acc[kPS];
 #pragma unroll
-    for (int d = 0; d < SGP_MAX_D; ++d) acc[d] = 0.0;
+    for (int d = 0; d < kPS; ++d) acc[d] = 0.0;
     const size_t total = (size_t)kp.M * kp.M;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(e % kp.M), m2 = (int)(e / kp.M);
         double c[SGP_MAX_D];
         const double r2 = r2_of(Z + (size_t)m * kp.D, Z + (size_t)m2 * kp.D, kp, c);
-        const double f = h_of(kp, r2) * B[e];
+        const double b = B[e];
+        if (m == m2) acc[SGP_MAX_D] += b;
+        const double f = h_of(kp, r2) * b;
 #pragma unroll
         for (int d = 0; d < SGP_MAX_D; ++d)
             if (d < kp.D) acc[d] = fma(f, c[d], acc[d]);
     }
-    __shared__ double s[8][SGP_MAX_D];
-    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 0; d < SGP_MAX_D; ++d) {
-        double a = acc[d];
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) s[wp][d] = a;
-    }
-    __syncthreads();
-    if (threadIdx.x < SGP_MAX_D) {
-        double a = 0.0;
-        for (int q = 0; q < 8; ++q) a += s[q][threadIdx.x];
-        partial[(size_t)blockIdx.x * SGP_MAX_D + threadIdx.x] = a;
-    }
+    reduce_and_finish(acc, partial, ticket, scale, total_out, trace_out);
 }
 
-// total[d] += scale * sum_b partial[b][d]   (one thread per d, fixed order)
-__global__ void finish_kernel(const double* __restrict__ partial, int nblocks, double scale, double* __restrict__ total) {
-    const int d = threadIdx.x;
-    if (d >= SGP_MAX_D) return;
-    double a = 0.0;
-    for (int b = 0; b < nblocks; ++b) a += partial[(size_t)b * SGP_MAX_D + d];
-    total[d] += scale * a;
-}
-
-// out[0] = sum_i a[i*sa] * (b ? b[i*sb] : 1)   single block, fixed order
-__global__ void dot_kernel2(const double* __restrict__ a, size_t sa, const double* __restrict__ b, size_t sb, size_t n, double* __restrict__ out) {
-    __shared__ double s[256];
-    double v = 0.0;
-    for (size_t i = threadIdx.x; i < n; i += 256) v = fma(a[i * sa], b ? b[i * sb] : 1.0, v);
-    s[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) out[0] = s[0];
+// res[8 .. 12] = the four scalars of the statistics; res[12] = the pivot record of the factorisations: ONE read-back for the whole step
+__global__ void gather_kernel(const double* __restrict__ scal, const int* __restrict__ info, double* __restrict__ res) {
+    if (threadIdx.x < 4) res[8 + threadIdx.x] = scal[threadIdx.x];
+    if (threadIdx.x == 4) res[12] = (double)*info;
 }
 
 inline unsigned nb(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
@@ -176,12 +183,14 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
     // other call expects).  Only the data part of the gradient below is rank-local and summed at the end.
     int rc = SGP_OK;
     if (!(ctx->have_stats && ctx->stats_of_data && ctx->Dout == 1)) { rc = sgp_sweep_resident(ctx, false); if (rc) return rc; }
-    if (!(ctx->have_kuu && ctx->kuu_jitter == jitter)) { rc = sgp_kuu_factor(ctx, jitter, nullptr); if (rc) return rc; }
+    // (enqueued only: the whole step has ONE host synchronisation, at the end, where the pivot record is checked too)
+    const bool factored_here = !(ctx->have_kuu && ctx->kuu_jitter == jitter);
+    if (factored_here) { rc = sgp_kuu_factor_enqueue(ctx, jitter); if (rc) return rc; }
 
     const int nc_max = (int)std::min<int64_t>(N, std::max<int64_t>(1024, (int64_t)(16u << 20) / M));     // K and G chunks: 2 x 128 MB at most
     const int cblocks = 4 * ctx->num_sms;
     // scratch: [Rv | A | B | T] (M x M each) | v (M) | res (64) | totals (2 x SGP_MAX_D) | K chunk | G chunk | block partials
-    size_t need = 4 * MM + (size_t)M + 64 + 2 * SGP_MAX_D + (want_grad ? 2 * (size_t)M * nc_max + (size_t)cblocks * SGP_MAX_D : 0);
+    size_t need = 4 * MM + (size_t)M + 64 + 2 * SGP_MAX_D + (want_grad ? 2 * (size_t)M * nc_max + (size_t)cblocks * kPS : 0);
     rc = sgp_ensure(ctx, &ctx->theta_dev, &ctx->theta_cap, need); if (rc) return rc;
     double* Rv = ctx->theta_dev; double* A = Rv + MM; double* B = A + MM; double* T = B + MM;
     double* vdev = T + MM; double* res = vdev + M; double* total = res + 64; double* total_data = total + SGP_MAX_D; double* Kc = total_data + SGP_MAX_D;
@@ -192,8 +201,12 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
     // R_v = Uv' Uv (host posterior) or Sigma_v + mu_v mu_v' (resident posterior: no Cholesky factor needed); A = R_v - K_uu^-1
     const double* v = nullptr;
     if (mu_v) {
-        SGP_CUDA(ctx, cudaMemcpyAsync(T, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        SGP_CUDA(ctx, cudaMemcpyAsync(vdev, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        // (on the copy stream: the upload runs beside the sweep and the K_uu job enqueued above; T and vdev are free -- every earlier call
+        //  that used them has been synchronised by its own final read-back)
+        SGP_CUDA(ctx, cudaMemcpyAsync(T, Uv, MM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream2));
+        SGP_CUDA(ctx, cudaMemcpyAsync(vdev, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream2));
+        SGP_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream2));
+        SGP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
         rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, T, M, T, M, 0.0, Rv, M, 0); if (rc) return rc;
         amat_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, nullptr, Rv, nullptr, nullptr, Kinv, M);
         v = vdev;
@@ -203,8 +216,8 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
     }
     // scalars in one pass: <Kinv, Psi2>, <Rv, Psi2>, v' Psi1
     rc = sgp_wterms_reduce(ctx, Kinv, psi2, Rv, nullptr, v, psi1, M, res); if (rc) return rc;
-    SGP_CUDA(ctx, cudaMemsetAsync(total, 0, 2 * SGP_MAX_D * sizeof(double), ctx->stream));
-    SGP_CUDA(ctx, cudaMemsetAsync(res + 4, 0, sizeof(double), ctx->stream));
+    SGP_CUDA(ctx, cudaMemsetAsync(res + 4, 0, (60 + 2 * SGP_MAX_D) * sizeof(double), ctx->stream));      // tr B, the ticket word and both totals (contiguous)
+    unsigned* ticket = reinterpret_cast<unsigned*>(res + 5);
 
     if (want_grad) {
         KParams kp{}; kp.kind = ctx->kind; kp.D = D; kp.M = M; kp.variance = ctx->variance;
@@ -212,25 +225,30 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
         // B = Kinv Psi2 Kinv, tr B, K_uu part of the lengthscale gradient (from the rank-summed statistics: identical on every rank)
         rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, Kinv, M, psi2, M, 0.0, T, M, 0); if (rc) return rc;
         rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, T, M, Kinv, M, 0.0, B, M, 0); if (rc) return rc;
-        dot_kernel2<<<1, 256, 0, ctx->stream>>>(B, (size_t)M + 1, nullptr, 0, (size_t)M, res + 4);
-        kuu_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->Z_dev, B, kp, partial);
-        finish_kernel<<<1, 32, 0, ctx->stream>>>(partial, cblocks, 0.5 * w, total);
+        kuu_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->Z_dev, B, kp, partial, ticket, 0.5 * w, total, res + 4);
         // data part (this rank's points), chunk by chunk: K chunk -> G = A K -> contraction
         for (int64_t n0 = 0; n0 < N; n0 += nc_max) {
             const int nc = (int)std::min<int64_t>(nc_max, N - n0);
             kuf_chunk_kernel<<<nb((size_t)M * nc), 256, 0, ctx->stream>>>(ctx->X_dev, ctx->Z_dev, Kc, n0, nc, kp);
             rc = sgp_gemm(ctx, 0, 0, M, nc, M, 1.0, A, M, Kc, M, 0.0, Gc, M, 0); if (rc) return rc;
-            grad_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, v, w, n0, nc, kp, partial);
-            finish_kernel<<<1, 32, 0, ctx->stream>>>(partial, cblocks, 1.0, total_data);
+            grad_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, v, w, n0, nc, kp, partial, ticket, total_data);
         }
         if (ctx->comm) { rc = sgp_comm_allreduce(ctx, total_data, (size_t)SGP_MAX_D); if (rc) return rc; }     // the only rank-local part
     }
     SGP_CUDA(ctx, cudaGetLastError());
-    double h[8], sc[4], tot[2 * SGP_MAX_D];
-    SGP_CUDA(ctx, cudaMemcpyAsync(h, res, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SGP_CUDA(ctx, cudaMemcpyAsync(sc, scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SGP_CUDA(ctx, cudaMemcpyAsync(tot, total, 2 * SGP_MAX_D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    // ONE read-back and ONE host synchronisation for the whole step: [res (64) | totals (2 x SGP_MAX_D)] are contiguous
+    gather_kernel<<<1, 32, 0, ctx->stream>>>(scal, ctx->info_dev, res);
+    SGP_CUDA(ctx, cudaGetLastError());
+    double hb[64 + 2 * SGP_MAX_D];
+    SGP_CUDA(ctx, cudaMemcpyAsync(hb, res, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
     SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double* h = hb; const double* sc = hb + 8; const double* tot = hb + 64;
+    if (factored_here && hb[12] != 0.0) {
+        ctx->have_kuu = false;
+        char buf[160];
+        snprintf(buf, sizeof buf, "theta_objective: Cholesky of K_uu met a non-positive pivot at row %d of %d", (int)hb[12], M);
+        SGP_FAIL(ctx, SGP_ERR_NOT_PD, buf);
+    }
     if (value) *value = 0.5 * w * (sc[0] - h[0] + h[1]) - w * h[2];
     if (dvariance) *dvariance = (0.5 * w * sc[0] - 0.5 * w * h[0] + w * h[1] - w * h[2] - 0.5 * w * jitter * h[4]) / ctx->variance;
     if (dlengthscale) for (int d = 0; d < D; ++d) dlengthscale[d] = (tot[d] + tot[SGP_MAX_D + d]) / (ctx->ell[d] * ctx->ell[d] * ctx->ell[d]);
