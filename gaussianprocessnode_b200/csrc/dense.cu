@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) wterms_kernel(const double* __restrict__ 
     for (int c = c_lo + warp; c < c_hi; c += 8) {
         const size_t off = (size_t)c * M;
         const double mc = mu_outer ? mu_outer[c] : 0.0;
+#pragma unroll 4                                                 // (the loads of four iterations in flight)
         for (int r = lane; r < M; r += 32) {
             const double p2 = Psi2[off + r];
             if (Kinv) a0 = fma(Kinv[off + r], p2, a0);
@@ -75,10 +76,12 @@ __global__ void __launch_bounds__(256) wterms_kernel(const double* __restrict__ 
     __syncthreads();
     if (last) {
         __threadfence();
-        if (tid < 4) {
+        if (warp < 4) {                                        // a warp per scalar: strided partial sums, then a fixed-shape tree
             double v = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partial + 4 * b + tid);
-            out[tid] = v;
+            for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(partial + 4 * b + warp);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) out[warp] = v;
         }
         if (tid == 0) *ticket = 0u;                            // ready for the next call on this stream
     }

@@ -183,6 +183,75 @@ __device__ __forceinline__ void gemm_task(typename TL::Acc& acc, const double* _
 #undef TCLK
 }
 
+// The same for the plain GEMMs (long K, one tile per CTA): the staging area is DOUBLE-BUFFERED, so a warp that has finished the DMMAs of chunk k
+// stores chunk k + 1 into the other buffer while the slower warps still multiply -- one barrier per chunk instead of two, and no
+// store phase in which the DMMA pipe idles.  buf: 2 x (TR x LDA + KC x LDB) doubles.  Warp tiles of 16 x 16 and larger only.
+template <class TL>
+__device__ __forceinline__ void gemm_task_db(typename TL::Acc& acc, const double* __restrict__ A, size_t a_rs, size_t a_ks, int rows,
+                                             const double* __restrict__ B, size_t b_ks, size_t b_cs, int cols, int K, double* __restrict__ buf) {
+    static_assert(TL::MI * TL::NJ > 2, "large warp tiles only");
+    constexpr int TR = TL::WTR * (8 / TL::WC), TC = TL::WTC * TL::WC, KC = TL::KC, SA = TR * TL::LDA, SB = KC * TL::LDB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp / TL::WC, wc = warp % TL::WC;
+    double ra[TL::AP], rb[TL::BP];
+    const bool a_rowfast = a_rs == 1, b_colfast = b_cs == 1;
+    auto dec_a = [&](int e, int& r, int& kk) {
+        const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
+        if (a_rowfast) { r = lo + 8 * (rest % (TR / 8)); kk = mid + 4 * (rest / (TR / 8)); }
+        else { kk = lo + 8 * (rest % (KC / 8)); r = mid + 4 * (rest / (KC / 8)); }
+    };
+    auto dec_b = [&](int e, int& c, int& kk) {
+        const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
+        if (b_colfast) { c = lo + 8 * (rest % (TC / 8)); kk = mid + 4 * (rest / (TC / 8)); }
+        else { kk = lo + 8 * (rest % (KC / 8)); c = mid + 4 * (rest / (KC / 8)); }
+    };
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < TL::AP; ++q) {
+            int r, kk; dec_a(tid + q * CT, r, kk);
+            ra[q] = (r < rows && k0 + kk < K) ? A[(size_t)r * a_rs + (size_t)(k0 + kk) * a_ks] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < TL::BP; ++q) {
+            int c, kk; dec_b(tid + q * CT, c, kk);
+            rb[q] = (c < cols && k0 + kk < K) ? B[(size_t)(k0 + kk) * b_ks + (size_t)c * b_cs] : 0.0;
+        }
+    };
+    auto sstore = [&](double* __restrict__ As, double* __restrict__ Bs) {
+#pragma unroll
+        for (int q = 0; q < TL::AP; ++q) { int r, kk; dec_a(tid + q * CT, r, kk); As[r * TL::LDA + kk] = ra[q]; }
+#pragma unroll
+        for (int q = 0; q < TL::BP; ++q) { int c, kk; dec_b(tid + q * CT, c, kk); Bs[kk * TL::LDB + c] = rb[q]; }
+    };
+    gload(0);
+    sstore(buf, buf + SA);
+    __syncthreads();
+    int cur = 0;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        const double* As = buf + cur * (SA + SB); const double* Bs = As + SA;
+        const bool more = k0 + KC < K;
+        if (more) gload(k0 + KC);
+#pragma unroll
+        for (int ks = 0; ks < KC / 4; ++ks) {
+            double a[TL::MI], b[TL::NJ];
+#pragma unroll
+            for (int i = 0; i < TL::MI; ++i) a[i] = As[(wr * TL::WTR + 8 * i + (lane >> 2)) * TL::LDA + ks * 4 + (lane & 3)];
+#pragma unroll
+            for (int j = 0; j < TL::NJ; ++j) b[j] = Bs[(ks * 4 + (lane & 3)) * TL::LDB + wc * TL::WTC + 8 * j + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < TL::MI; ++i)
+#pragma unroll
+                for (int j = 0; j < TL::NJ; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+        }
+        if (more) {
+            double* An = buf + (cur ^ 1) * (SA + SB);
+            sstore(An, An + SA);           // (the other buffer was last read before the previous barrier)
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
 // C(r, c) = alpha acc + beta C(r, c), r < rows, c < cols; C column-major (ldc).  lower_only: only elements with grow0 + r >= gcol0 + c.
 // Ct (optional): the same value to Ct(c, r) (mirror of a symmetric result).
 template <class TL>
@@ -210,7 +279,7 @@ __device__ __forceinline__ void store_task(const typename TL::Acc& acc, double* 
 using T64 = Tile<64, 64, 4, 32>;      // warp tile 16 x 32
 using T32 = Tile<32, 32, 4, 64>;      // warp tile  8 x 16: little MMA work per chunk, so a long chunk per barrier pair
 using T16 = Tile<16, 64, 2, 64>;      // row strip: warp tile 8 x 16
-using T63 = Tile<64, 32, 4, 32>;      // 64 x 32: warp tile 16 x 16
+using T63 = Tile<64, 32, 4, 64>;      // 64 x 32: warp tile 16 x 16, long chunks (the plain GEMMs: K is long)
 using TX = Tile<64, 16, 8, 64>;       // column slice of a row block of X: warp tile 8 x 16
 
 // The 32 x 32 sub-tile task every phase is made of, as ONE non-inlined routine (the kernel's instruction footprint decides its speed: each
@@ -893,14 +962,19 @@ __global__ void __launch_bounds__(CT) gemm2_kernel(const Gemm2Args g) {
         const double* Ab = g.opA == 0 ? g.A + (size_t)ti * TSR : g.A + (size_t)ti * TSR * g.lda;
         const double* Bb = g.opB == 0 ? g.B + (size_t)tj * TSC * g.ldb : g.B + (size_t)tj * TSC;
         typename TL::Acc acc; acc_zero<TL>(acc);
-        gemm_task<TL>(acc, Ab, g.opA == 0 ? 1 : (size_t)g.lda, g.opA == 0 ? (size_t)g.lda : 1, rows, Bb, g.opB == 0 ? 1 : (size_t)g.ldb,
-                      g.opB == 0 ? (size_t)g.ldb : 1, cols, g.k, As, Bs);
+        const int kk = g.lower_only == 2 ? min(g.k, (tj + 1) * TSC) : g.k;      // C = U'U, U upper triangular: column c needs k <= c only
+        if constexpr (TL::MI * TL::NJ > 2)
+            gemm_task_db<TL>(acc, Ab, g.opA == 0 ? 1 : (size_t)g.lda, g.opA == 0 ? (size_t)g.lda : 1, rows, Bb, g.opB == 0 ? 1 : (size_t)g.ldb,
+                             g.opB == 0 ? (size_t)g.ldb : 1, cols, kk, sm);
+        else
+            gemm_task<TL>(acc, Ab, g.opA == 0 ? 1 : (size_t)g.lda, g.opA == 0 ? (size_t)g.lda : 1, rows, Bb, g.opB == 0 ? 1 : (size_t)g.ldb,
+                          g.opB == 0 ? (size_t)g.ldb : 1, cols, kk, As, Bs);
         store_task<TL>(acc, g.C + (size_t)ti * TSR + (size_t)tj * TSC * g.ldc, g.ldc, rows, cols, g.alpha, g.beta);
     }
 }
 template <class TL, int TSR, int TSC>
 int launch_gemm2(sgp_ctx* ctx, const Gemm2Args& g, int grid) {
-    const size_t smem = (size_t)(STAGE_A + STAGE_B) * sizeof(double);
+    const size_t smem = TL::MI * TL::NJ > 2 ? (size_t)2 * (TSR * TL::LDA + TL::KC * TL::LDB) * sizeof(double) : (size_t)(STAGE_A + STAGE_B) * sizeof(double);
     SGP_CUDA(ctx, cudaFuncSetAttribute(gemm2_kernel<TL, TSR, TSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm2_kernel<TL, TSR, TSC><<<grid, CT, smem, ctx->stream>>>(g);
     SGP_CUDA(ctx, cudaGetLastError());

@@ -136,6 +136,16 @@ struct SgpDenseJob {
     int reset_info = 1;        // zero ctx->info_dev before the launch
 };
 int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& job);                          // enqueues; no host synchronisation
+// pinned host staging for the small read-backs (ctx->fetch_host), at least n doubles; nullptr on failure
+inline double* sgp_host_stage(sgp_ctx* ctx, size_t n) {
+    if (ctx->fetch_cap < n) {
+        if (ctx->fetch_host) cudaFreeHost(ctx->fetch_host);
+        ctx->fetch_host = nullptr; ctx->fetch_cap = 0;
+        if (cudaHostAlloc((void**)&ctx->fetch_host, (n + 1024) * sizeof(double), cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        ctx->fetch_cap = n + 1024;
+    }
+    return ctx->fetch_host;
+}
 int sgp_kuu_factor_enqueue(sgp_ctx* ctx, double jitter);                         // api.cu: K_uu job without the host synchronisation
 int sgp_dense_info(sgp_ctx* ctx, const char* what);                               // synchronises; non-positive pivot -> SGP_ERR_NOT_PD
 int sgp_potrf_lower(sgp_ctx* ctx, double* A, int M);                              // in place, column-major, lower (synchronises)

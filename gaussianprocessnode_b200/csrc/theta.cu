@@ -16,6 +16,9 @@
 #include <cmath>
 #include <algorithm>
 #include <vector>
+#include <utility>
+#include <cstdio>
+#include <cstdlib>
 
 int sgp_gemm(sgp_ctx* ctx, int opA, int opB, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc, int lower_only);
@@ -30,8 +33,9 @@ struct KParams {
 
 __device__ __forceinline__ double r2_of(const double* __restrict__ x, const double* __restrict__ z, const KParams& kp, double* c) {
     double r2 = 0.0;
-    for (int d = 0; d < kp.D; ++d) {
-        const double t = x[d] - z[d];
+#pragma unroll                                                    // (static indices: c stays in registers)
+    for (int d = 0; d < SGP_MAX_D; ++d) {
+        const double t = d < kp.D ? x[d] - z[d] : 0.0;
         c[d] = t * t;                                             // (x_d - z_d)^2, unscaled
         r2 = fma(c[d], kp.ell_inv[d] * kp.ell_inv[d], r2);
     }
@@ -77,7 +81,7 @@ __device__ __forceinline__ void reduce_and_finish(const double (&acc)[kPS], doub
     if (threadIdx.x < kPS) {
         double a = 0.0;
         for (int q = 0; q < 8; ++q) a += s[q][threadIdx.x];
-        partial[(size_t)blockIdx.x * kPS + threadIdx.x] = a;
+        partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = a;          // [d][block]: the finish reads along the blocks
     }
     __threadfence();
     __syncthreads();
@@ -91,7 +95,8 @@ __device__ __forceinline__ void reduce_and_finish(const double (&acc)[kPS], doub
     __threadfence();
     for (int d = wp; d < kPS; d += 8) {
         double a = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) a += __ldcg(partial + (size_t)b * kPS + d);
+#pragma unroll 4
+        for (int b = lane; b < (int)gridDim.x; b += 32) a += __ldcg(partial + (size_t)d * gridDim.x + b);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (lane == 0) {
@@ -152,12 +157,14 @@ __global__ void gather_kernel(const double* __restrict__ scal, const int* __rest
 
 inline unsigned nb(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
-// A = (R ? R : Sig + mu mu') - Kinv, and Rv (optional) = that first term
-__global__ void amat_kernel(double* __restrict__ A, double* __restrict__ Rv, const double* __restrict__ R, const double* __restrict__ Sig, const double* __restrict__ mu,
+// A = (R ? R : Sig + mu mu') - Kinv, and Rv (optional) = that first term.  R: only its lower triangle is read (Rv may be R itself: the
+// mirror is written into the part nobody reads).
+__global__ void amat_kernel(double* __restrict__ A, double* Rv, const double* R, const double* __restrict__ Sig, const double* __restrict__ mu,
                             const double* __restrict__ Kinv, int M) {
     const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (e >= (size_t)M * M) return;
-    const double r = R ? R[e] : fma(mu[e % M], mu[e / M], Sig[e]);
+    const size_t i = e % M, j = e / M;
+    const double r = R ? R[i >= j ? e : j + i * M] : fma(mu[i], mu[j], Sig[e]);
     if (Rv) Rv[e] = r;
     A[e] = r - Kinv[e];
 }
@@ -182,13 +189,23 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
     // those, otherwise the regular sweep runs (with a communicator: summed over the ranks, so that the resident statistics stay what every
     // other call expects).  Only the data part of the gradient below is rank-local and summed at the end.
     int rc = SGP_OK;
+    // tuning aid (SGP_THETA_TIMING=1): device time of every stage on stdout
+    static const bool timing = std::getenv("SGP_THETA_TIMING") != nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    auto mark = [&](const char* name) {
+        if (!timing) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); marks.emplace_back(name, e);
+    };
+    mark("start");
     if (!(ctx->have_stats && ctx->stats_of_data && ctx->Dout == 1)) { rc = sgp_sweep_resident(ctx, false); if (rc) return rc; }
+    mark("sweep");
     // (enqueued only: the whole step has ONE host synchronisation, at the end, where the pivot record is checked too)
     const bool factored_here = !(ctx->have_kuu && ctx->kuu_jitter == jitter);
     if (factored_here) { rc = sgp_kuu_factor_enqueue(ctx, jitter); if (rc) return rc; }
+    mark("K_uu job");
 
     const int nc_max = (int)std::min<int64_t>(N, std::max<int64_t>(1024, (int64_t)(16u << 20) / M));     // K and G chunks: 2 x 128 MB at most
-    const int cblocks = 4 * ctx->num_sms;
+    const int cblocks = 2 * ctx->num_sms;
     // scratch: [Rv | A | B | T] (M x M each) | v (M) | res (64) | totals (2 x SGP_MAX_D) | K chunk | G chunk | block partials
     size_t need = 4 * MM + (size_t)M + 64 + 2 * SGP_MAX_D + (want_grad ? 2 * (size_t)M * nc_max + (size_t)cblocks * kPS : 0);
     rc = sgp_ensure(ctx, &ctx->theta_dev, &ctx->theta_cap, need); if (rc) return rc;
@@ -207,15 +224,17 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
         SGP_CUDA(ctx, cudaMemcpyAsync(vdev, mu_v, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream2));
         SGP_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream2));
         SGP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
-        rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, T, M, T, M, 0.0, Rv, M, 0); if (rc) return rc;
-        amat_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, nullptr, Rv, nullptr, nullptr, Kinv, M);
+        rc = sgp_gemm(ctx, 1, 0, M, M, M, 1.0, T, M, T, M, 0.0, Rv, M, 2); if (rc) return rc;      // lower triangle, triangular K range
+        amat_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, Rv, Rv, nullptr, nullptr, Kinv, M);
         v = vdev;
     } else {
         v = sgp_resident_mu(ctx);
         amat_kernel<<<nb(MM), 256, 0, ctx->stream>>>(A, Rv, nullptr, sgp_resident_sigma(ctx), v, Kinv, M);
     }
+    mark("R_v, A");
     // scalars in one pass: <Kinv, Psi2>, <Rv, Psi2>, v' Psi1
     rc = sgp_wterms_reduce(ctx, Kinv, psi2, Rv, nullptr, v, psi1, M, res); if (rc) return rc;
+    mark("scalars");
     SGP_CUDA(ctx, cudaMemsetAsync(res + 4, 0, (60 + 2 * SGP_MAX_D) * sizeof(double), ctx->stream));      // tr B, the ticket word and both totals (contiguous)
     unsigned* ticket = reinterpret_cast<unsigned*>(res + 5);
 
@@ -224,8 +243,12 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
         for (int d = 0; d < D; ++d) kp.ell_inv[d] = 1.0 / ctx->ell[d];
         // B = Kinv Psi2 Kinv, tr B, K_uu part of the lengthscale gradient (from the rank-summed statistics: identical on every rank)
         rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, Kinv, M, psi2, M, 0.0, T, M, 0); if (rc) return rc;
+        // (B in full, not its lower triangle mirrored: with an ill-conditioned K_uu the rounding of (Kinv Psi2) Kinv is far from symmetric
+        //  and the contraction below relies on the two halves averaging out, as the reference's does)
         rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, T, M, Kinv, M, 0.0, B, M, 0); if (rc) return rc;
+        mark("B = Kinv Psi2 Kinv");
         kuu_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->Z_dev, B, kp, partial, ticket, 0.5 * w, total, res + 4);
+        mark("K_uu contraction");
         // data part (this rank's points), chunk by chunk: K chunk -> G = A K -> contraction
         for (int64_t n0 = 0; n0 < N; n0 += nc_max) {
             const int nc = (int)std::min<int64_t>(nc_max, N - n0);
@@ -233,15 +256,25 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
             rc = sgp_gemm(ctx, 0, 0, M, nc, M, 1.0, A, M, Kc, M, 0.0, Gc, M, 0); if (rc) return rc;
             grad_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, v, w, n0, nc, kp, partial, ticket, total_data);
         }
+        mark("data part (K chunk, G = A K, contraction)");
         if (ctx->comm) { rc = sgp_comm_allreduce(ctx, total_data, (size_t)SGP_MAX_D); if (rc) return rc; }     // the only rank-local part
     }
     SGP_CUDA(ctx, cudaGetLastError());
     // ONE read-back and ONE host synchronisation for the whole step: [res (64) | totals (2 x SGP_MAX_D)] are contiguous
     gather_kernel<<<1, 32, 0, ctx->stream>>>(scal, ctx->info_dev, res);
     SGP_CUDA(ctx, cudaGetLastError());
-    double hb[64 + 2 * SGP_MAX_D];
-    SGP_CUDA(ctx, cudaMemcpyAsync(hb, res, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+    double* hb = sgp_host_stage(ctx, 64 + 2 * SGP_MAX_D);
+    if (!hb) SGP_FAIL(ctx, SGP_ERR_CUDA, "theta_objective: pinned staging buffer");
+    SGP_CUDA(ctx, cudaMemcpyAsync(hb, res, (64 + 2 * SGP_MAX_D) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    mark("read-back");
     SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (timing) {
+        printf("theta step M=%d N=%lld:", M, (long long)N);
+        for (size_t i = 1; i < marks.size(); ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second); printf(" %s %.1f us |", marks[i].first, ms * 1e3f); }
+        float ms = 0.f; cudaEventElapsedTime(&ms, marks.front().second, marks.back().second); printf(" total %.1f us\n", ms * 1e3f);
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        fflush(stdout);
+    }
     const double* h = hb; const double* sc = hb + 8; const double* tot = hb + 64;
     if (factored_here && hb[12] != 0.0) {
         ctx->have_kuu = false;
