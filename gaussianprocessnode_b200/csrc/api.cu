@@ -102,7 +102,7 @@ int sgp_create(sgp_ctx** out, int device_id) {
     if (cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail("event");
     if (cudaMalloc((void**)&ctx->exptab_dev, SGP_EXP_TAB * sizeof(double)) != cudaSuccess) return fail("malloc");
-    if (cudaMalloc((void**)&ctx->info_dev, sizeof(int)) != cudaSuccess) return fail("malloc");
+    if (cudaMalloc((void**)&ctx->info_dev, 2 * sizeof(int)) != cudaSuccess) return fail("malloc");
     std::vector<double> tab(SGP_EXP_TAB);
     for (int j = 0; j < SGP_EXP_TAB; ++j) tab[j] = std::exp2((double)j / SGP_EXP_TAB);
     if (cudaMemcpy(ctx->exptab_dev, tab.data(), SGP_EXP_TAB * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return fail("memcpy");
@@ -156,7 +156,7 @@ int sgp_set_inducing(sgp_ctx* ctx, int M, const double* Z) {
     }
     SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->M = M; ctx->have_Z = true; ctx->have_kuu = false; ctx->have_stats = false;
-    size_t need = (size_t)4 * M * M + 4 * (size_t)M + 64;
+    size_t need = (size_t)6 * M * M + 4 * (size_t)M + 64 + 2;      // (the last two M x M blocks: scratch of a K_uu job that shares the posterior's launch)
     return sgp_ensure(ctx, &ctx->dense_dev, &ctx->dense_cap, need);
 }
 
@@ -420,7 +420,7 @@ int sgp_stats_dev(sgp_ctx* ctx, double** psi2_dev, double** psi1_dev, double** s
 }  // extern "C"
 // Enqueues the K_uu job without synchronising: the caller checks the pivot record (sgp_dense_info, or its own read of ctx->info_dev) when it
 // next synchronises, and clears ctx->have_kuu if that fails.
-int sgp_kuu_factor_enqueue(sgp_ctx* ctx, double jitter) {
+static int kuu_job_prepare(sgp_ctx* ctx, double jitter, double* scratch /* 2 M x M */, SgpDenseJob& j) {
     const int M = ctx->M;
     if (ctx->KuuL_M != M) {
         if (ctx->KuuL_dev) SGP_CUDA(ctx, cudaFree(ctx->KuuL_dev));
@@ -435,11 +435,15 @@ int sgp_kuu_factor_enqueue(sgp_ctx* ctx, double jitter) {
     // -> X = L^-1 -> K_uu^-1 = X' X, which the :w rule / energy / theta step contract with Psi2
     const size_t nd = (size_t)((M + 63) / 64) * 64 * 64, MM = (size_t)M * M;
     int rc = sgp_ensure_zero(ctx, &ctx->kuu_dinv_dev, &ctx->kuu_dinv_cap, nd); if (rc) return rc;
-    double* d = ctx->dense_dev + 64;
+    j = SgpDenseJob{};
+    j.M = M; j.build = 2; j.jitter = jitter; j.A = ctx->KuuL_dev; j.Dinv = ctx->kuu_dinv_dev; j.X = scratch; j.Tmp = scratch + MM; j.S = ctx->Kinv_dev;
+    return SGP_OK;
+}
+int sgp_kuu_factor_enqueue(sgp_ctx* ctx, double jitter) {
     SgpDenseJob j;
-    j.M = M; j.build = 2; j.jitter = jitter; j.A = ctx->KuuL_dev; j.Dinv = ctx->kuu_dinv_dev; j.X = d; j.Tmp = d + MM; j.S = ctx->Kinv_dev;
+    int rc = kuu_job_prepare(ctx, jitter, ctx->dense_dev + 64, j); if (rc) return rc;
     rc = sgp_dense_job(ctx, j); if (rc) return rc;
-    ctx->have_kuu = true; ctx->kuu_jitter = jitter;
+    ctx->have_kuu = true; ctx->kuu_jitter = jitter; ctx->kuu_jitter_known = true;
     return SGP_OK;
 }
 extern "C" {
@@ -514,7 +518,15 @@ static int posterior_core(sgp_ctx* ctx, double w, bool carry, bool want_uv, doub
     a.M = M; a.build = 1; a.S2 = psi2; a.s1 = psi1; a.P = post_LamP(ctx); a.xip = post_xiP(ctx); a.xi = xi; a.w = w; a.carry = carry ? 1 : 0;
     a.A = Lam; a.Dinv = ctx->dinv_dev; a.X = X; a.Tmp = T; a.S = post_Sig(ctx); a.mu = post_mu(ctx);
     if (flip) { a.flip = 1; a.S = d + 2 * MM; a.Sout = post_Sig(ctx); if (want_uv) a.Uv = post_Uv(ctx); }
-    rc = sgp_dense_job(ctx, a); if (rc) return rc;
+    // K_uu stale (new theta or inducing points) and a jitter on record: its factorisation + inverse share this launch -- a job is a serial chain on
+    // ONE CTA with the others mostly waiting, so the second job costs next to nothing (kin40k mini-batch schedule: prod, then the theta step).
+    // Speculative: a non-positive pivot there is not this call's error (the next sgp_kuu_factor / theta step reports it).
+    static const bool no_fuse = std::getenv("SGP_DENSE_FUSE_KUU") != nullptr && std::atoi(std::getenv("SGP_DENSE_FUSE_KUU")) == 0;
+    const bool with_kuu = !no_fuse && !ctx->have_kuu && ctx->kuu_jitter_known && ctx->have_kernel && ctx->have_Z;
+    SgpDenseJob kj;
+    if (with_kuu) { rc = kuu_job_prepare(ctx, ctx->kuu_jitter, d + 4 * MM + ((4 * (size_t)M + 1) & ~(size_t)1), kj); if (rc) return rc; }
+    rc = sgp_dense_job(ctx, a, with_kuu ? &kj : nullptr); if (rc) return rc;
+    ctx->kuu_speculative = with_kuu;
     ctx->have_post = true; ctx->have_post_uv = flip && want_uv;
     if (flip) want_uv = false;                                  // (done)
     const bool early = (Sigma_v || mu_v) && want_uv;            // something to copy while the second factorisation runs
@@ -538,6 +550,10 @@ static int posterior_core(sgp_ctx* ctx, double w, bool carry, bool want_uv, doub
         if (mu_v) SGP_CUDA(ctx, cudaMemcpyAsync(mu_v, post_mu(ctx), (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     rc = sgp_dense_info(ctx, "posterior_v");                   // the one host synchronisation of the call
+    if (ctx->kuu_speculative) {
+        ctx->kuu_speculative = false;
+        if (rc == SGP_OK && ctx->info2_last == 0) ctx->have_kuu = true;      // (jitter unchanged: ctx->kuu_jitter)
+    }
     if (early && cudaStreamSynchronize(ctx->stream2) != cudaSuccess && rc == SGP_OK) { ctx->err = "posterior_v: copy stream failure"; rc = SGP_ERR_CUDA; }
     if (rc) { ctx->have_post = ctx->have_post_uv = false; }
     return rc;

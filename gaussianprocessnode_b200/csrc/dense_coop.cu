@@ -31,6 +31,7 @@ constexpr int CT = 256;       // threads per CTA (8 warps)
 constexpr int STAGE_A = TB * (64 + 4), STAGE_B = 64 * (TB + 4);          // staging of the largest tile configurations (Tile::LDA/LDB)
 constexpr int LDT = TB + 4;   // leading dimension of the 64 x 64 shared-memory blocks (= 4 mod 16: conflict-free DMMA fragment loads)
 static_assert(4 * SGP_FLIP_UV_MAX_M <= 2 * 64 * 68 + 66 + 2 * 64 * 68, "p, G and the scan buffers in shared memory");
+constexpr int kFineTiles = 148;   // S tiles of the last step / final update as 32 x 32 when 4 x their number fits about one round of a full grid (a function of M only: results do not depend on the grid)
 constexpr int kPParts = 4;    // partial sums per row strip of p = X xi (more CTAs on a memory-latency-bound pass)
 constexpr int SMEM_DOUBLES = 2 * TB * LDT + TB + 2 + STAGE_A + STAGE_B;     // T | Xi | rdiag | progress word | As | Bs
 
@@ -606,12 +607,23 @@ struct DenseJob {
     long long* clk;                        // optional: CTA 0's clocks {build, factor, panel, trailing (+ X rows / S updates on the last step), barriers, mu, last S update, tail | inside factor: ...}
 };
 
-__global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant__ DenseJob j) {
+// One or TWO independent jobs of the same M per launch: every job is a serial chain on its own CTA 0 with the other CTAs waiting on it most of
+// the time, so a second job (the N-th prod's Lambda and K_uu at a new theta, in the mini-batch schedule) runs in the shadow of the first.  CTAs are
+// dealt alternately; both halves execute the same grid barriers (same block count; `sync_build` / `sync_tail` are the OR over the jobs).
+struct DenseJobs {
+    DenseJob job[2];
+    int njobs, sync_build, sync_tail;
+};
+
+__global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant__ DenseJobs jj) {
+    const int jsel = jj.njobs == 2 ? (int)(blockIdx.x & 1u) : 0;
+    const DenseJob& j = jj.job[jsel];
     extern __shared__ double sm[];
     double* T = sm; double* Xi = T + TB * LDT; double* rdiag = Xi + TB * LDT; double* As = rdiag + TB + 2; double* Bs = As + STAGE_A;
     double* Lc = As;        // the factorisation's column-major scratch (32 x LCS) shares the GEMM staging area: never live together
     cg::grid_group grid = cg::this_grid();
-    const int M = j.M, nblk = (M + TB - 1) / TB, ncta = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncta = jj.njobs == 2 ? ((int)gridDim.x + 1 - jsel) / 2 : (int)gridDim.x, cta = jj.njobs == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int M = j.M, nblk = (M + TB - 1) / TB, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t MM = (size_t)M * M;
     double* __restrict__ A = j.A;
     long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fc[4] = {0, 0, 0, 0}, t0 = clock64(), t1;
@@ -663,7 +675,7 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
     } else if (j.build == 3) {
         for (size_t e = (size_t)cta * CT + tid; e < MM; e += (size_t)ncta * CT) A[e] = fma(j.mu_in[e % M], j.mu_in[e / M], j.Sig[e]);
     }
-    if (j.build) grid.sync();        // (grid.sync orders every thread's earlier stores: no explicit fence in front of the barriers)
+    if (jj.sync_build) grid.sync();  // (grid.sync orders every thread's earlier stores: no explicit fence in front of the barriers)
     DCLK(0);
 
     // ---- Cholesky ----------------------------------------------------------------------------------------------------------------
@@ -746,7 +758,7 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
         const int n_p = (X && k >= 1) ? nb * k : 0;
         int n_s = (X && j.S && k >= 1) ? k * (k + 1) / 2 : 0;
         const int n_x = X ? 4 * k + 1 : 0;
-        const bool s32 = !has_next && n_s > 0 && 3 * n_s <= nw;           // last step (nobody factorises meanwhile): finer tasks when they fit one round
+        const bool s32 = !has_next && n_s > 0 && 3 * n_s <= kFineTiles;           // last step (nobody factorises meanwhile): finer tasks when they fit one round
         if (s32) n_s = k * (2 * k + 1);
         for (int t = w; t < n_tr + n_p + n_s + n_x; t += nw) {
             if (t < n_tr) trailing_tile(k, t);
@@ -789,7 +801,7 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
         DCLK(4);
     }
     if (X && j.S) {       // the last row block of X into S (every tile receives its last contribution here: mirrored on the way out), then mu
-        if (3 * nblk * (nblk + 1) / 2 <= ncta) {
+        if (3 * nblk * (nblk + 1) / 2 <= kFineTiles) {
             const int n32 = (M + 31) / 32;
             for (int t = cta; t < n32 * (n32 + 1) / 2; t += ncta) s_tile32(nblk - 1, t, true);
         } else {
@@ -820,7 +832,9 @@ __global__ void __launch_bounds__(CT, 1) dense_job_kernel(const __grid_constant_
             }
         }
         DCLK(6);
-        if (j.mu || j.flip) grid.sync();
+    }
+    if (jj.sync_tail) grid.sync();
+    if (X && j.S) {
         if (!j.flip) {
             if (j.mu)          // mu = S xi: a warp per column of the symmetric S (fixed-shape tree: deterministic)
                 for (int i = cta * (CT / 32) + warp; i < M; i += ncta * (CT / 32)) {
@@ -983,10 +997,10 @@ int launch_gemm2(sgp_ctx* ctx, const Gemm2Args& g, int grid) {
 
 }  // namespace
 
-// One cooperative launch of dense_job_kernel on the ctx stream.  The caller checks *info_dev (sgp_dense_info) when it next synchronises.
-int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in) {
-    DenseJob j{};
-    j.M = in.M; j.build = in.build; j.A = in.A; j.Dinv = in.Dinv; j.info = ctx->info_dev;
+// One cooperative launch of dense_job_kernel on the ctx stream: job `in`, and optionally a second independent job `in2` of the same M beside
+// it (pivot record of the second job: ctx->info_dev[1]).  The caller checks *info_dev (sgp_dense_info) when it next synchronises.
+static int fill_job(sgp_ctx* ctx, const SgpDenseJob& in, DenseJob& j, int* info) {
+    j.M = in.M; j.build = in.build; j.A = in.A; j.Dinv = in.Dinv; j.info = info;
     j.S2 = in.S2; j.s1 = in.s1; j.P = in.P; j.xip = in.xip; j.xi = in.xi; j.w = in.w; j.carry = in.carry;
     j.Z = ctx->Z_dev; j.D = ctx->D; j.kind = ctx->kind; j.variance = ctx->variance; j.jitter = in.jitter;
     for (int d = 0; d < SGP_MAX_D; ++d) j.ell_inv[d] = d < ctx->D ? 1.0 / ctx->ell[d] : 0.0;
@@ -995,6 +1009,23 @@ int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in) {
     if (j.mu && !(j.S && j.xi)) SGP_FAIL(ctx, SGP_ERR_ARG, "dense job: mu needs S and xi");
     if (j.flip && !(j.build == 1 && j.X && j.S && j.Sout)) SGP_FAIL(ctx, SGP_ERR_ARG, "dense job: the reversed order is for build 1 with X, S and Sout");
     if (j.Uv && !(j.flip && j.mu && j.M <= SGP_FLIP_UV_MAX_M)) SGP_FAIL(ctx, SGP_ERR_ARG, "dense job: Uv needs the reversed order, mu and M <= 4096");
+    return SGP_OK;
+}
+int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in, const SgpDenseJob* in2) {
+    DenseJobs jj{};
+    int rc = fill_job(ctx, in, jj.job[0], ctx->info_dev); if (rc) return rc;
+    jj.njobs = 1;
+    if (in2) {
+        if (in2->M != in.M) SGP_FAIL(ctx, SGP_ERR_ARG, "dense job: two jobs in one launch need the same M");
+        rc = fill_job(ctx, *in2, jj.job[1], ctx->info_dev + 1); if (rc) return rc;
+        jj.njobs = 2;
+    }
+    for (int q = 0; q < jj.njobs; ++q) {
+        const DenseJob& j = jj.job[q];
+        jj.sync_build |= j.build != 0;
+        jj.sync_tail |= (j.X && j.S && (j.mu || j.flip)) ? 1 : 0;
+    }
+    DenseJob& j = jj.job[0];
     const int M = in.M, nblk = (M + TB - 1) / TB, n32 = (M + 31) / 32;
     const size_t smem = SMEM_DOUBLES * sizeof(double);
     SGP_CUDA(ctx, cudaFuncSetAttribute(dense_job_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1005,9 +1036,10 @@ int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_job_kernel, CT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     int want = std::max(1, n32 * (n32 + 1) / 2);                    // the widest phases: trailing sub-tiles of the first panel, S = X'X
     if (nblk == 1 && !in.X) want = 1;
-    const int grid = std::max(1, std::min(want, per_sm * ctx->num_sms));
-    if (in.reset_info) SGP_CUDA(ctx, cudaMemsetAsync(ctx->info_dev, 0, sizeof(int), ctx->stream));
-    void* args[] = {&j};
+    if (in2) want = std::max(2, 2 * want);
+    const int grid = std::max(jj.njobs, std::min(want, per_sm * ctx->num_sms));
+    if (in.reset_info) SGP_CUDA(ctx, cudaMemsetAsync(ctx->info_dev, 0, 2 * sizeof(int), ctx->stream));
+    void* args[] = {&jj};
     SGP_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)dense_job_kernel, dim3(grid), dim3(CT), args, smem, ctx->stream));
     SGP_CUDA(ctx, cudaGetLastError());
     if (clk_dev) {
@@ -1015,10 +1047,9 @@ int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in) {
         SGP_CUDA(ctx, cudaMemcpyAsync(c, clk_dev, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
         SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(clk_dev);
-        printf("dense job M=%d build=%d grid=%d: clocks build %lld | factor %lld | panel %lld | trailing %lld | barriers %lld | mu %lld | last S update %lld | tail %lld || factor: chol32 %lld | inv32 %lld | products %lld | write-out %lld\n",
-               M, in.build, grid, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10], c[11]);
-        printf("    CTA 0's 32x32 tasks: %lld tasks, %lld chunks: barrier %lld | load+stage %lld | mma %lld ;  64x64 diagonal updates: barrier %lld | load+stage %lld | mma %lld\n",
-               c[15], c[16], c[12], c[13], c[14], c[20], c[21], c[22]);
+        printf("dense job M=%d build=%d jobs=%d grid=%d: clocks build %lld | factor %lld | panel %lld | next diagonal block (+ the last step's tasks) %lld | barriers %lld | mu, Uv %lld | last S update %lld | tail %lld || factor: chol32 %lld | inv32 %lld | products %lld | write-out %lld\n",
+               M, in.build, jj.njobs, grid, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10], c[11]);
+        printf("    CTA 0's tile tasks: %lld tasks, %lld chunks: barrier %lld | load+stage %lld | mma %lld\n", c[15], c[16], c[12], c[13], c[14]);
         fflush(stdout);
     }
     return SGP_OK;
@@ -1026,9 +1057,11 @@ int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& in) {
 
 // Synchronises the stream and turns a recorded non-positive pivot into SGP_ERR_NOT_PD.
 int sgp_dense_info(sgp_ctx* ctx, const char* what) {
-    int info = 0;
-    SGP_CUDA(ctx, cudaMemcpyAsync(&info, ctx->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    int both[2] = {0, 0};
+    SGP_CUDA(ctx, cudaMemcpyAsync(both, ctx->info_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int info = both[0];
+    ctx->info2_last = both[1];             // (second job of a two-job launch)
     if (info != 0) {
         char buf[160];
         snprintf(buf, sizeof buf, "%s: Cholesky met a non-positive pivot at row %d of %d", what, info, ctx->M);

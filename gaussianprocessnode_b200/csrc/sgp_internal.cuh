@@ -67,6 +67,7 @@ struct sgp_ctx {
 
     // K_uu factor
     double* KuuL_dev = nullptr; int KuuL_M = 0; bool have_kuu = false; double kuu_jitter = 0.0;
+    bool kuu_jitter_known = false, kuu_speculative = false; int info2_last = 0;    // K_uu job sharing the posterior's launch (api.cu posterior_core)
     double* Kinv_dev = nullptr;                            // K_uu^-1 (full symmetric), refreshed by sgp_kuu_factor
     double* kuu_dinv_dev = nullptr; size_t kuu_dinv_cap = 0; // inverses of the 64 x 64 diagonal blocks of KuuL
     double* dinv_dev = nullptr; size_t dinv_cap = 0;       // ... of the factor produced by the last sgp_potrf_lower
@@ -135,7 +136,7 @@ struct SgpDenseJob {
     long long* clk = nullptr;  // optional: 8 phase clocks of CTA 0
     int reset_info = 1;        // zero ctx->info_dev before the launch
 };
-int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& job);                          // enqueues; no host synchronisation
+int sgp_dense_job(sgp_ctx* ctx, const SgpDenseJob& job, const SgpDenseJob* second = nullptr);   // enqueues (optionally a second independent job of the same M in the same launch; its pivot record: info_dev[1]); no host synchronisation
 // pinned host staging for the small read-backs (ctx->fetch_host), at least n doubles; nullptr on failure
 inline double* sgp_host_stage(sgp_ctx* ctx, size_t n) {
     if (ctx->fetch_cap < n) {

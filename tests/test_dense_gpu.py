@@ -215,3 +215,31 @@ def test_one_launch_posterior_agrees_with_the_two_factorisation_form(tmp_path, M
     errs = [fro(out["one"][k], out["two"][k]) for k in ("Sig", "mu", "Uv")]
     assert max(errs) < tol, (errs, tol)
     assert np.allclose(np.tril(out["one"]["Uv"], -1), 0.0)
+
+
+@pytest.mark.parametrize("M", [100, 512])
+def test_kuu_job_in_the_shadow_of_the_posterior(ctx, M):
+    # mini-batch schedule at a NEW theta: the stale K_uu is refactored inside the posterior's launch (two jobs, one cooperative kernel);
+    # the consumers of K_uu^-1 must see exactly what an explicit sgp_kuu_factor gives
+    rng = np.random.default_rng(3 * M)
+    N, D, w, jit = 2000, 4, 30.0, 1e-6
+    X = rng.normal(size=(N, D)); y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=N)
+    Z = X[rng.choice(N, M, replace=False)]
+    ctx.set_kernel(1.0, np.full(D, 1.2)); ctx.set_inducing(Z); ctx.set_data(X, y)
+    ctx.kuu_factor(jit, fetch=False)                        # puts the jitter on record
+    ell2 = np.full(D, 1.5)
+    # explicit path
+    ctx.set_kernel(0.8, ell2); ctx.sweep_psi(fetch=False); ctx.kuu_factor(jit, fetch=False); ctx.prior_set_isotropic(50.0)
+    mu_a, Sig_a, Uv_a = ctx.posterior_v_stream(w, carry=False, fetch=True)
+    w_a = ctx.w_terms(None, None); t_a = ctx.theta_objective(None, None, w, jit)
+    # fused path: K_uu is stale when the posterior runs
+    ctx.set_kernel(0.8, ell2); ctx.sweep_psi(fetch=False); ctx.prior_set_isotropic(50.0)
+    mu_b, Sig_b, Uv_b = ctx.posterior_v_stream(w, carry=False, fetch=True)
+    w_b = ctx.w_terms(None, None)                           # needs K_uu^-1: no explicit factorisation since set_kernel
+    t_b = ctx.theta_objective(None, None, w, jit)
+    assert np.array_equal(mu_a, mu_b) and np.array_equal(Sig_a, Sig_b) and np.array_equal(Uv_a, Uv_b)
+    assert w_a == w_b
+    assert t_a[0] == t_b[0] and t_a[1] == t_b[1] and np.array_equal(t_a[2], t_b[2])
+    Xs = ctx.kuu_solve(np.eye(M)[:, :3])
+    K = kernels.kuu(Z, 0.8, ell2, jitter=jit)
+    assert np.linalg.norm(K @ Xs - np.eye(M)[:, :3]) / (np.linalg.norm(K) * np.linalg.norm(Xs)) < 1e-13
