@@ -1,15 +1,19 @@
-// M x M factorisations of the path as ONE cooperative kernel per job (M = 20 ... 2048: latency-bound, so the design minimises the
+// M x M factorisations of the path as ONE cooperative kernel per job (M = 20 ... 4096: latency-bound, so the design minimises the
 // critical path, not the FLOP count):
 //
-//   dense_job_kernel   [build A] -> blocked right-looking Cholesky, with [X = L^-1 and S = X'X built row block by row block by the CTAs that
-//                      would otherwise wait for the diagonal-block factorisation] -> [mu = S xi] -> [transposed copy of L]
-//       build:  A = Lambda_prior + w Psi2 (the N-th `prod`), A = K_uu(Z) + jitter I, A = Sigma + mu mu', or A as given
+//   dense_job_kernel   [build A] -> blocked right-looking Cholesky, with X = L^-1 and S = X'X built by the CTAs that would otherwise wait for
+//                      the diagonal-block factorisation -> [mu, Uv | transposed copy of L].  One or TWO independent jobs per launch.
+//       build:  A = Lambda_prior + w Psi2 (the N-th `prod`; index-reversed, see below), A = K_uu(Z) + jitter I, A = Sigma + mu mu', or A as given
 //       Cholesky, per 64-wide panel:  panel L21 = A21 Dinv'  (16 x 64 row strips, one per CTA)  | grid barrier |
-//                      trailing update in 32 x 32 sub-tiles over all CTAs, while CTA 0 updates the next diagonal block straight into
-//                      shared memory and factorises it there | grid barrier
-//       diagonal block (64 x 64, one CTA, shared memory): two 32 x 32 Cholesky factorisations by ONE WARP with the block's rows in
-//                      registers (pivots and multipliers travel by shuffle: ~110 clocks per pivot, no block barrier inside), their
-//                      inverses by one warp (a lane per column), and four 32^3 DMMA products for the off-diagonal parts
+//                      CTA 0 forms the next diagonal block in shared memory (A - P P' from ONE shared-memory copy of the panel block P) and
+//                      factorises it there, while the other CTAs work through the step's list of 64 x 64 tile tasks: trailing update,
+//                      row block k of X, the running products P(i, j) for the rows below, row block k - 1 of X into S | grid barrier
+//       diagonal block (64 x 64, one CTA, shared memory): two 32 x 32 Cholesky factorisations by ONE WARP (rolled pivot loop, the row in
+//                      rotating registers, finished columns read back from a column-major shared-memory copy), the forward substitution of
+//                      the rows below and the inverse by two more warps one pivot behind, DMMA products for the off-diagonal parts
+//       N-th prod:     the job factorises J Lambda J (J = index reversal): the inverse of THAT factor is the Cholesky factor of Sigma up to
+//                      the reversal, so mu = U0' (U0 xi) and Uv = chol(Sigma + mu mu').U = G U0 with the closed-form factor G of I + p p'
+//                      (a running sum down the columns of X in the kernel's tail) -- no second factorisation
 //       every GEMM-shaped piece is a `gemm_task`: global -> registers -> shared-memory staging (software pipelined), DMMA.8x8x4
 //
 // Replaces LAPACK potrf / potri behind fastcholesky! / cholinv and the posterior update of the N-th `prod`
