@@ -110,7 +110,11 @@ int sgp_kuu_solve(sgp_ctx* ctx, int nrhs, double* B);
 /* The N-th `prod` (GPnode/UniSGPnode.jl:62-73) on the statistics of the last sweep:
  *   Lambda = Lambda0 + w Psi2, xi = xi0 + w Psi1, Sigma_v = cholinv(Lambda), mu_v = Sigma_v xi,
  *   Uv = fastcholesky!(Sigma_v + mu_v mu_v').U.   Lambda0 (M x M) / xi0 (M) are the prior's natural parameters.
- * Outputs may be NULL. */
+ * Outputs may be NULL.  ONE kernel launch (M <= 4096): Lambda is factorised in reversed index order, so that the inverse of the factor is the
+ * Cholesky factor of Sigma_v and Uv follows by a closed-form rank-one update; a non-positive pivot is reported as SGP_ERR_NOT_PD (the row
+ * number in the message counts from the END of the matrix).  When K_uu is stale (sgp_set_kernel / sgp_set_inducing since the last
+ * sgp_kuu_factor) and a jitter is on record, K_uu is refactored with that jitter in the same launch (as if sgp_kuu_factor had been
+ * called; a failure of that part is not this call's error -- the next sgp_kuu_factor reports it). */
 int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, double w, double* mu_v, double* Sigma_v,
                     double* Uv);
 /* Streaming prior (experiments/regression_kin40k.ipynb:200-213: the posterior of mini-batch b is the prior of mini-batch b+1,
@@ -120,8 +124,8 @@ int sgp_posterior_v(sgp_ctx* ctx, const double* xi0, const double* Lambda0, doub
  *   sgp_posterior_v_stream   the N-th prod on the resident prior and the last sweep; carry != 0: the posterior's natural
  *                            parameters become the resident prior.  Outputs may be NULL (nothing is copied back); mu_v / Sigma_v
  *                            of the last posterior stay resident for sgp_w_terms / sgp_theta_objective (pass NULL there).
- *                            Uv == NULL skips the second Cholesky factorisation (of Sigma_v + mu_v mu_v') altogether: the resident
- *                            consumers use <R_v, Psi2> = <Sigma_v, Psi2> + mu_v' Psi2 mu_v instead of the factor. */
+ *                            Uv == NULL: the factor of Sigma_v + mu_v mu_v' is not formed; the resident consumers use
+ *                            <R_v, Psi2> = <Sigma_v, Psi2> + mu_v' Psi2 mu_v instead. */
 int sgp_prior_set(sgp_ctx* ctx, const double* xi0, const double* Lambda0);
 int sgp_prior_set_isotropic(sgp_ctx* ctx, double variance);
 int sgp_posterior_v_stream(sgp_ctx* ctx, double w, int carry, double* mu_v, double* Sigma_v, double* Uv);
@@ -148,7 +152,8 @@ int sgp_predict_probit(sgp_ctx* ctx, int64_t Nt, const double* Xt, const double*
  * value = F, dvariance = dF/d sigma^2, dlengthscale[D] = dF/d ell_d (analytic; the host applies its own chain rule for the
  * raw parameters, e.g. softplus').  mu_v (M) and Uv (M x M upper, column-major) are inputs (both NULL = resident posterior).  Any output may be NULL; without
  * gradient outputs only the value is computed.  The statistics of the last sgp_sweep_psi on the same data and kernel are reused (otherwise the sweep
- * runs first); K_uu is refactored only when the kernel, Z or the jitter changed.  With a communicator attached the call is COLLECTIVE: the
+ * runs first); K_uu is refactored only when the kernel, Z or the jitter changed.  The whole step is enqueued without intermediate host
+ * synchronisation and ends in one read-back.  With a communicator attached the call is COLLECTIVE: the
  * statistics are the rank-summed ones and the rank-local part of the gradient is summed over the ranks. */
 int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const double* Uv, double w, double jitter, double* value,
                         double* dvariance, double* dlengthscale);
