@@ -64,6 +64,63 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {     // shared-memory 
     return v;
 }
 
+// Staging map of a TR x KC (KC x TC) operand chunk: element e = tid + q * 256 of the chunk -> (r, kk), 8 consecutive threads along the operand's
+// contiguous index (64-byte global runs), the next 4 along the other (<= 2-way bank conflicts in shared memory for either orientation).
+// With 256 threads and 2, 4 or 8 groups of 8 along the fast index the map is AFFINE in q -- (r, kk) = (r0 + q dr, kk0 + q dk) -- so a thread
+// keeps one base pointer per operand and a constant stride (no per-element 64-bit index arithmetic in the chunk loop), and full tiles take
+// a path without bounds predicates.
+template <class TL>
+struct StageMap {
+    static constexpr int TR = TL::WTR * (8 / TL::WC), TC = TL::WTC * TL::WC, KC = TL::KC;
+    static_assert(8 % (TR / 8) == 0 && 8 % (TC / 8) == 0 && 8 % (KC / 8) == 0, "affine staging map");
+    const double* pa; const double* pb;       // element q = 0 of chunk 0
+    long long sa, sb, ca, cb;                 // pointer strides per q and per chunk
+    int ar0, akk0, adr, adk, br0, bkk0, bdr, bdk;      // (r, kk) of q = 0 and the step per q (b: r means the column c)
+    int rows, cols, K;
+    bool full;
+    __device__ __forceinline__ static void dec(int e, bool fast_first, int n_first, int& first, int& kk) {
+        // fast_first: the tile index (r or c, n_first of them) is the contiguous one; else kk (KC of them) is
+        const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
+        if (fast_first) { first = lo + 8 * (rest % (n_first / 8)); kk = mid + 4 * (rest / (n_first / 8)); }
+        else { kk = lo + 8 * (rest % (KC / 8)); first = mid + 4 * (rest / (KC / 8)); }
+    }
+    __device__ __forceinline__ StageMap(const double* A, size_t a_rs, size_t a_ks, int rows_, const double* B, size_t b_ks, size_t b_cs, int cols_, int K_)
+        : rows(rows_), cols(cols_), K(K_) {
+        const int tid = threadIdx.x;
+        int r1, k1;
+        dec(tid, a_rs == 1, TR, ar0, akk0); dec(tid + CT, a_rs == 1, TR, r1, k1); adr = r1 - ar0; adk = k1 - akk0;
+        dec(tid, b_cs == 1, TC, br0, bkk0); dec(tid + CT, b_cs == 1, TC, r1, k1); bdr = r1 - br0; bdk = k1 - bkk0;
+        pa = A + (long long)ar0 * (long long)a_rs + (long long)akk0 * (long long)a_ks;
+        pb = B + (long long)bkk0 * (long long)b_ks + (long long)br0 * (long long)b_cs;
+        sa = (long long)adr * (long long)a_rs + (long long)adk * (long long)a_ks;
+        sb = (long long)bdk * (long long)b_ks + (long long)bdr * (long long)b_cs;
+        ca = (long long)KC * (long long)a_ks; cb = (long long)KC * (long long)b_ks;
+        full = rows == TR && cols == TC && K % KC == 0;
+    }
+    __device__ __forceinline__ void gload(double (&ra)[TL::AP], double (&rb)[TL::BP], int k0) const {
+        const double* a = pa + (long long)(k0 / KC) * ca; const double* b = pb + (long long)(k0 / KC) * cb;
+        if (full) {
+#pragma unroll
+            for (int q = 0; q < TL::AP; ++q) ra[q] = a[q * sa];
+#pragma unroll
+            for (int q = 0; q < TL::BP; ++q) rb[q] = b[q * sb];
+        } else {
+#pragma unroll
+            for (int q = 0; q < TL::AP; ++q) ra[q] = (ar0 + q * adr < rows && k0 + akk0 + q * adk < K) ? a[q * sa] : 0.0;
+#pragma unroll
+            for (int q = 0; q < TL::BP; ++q) rb[q] = (br0 + q * bdr < cols && k0 + bkk0 + q * bdk < K) ? b[q * sb] : 0.0;
+        }
+    }
+    __device__ __forceinline__ void sstore(const double (&ra)[TL::AP], const double (&rb)[TL::BP], double* __restrict__ As, double* __restrict__ Bs) const {
+        double* a = As + ar0 * TL::LDA + akk0; double* b = Bs + bkk0 * TL::LDB + br0;
+        const int ia = adr * TL::LDA + adk, ib = bdk * TL::LDB + bdr;
+#pragma unroll
+        for (int q = 0; q < TL::AP; ++q) a[q * ia] = ra[q];
+#pragma unroll
+        for (int q = 0; q < TL::BP; ++q) b[q * ib] = rb[q];
+    }
+};
+
 // A(r, k) = A[r * a_rs + k * a_ks] (r < rows), B(k, c) = B[k * b_ks + c * b_cs] (c < cols); out-of-range elements read as zero.
 // Staging map: a thread owns an (8 fast x 4 slow)-interleaved element so that both the global loads (64-byte runs along the fast
 // index) and the shared-memory stores (two-way bank conflicts at most, for either orientation) are efficient.
@@ -76,46 +133,9 @@ __device__ __forceinline__ void gemm_task(typename TL::Acc& acc, const double* _
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp / TL::WC, wc = warp % TL::WC;
     double ra[TL::AP], rb[TL::BP];
-    const bool a_rowfast = a_rs == 1, b_colfast = b_cs == 1;
-    // element e of the TR x KC (KC x TC) chunk -> (r, kk): 8 consecutive threads run along the operand's contiguous index, the next 4 along the other
-    auto dec_a = [&](int e, int& r, int& kk) {
-        const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
-        if (a_rowfast) { r = lo + 8 * (rest % (TR / 8)); kk = mid + 4 * (rest / (TR / 8)); }
-        else { kk = lo + 8 * (rest % (KC / 8)); r = mid + 4 * (rest / (KC / 8)); }
-    };
-    auto dec_b = [&](int e, int& c, int& kk) {
-        const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
-        if (b_colfast) { c = lo + 8 * (rest % (TC / 8)); kk = mid + 4 * (rest / (TC / 8)); }
-        else { kk = lo + 8 * (rest % (KC / 8)); c = mid + 4 * (rest / (KC / 8)); }
-    };
-    auto gload = [&](int k0) {
-#pragma unroll
-        for (int q = 0; q < TL::AP; ++q) {
-            const int e = tid + q * CT;
-            int r, kk; dec_a(e, r, kk);
-            ra[q] = (r < rows && k0 + kk < K) ? A[(size_t)r * a_rs + (size_t)(k0 + kk) * a_ks] : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < TL::BP; ++q) {
-            const int e = tid + q * CT;
-            int c, kk; dec_b(e, c, kk);
-            rb[q] = (c < cols && k0 + kk < K) ? B[(size_t)(k0 + kk) * b_ks + (size_t)c * b_cs] : 0.0;
-        }
-    };
-    auto sstore = [&]() {
-#pragma unroll
-        for (int q = 0; q < TL::AP; ++q) {
-            const int e = tid + q * CT;
-            int r, kk; dec_a(e, r, kk);
-            As[r * TL::LDA + kk] = ra[q];
-        }
-#pragma unroll
-        for (int q = 0; q < TL::BP; ++q) {
-            const int e = tid + q * CT;
-            int c, kk; dec_b(e, c, kk);
-            Bs[kk * TL::LDB + c] = rb[q];
-        }
-    };
+    StageMap<TL> sm_(A, a_rs, a_ks, rows, B, b_ks, b_cs, cols, K);
+    auto gload = [&](int k0) { sm_.gload(ra, rb, k0); };
+    auto sstore = [&]() { sm_.sstore(ra, rb, As, Bs); };
     typename TL::Acc part[4];                              // (small warp tiles only)
     if constexpr (TL::MI * TL::NJ <= 2) {
 #pragma unroll
@@ -199,35 +219,9 @@ __device__ __forceinline__ void gemm_task_db(typename TL::Acc& acc, const double
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp / TL::WC, wc = warp % TL::WC;
     double ra[TL::AP], rb[TL::BP];
-    const bool a_rowfast = a_rs == 1, b_colfast = b_cs == 1;
-    auto dec_a = [&](int e, int& r, int& kk) {
-        const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
-        if (a_rowfast) { r = lo + 8 * (rest % (TR / 8)); kk = mid + 4 * (rest / (TR / 8)); }
-        else { kk = lo + 8 * (rest % (KC / 8)); r = mid + 4 * (rest / (KC / 8)); }
-    };
-    auto dec_b = [&](int e, int& c, int& kk) {
-        const int lo = e & 7, mid = (e >> 3) & 3, rest = e >> 5;
-        if (b_colfast) { c = lo + 8 * (rest % (TC / 8)); kk = mid + 4 * (rest / (TC / 8)); }
-        else { kk = lo + 8 * (rest % (KC / 8)); c = mid + 4 * (rest / (KC / 8)); }
-    };
-    auto gload = [&](int k0) {
-#pragma unroll
-        for (int q = 0; q < TL::AP; ++q) {
-            int r, kk; dec_a(tid + q * CT, r, kk);
-            ra[q] = (r < rows && k0 + kk < K) ? A[(size_t)r * a_rs + (size_t)(k0 + kk) * a_ks] : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < TL::BP; ++q) {
-            int c, kk; dec_b(tid + q * CT, c, kk);
-            rb[q] = (c < cols && k0 + kk < K) ? B[(size_t)(k0 + kk) * b_ks + (size_t)c * b_cs] : 0.0;
-        }
-    };
-    auto sstore = [&](double* __restrict__ As, double* __restrict__ Bs) {
-#pragma unroll
-        for (int q = 0; q < TL::AP; ++q) { int r, kk; dec_a(tid + q * CT, r, kk); As[r * TL::LDA + kk] = ra[q]; }
-#pragma unroll
-        for (int q = 0; q < TL::BP; ++q) { int c, kk; dec_b(tid + q * CT, c, kk); Bs[kk * TL::LDB + c] = rb[q]; }
-    };
+    StageMap<TL> sm_(A, a_rs, a_ks, rows, B, b_ks, b_cs, cols, K);
+    auto gload = [&](int k0) { sm_.gload(ra, rb, k0); };
+    auto sstore = [&](double* __restrict__ As, double* __restrict__ Bs) { sm_.sstore(ra, rb, As, Bs); };
     gload(0);
     sstore(buf, buf + SA);
     __syncthreads();
