@@ -31,29 +31,34 @@ __global__ void dot_finish_kernel(const double* __restrict__ partial, int nb, do
     if (threadIdx.x == 0) { double v = 0.0; for (int i = 0; i < nb; ++i) v += partial[i]; out[0] = v; }
 }
 
-// One pass over the M x M matrices for every scalar the :w rule / energy / theta objective need.  Block b covers columns
-// [b, b+1) * M / nblocks; partial[b][4]; the LAST block to finish (ticket counter) adds the partials in block order: deterministic.
-constexpr int WT_BLOCKS = 64;
+// One pass over the M x M matrices for every scalar the :w rule / energy / theta objective need.  Block b covers a contiguous range of
+// (column, row part) tasks; partial[b][4]; the LAST block to finish (ticket counter) adds the partials in a fixed order: deterministic.
+constexpr int WT_BLOCKS = 256;
 __global__ void __launch_bounds__(256) wterms_kernel(const double* __restrict__ Kinv, const double* __restrict__ Psi2, const double* __restrict__ R,
                                                      const double* __restrict__ mu_outer, const double* __restrict__ mu, const double* __restrict__ psi1,
-                                                     int M, double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ out) {
+                                                     int M, int nparts, double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ out) {
     __shared__ double s[4][8];
     __shared__ bool last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c_lo = (int)((long long)M * blockIdx.x / gridDim.x), c_hi = (int)((long long)M * (blockIdx.x + 1) / gridDim.x);
+    // tasks = (column, row part): nparts row parts per column so that a small M still fills the machine with warps; a block takes a contiguous
+    // range of tasks, a warp every eighth of them
+    const int ntask = M * nparts;
+    const int t_lo = (int)((long long)ntask * blockIdx.x / gridDim.x), t_hi = (int)((long long)ntask * (blockIdx.x + 1) / gridDim.x);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    for (int c = c_lo + warp; c < c_hi; c += 8) {
+    for (int t = t_lo + warp; t < t_hi; t += 8) {
+        const int c = t / nparts, part = t - c * nparts;
+        const int r_lo = (int)((long long)M * part / nparts), r_hi = (int)((long long)M * (part + 1) / nparts);
         const size_t off = (size_t)c * M;
         const double mc = mu_outer ? mu_outer[c] : 0.0;
 #pragma unroll 4                                                 // (the loads of four iterations in flight)
-        for (int r = lane; r < M; r += 32) {
+        for (int r = r_lo + lane; r < r_hi; r += 32) {
             const double p2 = Psi2[off + r];
             if (Kinv) a0 = fma(Kinv[off + r], p2, a0);
             double rv = R ? R[off + r] : 0.0;
             if (mu_outer) rv = fma(mu_outer[r], mc, rv);
             a1 = fma(rv, p2, a1);
         }
-        if (lane == 0) {
+        if (lane == 0 && part == 0) {
             if (mu && psi1) a2 = fma(mu[c], psi1[c], a2);
             if (Kinv) a3 += Kinv[off + c];
         }
@@ -105,8 +110,9 @@ int sgp_wterms_reduce(sgp_ctx* ctx, const double* Kinv, const double* Psi2, cons
         SGP_CUDA(ctx, cudaMalloc((void**)&ctx->wt_dev, (4 * WT_BLOCKS + 8) * sizeof(double)));
         SGP_CUDA(ctx, cudaMemsetAsync(ctx->wt_dev, 0, (4 * WT_BLOCKS + 8) * sizeof(double), ctx->stream));
     }
-    const int nblk = std::max(1, std::min(WT_BLOCKS, M / 8));
-    wterms_kernel<<<nblk, 256, 0, ctx->stream>>>(Kinv, Psi2, R, mu_outer, mu, psi1, M, ctx->wt_dev, reinterpret_cast<unsigned*>(ctx->wt_dev + 4 * WT_BLOCKS), out);
+    const int nparts = std::max(1, std::min(8, 2048 / std::max(1, M)));
+    const int nblk = std::max(1, std::min(WT_BLOCKS, M * nparts / 8));
+    wterms_kernel<<<nblk, 256, 0, ctx->stream>>>(Kinv, Psi2, R, mu_outer, mu, psi1, M, nparts, ctx->wt_dev, reinterpret_cast<unsigned*>(ctx->wt_dev + 4 * WT_BLOCKS), out);
     SGP_CUDA(ctx, cudaGetLastError());
     return SGP_OK;
 }

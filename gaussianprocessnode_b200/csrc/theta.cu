@@ -31,10 +31,12 @@ struct KParams {
     double ell_inv[SGP_MAX_D];
 };
 
+// DP = D rounded up to 4 / 8 / 16: the unrolled loops cover DP dimensions only
+template <int DP = SGP_MAX_D>
 __device__ __forceinline__ double r2_of(const double* __restrict__ x, const double* __restrict__ z, const KParams& kp, double* c) {
     double r2 = 0.0;
 #pragma unroll                                                    // (static indices: c stays in registers)
-    for (int d = 0; d < SGP_MAX_D; ++d) {
+    for (int d = 0; d < DP; ++d) {
         const double t = d < kp.D ? x[d] - z[d] : 0.0;
         c[d] = t * t;                                             // (x_d - z_d)^2, unscaled
         r2 = fma(c[d], kp.ell_inv[d] * kp.ell_inv[d], r2);
@@ -107,6 +109,7 @@ __device__ __forceinline__ void reduce_and_finish(const double (&acc)[kPS], doub
 }
 
 // total[d] += sum over the chunk's (m, j) of h_mj c_mjd (w G_mj - w y_j v_m)
+template <int DP>
 __global__ void __launch_bounds__(256) grad_contract_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ Z,
                                                             const double* __restrict__ G, const double* __restrict__ v, double w, long long n0,
                                                             int nc, KParams kp, double* __restrict__ partial, unsigned* __restrict__ ticket,
@@ -117,17 +120,17 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const double* __rest
     const size_t total = (size_t)kp.M * nc;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(e % kp.M); const long long j = (long long)(e / kp.M);
-        double c[SGP_MAX_D];
-        const double r2 = r2_of(X + (n0 + j) * kp.D, Z + (size_t)m * kp.D, kp, c);
+        double c[DP];
+        const double r2 = r2_of<DP>(X + (n0 + j) * kp.D, Z + (size_t)m * kp.D, kp, c);
         const double f = h_of(kp, r2) * (w * G[e] - w * y[n0 + j] * v[m]);
 #pragma unroll
-        for (int d = 0; d < SGP_MAX_D; ++d)
-            if (d < kp.D) acc[d] = fma(f, c[d], acc[d]);
+        for (int d = 0; d < DP; ++d) acc[d] = fma(f, c[d], acc[d]);       // (c[d] = 0 beyond D)
     }
     reduce_and_finish(acc, partial, ticket, 1.0, total_out, nullptr);
 }
 
 // total[d] += scale * sum over (m, m') of B_mm' h_mm' c_mm'd   (K_uu part of the gradient);  *trace_out += tr B
+template <int DP>
 __global__ void __launch_bounds__(256) kuu_contract_kernel(const double* __restrict__ Z, const double* __restrict__ B, KParams kp, double* __restrict__ partial,
                                                            unsigned* __restrict__ ticket, double scale, double* __restrict__ total_out,
                                                            double* __restrict__ trace_out) {
@@ -137,14 +140,13 @@ __global__ void __launch_bounds__(256) kuu_contract_kernel(const double* __restr
     const size_t total = (size_t)kp.M * kp.M;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(e % kp.M), m2 = (int)(e / kp.M);
-        double c[SGP_MAX_D];
-        const double r2 = r2_of(Z + (size_t)m * kp.D, Z + (size_t)m2 * kp.D, kp, c);
+        double c[DP];
+        const double r2 = r2_of<DP>(Z + (size_t)m * kp.D, Z + (size_t)m2 * kp.D, kp, c);
         const double b = B[e];
         if (m == m2) acc[SGP_MAX_D] += b;
         const double f = h_of(kp, r2) * b;
 #pragma unroll
-        for (int d = 0; d < SGP_MAX_D; ++d)
-            if (d < kp.D) acc[d] = fma(f, c[d], acc[d]);
+        for (int d = 0; d < DP; ++d) acc[d] = fma(f, c[d], acc[d]);
     }
     reduce_and_finish(acc, partial, ticket, scale, total_out, trace_out);
 }
@@ -247,14 +249,18 @@ extern "C" int sgp_theta_objective(sgp_ctx* ctx, const double* mu_v, const doubl
         //  and the contraction below relies on the two halves averaging out, as the reference's does)
         rc = sgp_gemm(ctx, 0, 0, M, M, M, 1.0, T, M, Kinv, M, 0.0, B, M, 0); if (rc) return rc;
         mark("B = Kinv Psi2 Kinv");
-        kuu_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->Z_dev, B, kp, partial, ticket, 0.5 * w, total, res + 4);
+        if (D <= 4) kuu_contract_kernel<4><<<cblocks, 256, 0, ctx->stream>>>(ctx->Z_dev, B, kp, partial, ticket, 0.5 * w, total, res + 4);
+        else if (D <= 8) kuu_contract_kernel<8><<<cblocks, 256, 0, ctx->stream>>>(ctx->Z_dev, B, kp, partial, ticket, 0.5 * w, total, res + 4);
+        else kuu_contract_kernel<16><<<cblocks, 256, 0, ctx->stream>>>(ctx->Z_dev, B, kp, partial, ticket, 0.5 * w, total, res + 4);
         mark("K_uu contraction");
         // data part (this rank's points), chunk by chunk: K chunk -> G = A K -> contraction
         for (int64_t n0 = 0; n0 < N; n0 += nc_max) {
             const int nc = (int)std::min<int64_t>(nc_max, N - n0);
             kuf_chunk_kernel<<<nb((size_t)M * nc), 256, 0, ctx->stream>>>(ctx->X_dev, ctx->Z_dev, Kc, n0, nc, kp);
             rc = sgp_gemm(ctx, 0, 0, M, nc, M, 1.0, A, M, Kc, M, 0.0, Gc, M, 0); if (rc) return rc;
-            grad_contract_kernel<<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, v, w, n0, nc, kp, partial, ticket, total_data);
+            if (D <= 4) grad_contract_kernel<4><<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, v, w, n0, nc, kp, partial, ticket, total_data);
+            else if (D <= 8) grad_contract_kernel<8><<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, v, w, n0, nc, kp, partial, ticket, total_data);
+            else grad_contract_kernel<16><<<cblocks, 256, 0, ctx->stream>>>(ctx->X_dev, ctx->y_dev, ctx->Z_dev, Gc, v, w, n0, nc, kp, partial, ticket, total_data);
         }
         mark("data part (K chunk, G = A K, contraction)");
         if (ctx->comm) { rc = sgp_comm_allreduce(ctx, total_data, (size_t)SGP_MAX_D); if (rc) return rc; }     // the only rank-local part
