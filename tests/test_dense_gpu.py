@@ -51,7 +51,7 @@ def test_not_positive_definite_is_an_error(ctx):
 
 
 @pytest.mark.parametrize("N,D,M,w", [(50, 1, 20, 25.0), (300, 2, 33, 10.0), (2000, 2, 64, 3.0), (3000, 3, 100, 30.0), (5000, 8, 256, 100.0),
-                                     (10000, 8, 512, 1.0e4), (6000, 8, 600, 1.0e3), (4000, 8, 1000, 50.0)])
+                                     (10000, 8, 512, 1.0e4), (6000, 8, 600, 1.0e3), (4000, 8, 1000, 50.0), (3000, 6, 2100, 20.0)])
 def test_posterior_and_w_terms(ctx, N, D, M, w):
     rng = np.random.default_rng(N + M)
     X = rng.normal(size=(N, D)); y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=N)
