@@ -18,6 +18,10 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(_lib.c_double_p)
 
 
+def _is_plain(a):
+    return a is None or (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous)
+
+
 def _f64(a, shape=None):
     if a is None:
         return None
@@ -66,6 +70,7 @@ class SGPContext:
         self.M = 0
         self.D = 0
         self.N = 0
+        self._host_call = None      # cached argument marshalling of sweep_psi_host (same arrays every step)
 
     def close(self):
         if getattr(self, "h", None):
@@ -130,13 +135,24 @@ class SGPContext:
 
     def sweep_psi_host(self, X, ybar=None, yvar=None, wts=None, out=None):
         """set_data + sweep_psi in one call (one host synchronisation); `out` = (psi1, psi2) preallocated arrays."""
-        X = _f64(X).reshape(-1, self.D)
-        N = X.shape[0]; M = self.M
-        ybar, yvar, wts = _f64(ybar, (N,)), _f64(yvar, (N,)), _f64(wts, (N,))
-        psi1, psi2 = out if out is not None else (np.empty(M), np.empty((M, M), order="F"))
-        psi0, sy2 = ctypes.c_double(), ctypes.c_double()
-        self._ck(self.lib.sgp_sweep_psi_host(self.h, N, _p(X), _p(ybar), _p(yvar), _p(wts), ctypes.byref(psi0), _p(psi1), _p(psi2),
-                                             ctypes.byref(sy2)))
+        # Steady-state callers pass the SAME (pinned) arrays every step: the argument marshalling (~20 us of ctypes / numpy work, a tenth of the
+        # call at the kin40k shape) is cached on the identity of the array objects -- their buffers cannot move while we hold references.
+        c = self._host_call
+        if (c is not None and out is not None and c[0] is X and c[1] is ybar and c[2] is yvar and c[3] is wts and c[4] is out[0] and c[5] is out[1]
+                and c[6] == X.shape and c[7] == (self.M, self.D)):
+            N, args, psi0, sy2 = c[8], c[9], c[10], c[11]
+            psi1, psi2 = out
+        else:
+            Xc = _f64(X).reshape(-1, self.D)
+            N = Xc.shape[0]; M = self.M
+            yb, yv, w = _f64(ybar, (N,)), _f64(yvar, (N,)), _f64(wts, (N,))
+            psi1, psi2 = out if out is not None else (np.empty(M), np.empty((M, M), order="F"))
+            assert psi1.size == M and psi2.shape == (M, M) and psi2.flags.f_contiguous and psi1.dtype == psi2.dtype == np.float64
+            psi0, sy2 = ctypes.c_double(), ctypes.c_double()
+            args = (self.h, N, _p(Xc), _p(yb), _p(yv), _p(w), ctypes.byref(psi0), _p(psi1), _p(psi2), ctypes.byref(sy2))
+            cacheable = out is not None and all(_is_plain(a) for a in (X, ybar, yvar, wts))      # (no converted temporaries behind the pointers)
+            self._host_call = (X, ybar, yvar, wts, out[0], out[1], X.shape, (M, self.D), N, args, psi0, sy2) if cacheable else None
+        self._ck(self.lib.sgp_sweep_psi_host(*args))
         self.N = N
         return psi0.value, psi1, psi2, sy2.value
 

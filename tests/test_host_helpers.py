@@ -36,3 +36,33 @@ def test_create_blockmatrix_views():
     A = np.arange(36.0).reshape(6, 6)
     blk = nd.create_blockmatrix(A, 2, 3)
     assert np.array_equal(blk[1][0], A[3:6, 0:3]) and np.shares_memory(blk[0][1], A)
+
+
+def test_sweep_psi_host_caches_its_marshalling_only_for_the_same_plain_arrays():
+    # host logic of the Python mirror (no GPU): the argument tuple of sgp_sweep_psi_host is reused while the caller passes the same
+    # C-contiguous float64 arrays, and rebuilt for new arrays, new shapes, converted inputs or a new M / D
+    import ctypes
+    from gaussianprocessnode_b200 import sgp
+
+    calls = []
+
+    class Lib:
+        def sgp_sweep_psi_host(self, *a):
+            calls.append(a)
+            return 0
+
+    c = sgp.SGPContext.__new__(sgp.SGPContext)
+    c.lib = Lib(); c.h = ctypes.c_void_p(1); c.M = 4; c.D = 2; c.N = 0; c._host_call = None
+    X = np.zeros((6, 2)); y = np.zeros(6); out = (np.zeros(4), np.zeros((4, 4), order="F"))
+    c.sweep_psi_host(X, y, out=out); c.sweep_psi_host(X, y, out=out)
+    assert calls[0][2] is calls[1][2] and calls[0][7] is calls[1][7] and calls[0][1] == 6      # the same pointer objects: cached
+    X2 = np.ones((6, 2))
+    c.sweep_psi_host(X2, y, out=out)
+    assert calls[2][2] is not calls[1][2] and c._host_call[0] is X2
+    c.sweep_psi_host(X2[:4], y[:4], out=out)                          # views are new objects: rebuilt, N follows
+    assert calls[3][1] == 4
+    c.sweep_psi_host(np.zeros((6, 2), dtype=np.float32), y, out=out)  # converted temporary: never cached
+    assert c._host_call is None
+    c.sweep_psi_host(X, y, out=out); c.M = 5
+    with __import__("pytest").raises(AssertionError):
+        c.sweep_psi_host(X, y, out=out)                               # M changed: the cached outputs no longer fit -> rebuilt and checked
