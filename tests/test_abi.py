@@ -65,3 +65,24 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def build_c_client(tmp_path):
+    """examples/c_client.c with gcc as plain C11 against include/sgp.h and libsgp.so; returns the binary's path."""
+    import subprocess
+    pkg = os.path.join(ROOT, "gaussianprocessnode_b200")
+    exe = str(tmp_path / "c_client")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_client.c"), "-o", exe,
+                    "-L" + pkg, "-lsgp", "-lm", "-Wl,-rpath," + pkg, "-Wl,--unresolved-symbols=ignore-in-shared-libs"], check=True, timeout=120)
+    return exe
+
+
+def test_plain_c_client_compiles_links_and_fails_loudly_without_a_gpu(lib, tmp_path):
+    # the header is valid C (not only C++), the entry points link from C, and without a device the first call fails with SGP_ERR_CUDA
+    import subprocess
+    import torch
+    exe = build_c_client(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the GPU test runs the client")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "sgp_create" in r.stderr and "-> -2" in r.stderr

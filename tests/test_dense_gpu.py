@@ -243,3 +243,39 @@ def test_kuu_job_in_the_shadow_of_the_posterior(ctx, M):
     Xs = ctx.kuu_solve(np.eye(M)[:, :3])
     K = kernels.kuu(Z, 0.8, ell2, jitter=jit)
     assert np.linalg.norm(K @ Xs - np.eye(M)[:, :3]) / (np.linalg.norm(K) * np.linalg.norm(Xs)) < 1e-13
+
+
+def test_plain_c_client_against_the_oracle(tmp_path):
+    # examples/c_client.c: sweep + N-th prod + :w terms through the C ABI from plain C (no Python, no torch in the process)
+    import subprocess
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("_abi_helpers", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_abi.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    build_c_client = mod.build_c_client
+    N, M, D = 300, 40, 3
+    r = subprocess.run([build_c_client(tmp_path), str(N), str(M), str(D)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = {ln.split()[0]: np.array([float(v) for v in ln.split()[1:]]) for ln in r.stdout.splitlines()[2:]}
+
+    state = [12345]
+
+    def lcg():
+        state[0] = (state[0] * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+        return ((state[0] >> 11) & ((1 << 53) - 1)) / float(1 << 52) - 1.0
+    X = np.array([2.0 * lcg() for _ in range(N * D)]).reshape(N, D)
+    y = np.array([np.sin(X[n, 0]) + 0.05 * lcg() for n in range(N)])
+    Z = np.array([2.0 * lcg() for _ in range(M * D)]).reshape(M, D)
+    ell = 1.0 + 0.1 * np.arange(D); var = 1.3; w = 25.0; jit = 1e-6
+    psi0, psi1, psi2, sy2 = batched.psi_stats_point(X, y, Z, var, ell)
+    assert abs(out["psi0"][0] - psi0) <= 1e-13 * abs(psi0) and abs(out["sum_y2"][0] - sy2) <= 1e-13 * abs(sy2)
+    assert fro(out["psi1"], psi1) < 1e-13 and fro(out["psi2_diag"], np.diag(psi2)) < 1e-13
+    o_mu, o_Sig, o_Uv, o_Lam, _ = batched.posterior_v(np.zeros(M), np.eye(M) / 50.0, w, psi1, psi2)
+    cond = np.linalg.cond(o_Lam)
+    assert fro(out["mu"], o_mu) < max(1e-10, 50 * cond * 2.2e-16)
+    assert fro(out["Uv_diag"], np.diag(o_Uv)) < max(1e-10, 50 * np.linalg.cond(o_Sig + np.outer(o_mu, o_mu)) * 2.2e-16)
+    Lo = np.linalg.cholesky(kernels.kuu(Z, var, ell, jitter=jit))
+    o1, o2 = batched.w_terms(psi0, psi1, psi2, sy2, Lo, o_mu, o_Uv)
+    scale = abs(psi0) + abs(sy2)
+    condK = np.linalg.cond(kernels.kuu(Z, var, ell, jitter=jit))
+    assert abs(out["sumI1"][0] - o1) < max(1e-10 * scale, 50 * condK * 2.2e-16 * abs(psi0 - o1))
+    assert abs(out["sumI2"][0] - o2) < 1e-9 * max(abs(o2), scale)
