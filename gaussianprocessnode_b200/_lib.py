@@ -28,6 +28,9 @@ SIGNATURES = {
     "sgp_sweep_psi": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sgp_sweep_psi_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                           c_double_p, c_double_p]),
+    "sgp_sweep_psi_host_packed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                                 c_double_p, c_double_p, c_double_p]),
+    "sgp_fetch_psi2_packed": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "sgp_sweep_psi_uncertain": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_double_p, c_double_p,
                                                ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sgp_kuu_factor": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_double_p]),

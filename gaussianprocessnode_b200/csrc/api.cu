@@ -123,6 +123,9 @@ void sgp_destroy(sgp_ctx* ctx) {
     cudaFree(ctx->kbuf_dev); cudaFree(ctx->sweep_flags_dev); cudaFree(ctx->flush_dev); cudaFree(ctx->in_dev); cudaFree(ctx->wt_dev); cudaFree(ctx->pred_dev);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->ready_dev) cudaFree(ctx->ready_dev);
+    if (ctx->ready_host) cudaFreeHost(ctx->ready_host);
+    if (ctx->packed_dev) cudaFree(ctx->packed_dev);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -178,7 +181,7 @@ static int alloc_data(sgp_ctx* ctx, int64_t N) {
     return SGP_OK;
 }
 
-static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts);
+static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts, bool beside = false);
 
 int sgp_set_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts) {
     int rc = upload_data(ctx, N, X, ybar, yvar, wts); if (rc) return rc;
@@ -186,8 +189,11 @@ int sgp_set_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, c
     return SGP_OK;
 }
 
-// H2D copies enqueued on the ctx stream, no host synchronisation
-static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts) {
+// H2D copies enqueued on the ctx stream, no host synchronisation.
+// beside: the copies go to the copy stream (ordered after everything already on the main stream) and end with the ready word; the main stream
+// is NOT ordered after them -- the generate-once sweep launched next waits for the ready word on the device (its launch latency and set-up run
+// under the copies), every other consumer calls sgp_join_upload first.
+static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts, bool beside) {
     if (check(ctx)) return SGP_ERR_ARG;
     SGP_RANGE("sgp_upload");
     if (!ctx->have_kernel) SGP_FAIL(ctx, SGP_ERR_ARG, "set_data: set_kernel first (D is taken from it)");
@@ -200,11 +206,29 @@ static int upload_data(sgp_ctx* ctx, int64_t N, const double* X, const double* y
     // the sweep stages whole chunks of 32 points: rows [N, cap) hold zeros from the allocation or finite values of an earlier, longer data
     // set -- either way they generate exact zeros (no per-upload memset)
     const size_t n = (size_t)N;
-    if (n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->X_dev, X, n * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (ybar && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->y_dev, ybar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    else SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, cap * sizeof(double), ctx->stream));
-    if (yvar && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->yv_dev, yvar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (wts && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->w_dev, wts, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    cudaStream_t st = ctx->stream;
+    if (beside && n) {
+        if (!ctx->ready_dev) {
+            SGP_CUDA(ctx, cudaMalloc((void**)&ctx->ready_dev, 64));
+            SGP_CUDA(ctx, cudaMemsetAsync(ctx->ready_dev, 0, 64, ctx->stream));
+            SGP_CUDA(ctx, cudaHostAlloc((void**)&ctx->ready_host, 8 * sizeof(unsigned), cudaHostAllocDefault));
+        }
+        SGP_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));           // the previous sweep may still be reading the buffers
+        SGP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_copy, 0));
+        st = ctx->stream2;
+    }
+    if (n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->X_dev, X, n * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (ybar && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->y_dev, ybar, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    else SGP_CUDA(ctx, cudaMemsetAsync(ctx->y_dev, 0, cap * sizeof(double), st));
+    if (yvar && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->yv_dev, yvar, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (wts && n) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->w_dev, wts, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (st != ctx->stream) {
+        // the ready word follows the data in stream order (one copy engine executes a stream's copies one after the other)
+        const unsigned e = ++ctx->ready_epoch;
+        ctx->ready_host[e & 7u] = e;
+        SGP_CUDA(ctx, cudaMemcpyAsync(ctx->ready_dev, ctx->ready_host + (e & 7u), sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        ctx->upload_pending = true;
+    }
     ctx->N = N; ctx->have_yv = yvar != nullptr; ctx->have_w = wts != nullptr; ctx->have_stats = false; ctx->have_data = true;
     return SGP_OK;
 }
@@ -236,11 +260,28 @@ int sgp_set_data_dev(sgp_ctx* ctx, int64_t N, const double* X_dev, const double*
     return SGP_OK;
 }
 
-static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2) {
+// packed[tri_col(j) + i - j] = A[i + j M], i >= j: the lower triangle column by column (LAPACK 'L' packed storage)
+__global__ void pack_lower_kernel(const double* __restrict__ A, double* __restrict__ packed, int M) {
+    const int j = blockIdx.x;
+    const long long off = (long long)j * M - (long long)j * (j - 1) / 2 - j;
+    for (int i = j + threadIdx.x; i < M; i += blockDim.x) packed[off + i] = A[(size_t)i + (size_t)j * M];
+}
+
+static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2, bool packed = false) {
     SGP_RANGE("sgp_fetch");
     const size_t M = (size_t)ctx->M, Do = (size_t)ctx->Dout;
     double* s2 = ctx->stats_dev; double* s1 = s2 + M * M; double* sc = s1 + M * Do;
-    if (psi2) SGP_CUDA(ctx, cudaMemcpyAsync(psi2, s2, M * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (psi2 && packed) {
+        const size_t tri = M * (M + 1) / 2;
+        const double* src = ctx->packed_src;
+        if (!src) {      // the sweep did not leave a packed copy (first fused kernel, NCCL path): pack the resident square
+            int rc = sgp_ensure(ctx, &ctx->packed_dev, &ctx->packed_cap, tri + 2); if (rc) return rc;
+            pack_lower_kernel<<<(unsigned)M, 128, 0, ctx->stream>>>(s2, ctx->packed_dev, (int)M);
+            SGP_CUDA(ctx, cudaGetLastError());
+            src = ctx->packed_dev;
+        }
+        SGP_CUDA(ctx, cudaMemcpyAsync(psi2, src, tri * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (psi2) SGP_CUDA(ctx, cudaMemcpyAsync(psi2, s2, M * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     // Psi1 and the scalars are adjacent on the device: ONE copy into a pinned staging buffer, split on the host
     const size_t small = M * Do + 4;
     if (ctx->fetch_cap < small) {
@@ -260,11 +301,21 @@ static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, d
 }
 
 }  // extern "C"
+// orders the main stream after an upload that sgp_sweep_psi_host put on the copy stream (no-op otherwise)
+int sgp_join_upload(sgp_ctx* ctx) {
+    if (!ctx->upload_pending) return SGP_OK;
+    ctx->upload_pending = false;
+    SGP_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream2));
+    SGP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    return SGP_OK;
+}
 int sgp_sweep_resident(sgp_ctx* ctx, bool time_main) {
     if (!ctx->have_data) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: no data (sgp_set_data)");
     SGP_RANGE("sgp_sweep");
     ctx->stats_of_data = false;
+    ctx->packed_src = nullptr;
     if (ctx->N == 0) {
+        { int rcj = sgp_join_upload(ctx); if (rcj) return rcj; }
         // an empty data set (e.g. a rank whose shard is empty): all statistics are zero; under sharding the rank still takes part in the sum
         if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: set_kernel and set_inducing first");
         const size_t cnt = (size_t)ctx->M * ctx->M + (size_t)ctx->M + 4;
@@ -283,6 +334,7 @@ int sgp_sweep_resident(sgp_ctx* ctx, bool time_main) {
     if (ctx->comm && !ctx->last_sweep_exchanged) {       // (the generate-once kernel exchanges over peer memory inside its own launch)
         rc = sgp_comm_allreduce_stats(ctx, ctx->M, ctx->Dout); if (rc) return rc;
         ctx->last_launches += 1;
+        ctx->packed_src = nullptr;   // (a packed copy written before the sum is stale)
     }
     ctx->stats_of_data = true;       // the resident statistics are those of the resident data (summed over the ranks)
     return SGP_OK;
@@ -296,11 +348,35 @@ int sgp_sweep_psi(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double
     return fetch_stats(ctx, psi0, psi1, psi2, sum_y2);
 }
 
+static int sweep_host(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts, double* psi0,
+                      double* psi1, double* psi2, double* sum_y2, bool packed) {
+    const char* ov = std::getenv("SGP_HOST_OVERLAP");
+    const bool beside = !(ov && ov[0] == '0');
+    int rc = upload_data(ctx, N, X, ybar, yvar, wts, beside); if (rc) return rc;
+    ctx->want_packed = packed && psi2 != nullptr;
+    rc = sgp_sweep_resident(ctx, false);
+    ctx->want_packed = false;
+    const int rcj = sgp_join_upload(ctx);      // (an error path that never launched a consumer of the ready word)
+    if (rc) return rc;
+    if (rcj) return rcj;
+    return fetch_stats(ctx, psi0, psi1, psi2, sum_y2, packed);       // the one host synchronisation of the step
+}
+
 int sgp_sweep_psi_host(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts, double* psi0,
                        double* psi1, double* psi2, double* sum_y2) {
-    int rc = upload_data(ctx, N, X, ybar, yvar, wts); if (rc) return rc;
-    rc = sgp_sweep_resident(ctx, false); if (rc) return rc;
-    return fetch_stats(ctx, psi0, psi1, psi2, sum_y2);       // the one host synchronisation of the step
+    return sweep_host(ctx, N, X, ybar, yvar, wts, psi0, psi1, psi2, sum_y2, false);
+}
+
+int sgp_sweep_psi_host_packed(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts, double* psi0,
+                              double* psi1, double* psi2_packed, double* sum_y2) {
+    return sweep_host(ctx, N, X, ybar, yvar, wts, psi0, psi1, psi2_packed, sum_y2, true);
+}
+
+int sgp_fetch_psi2_packed(sgp_ctx* ctx, double* psi2_packed) {
+    if (check(ctx) || !psi2_packed) return SGP_ERR_ARG;
+    if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "fetch_psi2_packed: no statistics (sweep first)");
+    SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
+    return fetch_stats(ctx, nullptr, nullptr, psi2_packed, nullptr, true);
 }
 
 int sgp_sweep_psi_uncertain(sgp_ctx* ctx, int method, int p, int64_t N, const double* mean, const double* cov, int D_out, const double* R,

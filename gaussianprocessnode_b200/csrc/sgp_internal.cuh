@@ -54,6 +54,14 @@ struct sgp_ctx {
     void* kbuf_window = nullptr; size_t kbuf_window_bytes = 0;   // L2 access-policy window currently set on the stream
     double* kbuf_dev = nullptr;  size_t kbuf_cap = 0;      // L2-resident K_uf panel of one slab (generate-once sweep)
     double* fetch_host = nullptr; size_t fetch_cap = 0;    // pinned staging of the small results (Psi1 | scalars)
+    // sgp_sweep_psi_host: the upload runs on stream2 BESIDE the sweep kernel's launch; the kernel waits for `ready_dev` (a word the copy engine
+    // writes after the data, in stream order) before it touches the data.  upload_pending: copies are in flight on stream2 that the main stream
+    // has not been ordered after yet (sgp_join_upload orders it; the generate-once sweep consumes the flag instead).
+    unsigned* ready_dev = nullptr; unsigned* ready_host = nullptr; unsigned ready_epoch = 0; bool upload_pending = false;
+    // packed lower triangle of Psi2 (LAPACK 'L' packed storage) for the host: written by the sweep's phase 2 / the exchange, or by pack_lower_kernel
+    double* packed_dev = nullptr; size_t packed_cap = 0;
+    bool want_packed = false;                              // the running call returns Psi2 packed: the sweep should leave it in packed_src
+    const double* packed_src = nullptr;                    // ... where the last sweep left it (nullptr: not produced, fetch packs it)
     void* flush_dev = nullptr; size_t flush_cap = 0;       // L2 flush buffer of sgp_sweep_timed_flushed
     unsigned sweep_bar_epoch = 0;                          // launch counter of the plain-launch grid barrier (SGP_SWEEP_COOP=0)
     unsigned* sweep_flags_dev = nullptr;                   // generation / consumption counters of the generate-once sweep
@@ -114,6 +122,7 @@ struct SgpRange {
 int sgp_ensure(sgp_ctx* ctx, double** p, size_t* cap, size_t need_doubles);
 int sgp_ensure_zero(sgp_ctx* ctx, double** p, size_t* cap, size_t need_doubles);      // zero-filled when (re)allocated
 
+int sgp_join_upload(sgp_ctx* ctx);     // api.cu: orders the main stream after an upload still in flight on the copy stream (no-op otherwise)
 // sweep.cu
 int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const double* yv, const double* w, int64_t N,
                      int64_t Ncap, bool time_main);

@@ -114,6 +114,20 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     ctx->last_sweep_exchanged = false;
     p.stats_out = ctx->stats_dev;
     if (ctx->want_exchange && sgp_comm_xchg(ctx, (size_t)M * (M + 1) / 2 + M + 4, &p.xr)) ctx->last_sweep_exchanged = true;
+    // the host wants Psi2 as the packed lower triangle (sgp_sweep_psi_host_packed): the exchange leaves exactly that in this rank's result
+    // buffer; without an exchange phase 2 writes a packed copy next to the full square
+    p.packed_out = nullptr;
+    if (ctx->want_packed) {
+        if (ctx->last_sweep_exchanged) ctx->packed_src = reinterpret_cast<const double*>(p.xr.peers[p.xr.rank] + p.xr.slot0_off + p.xr.slot_bytes);
+        else {
+            rc = sgp_ensure(ctx, &ctx->packed_dev, &ctx->packed_cap, (size_t)M * (M + 1) / 2 + 2); if (rc) return rc;
+            p.packed_out = ctx->packed_dev; ctx->packed_src = ctx->packed_dev;
+        }
+    }
+    // an upload still in flight on the copy stream (sgp_sweep_psi_host): the kernel is launched NOW and waits on the device for the ready word that
+    // follows the data -- launch latency and set-up run under the copies
+    p.ready = nullptr; p.ready_val = 0;
+    if (ctx->upload_pending) { p.ready = ctx->ready_dev; p.ready_val = ctx->ready_epoch; ctx->upload_pending = false; }
 
     // the panel ring is the only buffer worth keeping in L2: mark it persisting, everything else streams through the rest of the cache
     if (ctx->kbuf_window != (void*)ctx->kbuf_dev || ctx->kbuf_window_bytes != (size_t)nring * slab_chunks * chunk_doubles * sizeof(double)) {
@@ -170,6 +184,8 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
         }
     }
     ctx->last_sweep_exchanged = false;
+    ctx->packed_src = nullptr;
+    { int rcj = sgp_join_upload(ctx); if (rcj) return rcj; }      // (this kernel has no ready-word wait)
     const int M = ctx->M, D = ctx->D;
     const int dpad = D <= 4 ? 4 : D <= 8 ? 8 : 16;
     const int TM = (M > 192) ? 128 : 64;

@@ -70,6 +70,9 @@ struct Params {
     int coop;                     // 1: cooperative launch (grid.sync), 0: plain launch + ticket barrier
     SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none): phase 2 then writes [packed lower triangle of Psi2 | Psi1 | scalars] into this rank's contribution buffer
     double* stats_out;            // ... and the sums over the ranks land here (full symmetric Psi2 | Psi1 | scalars); = psi2 without exchange
+    double* packed_out;           // optional (no exchange): phase 2 also writes the packed lower triangle of Psi2 here (LAPACK 'L' packed storage, for the host)
+    const unsigned* ready;        // optional: a word the copy engine writes AFTER the input data of this sweep (sgp_sweep_psi_host): nothing reads
+    unsigned ready_val;           // X / y / w / yv before *ready == ready_val
 };
 
 __device__ __forceinline__ void mbar_wait_(unsigned long long* bar, unsigned parity) {
@@ -648,7 +651,10 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                         const int rl = e % SR, c = e / SR, r = r0 + rl, gi = I * TM + r, gj = J * TM + c;
                         if (gi < p.M && gj < p.M && (!diag || c <= r)) {
                             if (packed) sgp_xchg::put1(p.xr, sgp_xchg::tri_col(gj, p.M) + gi - gj, Sq[rl * LDS_ + c]);
-                            else p.psi2[(size_t)gi + (size_t)gj * p.M] = Sq[rl * LDS_ + c];
+                            else {
+                                p.psi2[(size_t)gi + (size_t)gj * p.M] = Sq[rl * LDS_ + c];
+                                if (p.packed_out) p.packed_out[sgp_xchg::tri_col(gj, p.M) + gi - gj] = Sq[rl * LDS_ + c];
+                            }
                         }
                     }
                     if (!packed) {   // mirror psi2[gj + gi*M]: consecutive threads -> consecutive columns (multi-GPU: the pull writes both halves)
@@ -716,12 +722,13 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     const int gblk = (int)(((long long)bcta * p.nblk) / p.ncta);
     const int glo = gen_lo(gblk, p.ncta, p.nblk), ghi = gen_lo(gblk + 1, p.ncta, p.nblk);
     const int gk = bcta - glo, gcnt = ghi - glo;
-    if (tid == 0) {    // the first generator phase's raw points: their DRAM latency overlaps the set-up below
+    auto first_points = [&]() {    // (thread 0) the first generator phase's raw points: their DRAM latency overlaps the set-up below
         const long long scs0 = min(p.slab_chunks, p.chunks);
         const long long c_lo = scs0 * gk / gcnt, c_hi = scs0 * (gk + 1) / gcnt;
         const int nch = (int)(c_hi - c_lo), ngr = (nch + kGC - 1) / kGC;
         for (int gi = 0; gi < kXStages - 1 && gi < ngr; ++gi) issue_points<TM, NB, DPAD, WEIGHTED>(p, sm, c_lo, nch, gi, 0u);
-    }
+    };
+    if (!p.ready && tid == 0) first_points();
     // exp table: loads first, stores after the scalar sums below (their loads overlap)
     double tabv[SGP_EXP_TAB / NT];
 #pragma unroll
@@ -742,6 +749,19 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
             if (++J > I) { ++I; J = 0; }
         }
         sm.segtab[8 * ns] = -1;
+    }
+    if (p.ready) {     // the input data are still on their way from the host (sgp_sweep_psi_host launches this kernel beside its upload): wait for
+                       // the word the copy engine writes after them; everything above ran under the copies
+        if (tid == 0) {
+            const long long t0 = clock64();
+            while (sgp_xchg::ld_acquire_sys(p.ready) != p.ready_val) {
+                __nanosleep(64);
+                if (clock64() - t0 > (1ll << 34)) __trap();      // a lost upload fails loudly instead of hanging the GPU
+            }
+            fence_proxy_async();      // ... before the TMA reads of the points
+            first_points();
+        }
+        __syncthreads();
     }
     {   // sum_n w_n and sum_n w_n (y_n^2 + yv_n) over this CTA's stripe of points
         const long long n_lo = p.N * bcta / p.ncta, n_hi = p.N * (bcta + 1) / p.ncta;

@@ -55,6 +55,24 @@ def pinned_empty(shape, order="C"):
     return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order=order)
 
 
+def pack_lower(A):
+    """Lower triangle of a square matrix column by column (LAPACK 'L' packed storage) -- the layout of sgp_sweep_psi_host_packed."""
+    A = np.asarray(A)
+    M = A.shape[0]
+    return np.concatenate([A[j:, j] for j in range(M)]) if M else np.empty(0)
+
+
+def unpack_lower(packed, M):
+    """Full symmetric matrix (column-major) from the packed lower triangle."""
+    out = np.empty((M, M), order="F")
+    r, c = np.tril_indices(M)
+    order = np.lexsort((r, c))                 # column by column
+    r, c = r[order], c[order]
+    out[r, c] = packed
+    out[c, r] = packed
+    return out
+
+
 class SGPContext:
     """Owns one ``sgp_ctx``.  Layout notes: the C ABI takes Julia's column-major D x N; a C-contiguous NumPy array of
     shape (N, D) is the same memory, so inputs here are (N, D) / (M, D) row-per-point arrays.  M x M results come back
@@ -133,28 +151,42 @@ class SGPContext:
         self._ck(self.lib.sgp_sweep_psi(self.h, ctypes.byref(psi0), _p(psi1), _p(psi2), ctypes.byref(sy2)))
         return psi0.value, psi1, psi2, sy2.value
 
-    def sweep_psi_host(self, X, ybar=None, yvar=None, wts=None, out=None):
-        """set_data + sweep_psi in one call (one host synchronisation); `out` = (psi1, psi2) preallocated arrays."""
+    def sweep_psi_host(self, X, ybar=None, yvar=None, wts=None, out=None, packed=False):
+        """set_data + sweep_psi in one call (one host synchronisation); `out` = (psi1, psi2) preallocated arrays.
+        packed=True: Psi2 comes back as its packed lower triangle (M (M + 1) / 2 doubles, column by column = LAPACK 'L' packed storage;
+        `unpack_lower` expands it) -- half the bytes over the bus (sgp_sweep_psi_host_packed)."""
         # Steady-state callers pass the SAME (pinned) arrays every step: the argument marshalling (~20 us of ctypes / numpy work, a tenth of the
         # call at the kin40k shape) is cached on the identity of the array objects -- their buffers cannot move while we hold references.
         c = self._host_call
         if (c is not None and out is not None and c[0] is X and c[1] is ybar and c[2] is yvar and c[3] is wts and c[4] is out[0] and c[5] is out[1]
-                and c[6] == X.shape and c[7] == (self.M, self.D)):
+                and c[6] == X.shape and c[7] == (self.M, self.D, bool(packed))):
             N, args, psi0, sy2 = c[8], c[9], c[10], c[11]
             psi1, psi2 = out
         else:
             Xc = _f64(X).reshape(-1, self.D)
             N = Xc.shape[0]; M = self.M
             yb, yv, w = _f64(ybar, (N,)), _f64(yvar, (N,)), _f64(wts, (N,))
-            psi1, psi2 = out if out is not None else (np.empty(M), np.empty((M, M), order="F"))
-            assert psi1.size == M and psi2.shape == (M, M) and psi2.flags.f_contiguous and psi1.dtype == psi2.dtype == np.float64
+            if packed:
+                psi1, psi2 = out if out is not None else (np.empty(M), np.empty(M * (M + 1) // 2))
+                assert psi1.size == M and psi2.shape == (M * (M + 1) // 2,) and psi2.flags.c_contiguous and psi1.dtype == psi2.dtype == np.float64
+            else:
+                psi1, psi2 = out if out is not None else (np.empty(M), np.empty((M, M), order="F"))
+                assert psi1.size == M and psi2.shape == (M, M) and psi2.flags.f_contiguous and psi1.dtype == psi2.dtype == np.float64
             psi0, sy2 = ctypes.c_double(), ctypes.c_double()
             args = (self.h, N, _p(Xc), _p(yb), _p(yv), _p(w), ctypes.byref(psi0), _p(psi1), _p(psi2), ctypes.byref(sy2))
             cacheable = out is not None and all(_is_plain(a) for a in (X, ybar, yvar, wts))      # (no converted temporaries behind the pointers)
-            self._host_call = (X, ybar, yvar, wts, out[0], out[1], X.shape, (M, self.D), N, args, psi0, sy2) if cacheable else None
-        self._ck(self.lib.sgp_sweep_psi_host(*args))
+            self._host_call = (X, ybar, yvar, wts, out[0], out[1], X.shape, (M, self.D, bool(packed)), N, args, psi0, sy2) if cacheable else None
+        self._ck((self.lib.sgp_sweep_psi_host_packed if packed else self.lib.sgp_sweep_psi_host)(*args))
         self.N = N
         return psi0.value, psi1, psi2, sy2.value
+
+    def fetch_psi2_packed(self, out=None):
+        """Psi2 of the last sweep as its packed lower triangle (sgp_fetch_psi2_packed)."""
+        M = self.M
+        out = np.empty(M * (M + 1) // 2) if out is None else out
+        assert out.shape == (M * (M + 1) // 2,) and out.dtype == np.float64 and out.flags.c_contiguous
+        self._ck(self.lib.sgp_fetch_psi2_packed(self.h, _p(out)))
+        return out
 
     def sweep_psi_uncertain(self, method, mean, cov, R=None, D_out=1, p=21, want_psi1_n=False):
         mean = _f64(mean).reshape(-1, self.D)

@@ -86,9 +86,19 @@ int sgp_set_data_dev(sgp_ctx* ctx, int64_t N, const double* X_dev, const double*
 int sgp_sweep_psi(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2);
 
 /* sgp_set_data + sgp_sweep_psi as ONE call with a single host synchronisation: the per-step call of a host whose data change
- * every step (mini-batches).  The data stay resident afterwards exactly as after sgp_set_data. */
+ * every step (mini-batches).  The data stay resident afterwards exactly as after sgp_set_data.  The upload runs on the library's copy
+ * stream BESIDE the launch of the sweep kernel, which waits on the device for a word the copy engine writes after the data (M > 384;
+ * SGP_HOST_OVERLAP=0 restores upload-then-launch); the host buffers must stay untouched until the call returns, as before. */
 int sgp_sweep_psi_host(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts,
                        double* psi0, double* psi1, double* psi2, double* sum_y2);
+/* The same call with Psi2 returned as its PACKED lower triangle, column by column -- psi2_packed[i + j (2M - j - 1) / 2] = Psi2[i, j], i >= j,
+ * M (M + 1) / 2 doubles: LAPACK's packed storage for uplo = 'L' (dpptrf / dspmv take it as is; Julia: the vector behind a
+ * `LinearAlgebra.SymmetricPacked`-style wrapper).  The running sum of `prod` (GPnode/UniSGPnode.jl:62-73) is symmetric, so this is all of it at
+ * half the bytes over the bus; the sweep's last phase writes the packed copy itself (no extra pass, no extra launch). */
+int sgp_sweep_psi_host_packed(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts,
+                              double* psi0, double* psi1, double* psi2_packed, double* sum_y2);
+/* Psi2 of the last sweep (any of the sweeps above), packed as in sgp_sweep_psi_host_packed. */
+int sgp_fetch_psi2_packed(sgp_ctx* ctx, double* psi2_packed);
 
 /* Uncertain inputs q(x_n) = N(mean_n, cov_n): replaces the cubature loop `approximate_kernel_expectation(!)`
  * (GPnode/UniSGPnode.jl:11-37, GPnode/MultiSGPnode.jl:11-35) inside `@rule UniSGP(:v)` (:125-140) and

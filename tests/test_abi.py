@@ -26,7 +26,7 @@ def test_header_declares_the_expected_surface():
     names = _declared()
     for must in ("sgp_create", "sgp_destroy", "sgp_set_kernel", "sgp_set_inducing", "sgp_set_data", "sgp_sweep_psi",
                  "sgp_sweep_psi_uncertain", "sgp_kuu_factor", "sgp_kuu_solve", "sgp_posterior_v", "sgp_w_terms",
-                 "sgp_predict_mean", "sgp_comm_unique_id", "sgp_comm_init", "sgp_sweep_psi_host", "sgp_theta_objective",
+                 "sgp_predict_mean", "sgp_comm_unique_id", "sgp_comm_init", "sgp_sweep_psi_host", "sgp_sweep_psi_host_packed", "sgp_fetch_psi2_packed", "sgp_theta_objective",
                  "sgp_in_logmessage", "sgp_uncertain_node_terms", "sgp_sweep_timed_flushed"):
         assert must in names
 

@@ -204,6 +204,38 @@ def test_one_call_host_step_equals_set_data_plus_sweep(ctx):
     assert np.array_equal(ctx.sweep_psi()[2], a[2])          # the data stay resident after the one-call step
 
 
+@pytest.mark.parametrize("N,D,M", [(3001, 8, 200), (10000, 8, 512), (5000, 3, 640), (0, 2, 400)])
+def test_host_step_with_packed_psi2_and_upload_beside_the_launch(ctx, N, D, M, monkeypatch):
+    # sgp_sweep_psi_host launches the generate-once sweep BESIDE its upload (the kernel waits on the device for the word the copy engine writes
+    # after the data) and sgp_sweep_psi_host_packed returns the lower triangle of Psi2 in LAPACK 'L' packed storage: both must give the bits of
+    # set_data + sweep_psi, for fresh data on every call (a stale read of the previous batch would show), with pinned and pageable buffers,
+    # for the first fused kernel (M <= 384: no device-side wait, packed by a kernel of its own) and with the overlap switched off
+    from gaussianprocessnode_b200 import pinned_empty
+    from gaussianprocessnode_b200.sgp import pack_lower, unpack_lower
+    rng = np.random.default_rng(N + M)
+    Z = rng.normal(size=(M, D))
+    ctx.set_kernel(1.2, np.full(D, 1.6)); ctx.set_inducing(Z)
+    tri = M * (M + 1) // 2
+    Xp = pinned_empty((max(N, 1), D))[:N]; yp = pinned_empty((max(N, 1),))[:N]
+    o1 = pinned_empty((M,)); o2 = pinned_empty((tri,))
+    for it in range(4):
+        X = rng.normal(size=(N, D)); y = rng.normal(size=N); yv = rng.uniform(0, 0.3, N) if it % 2 else None
+        Xp[...] = X; yp[...] = y
+        if it == 3:
+            monkeypatch.setenv("SGP_HOST_OVERLAP", "0")     # upload, then launch (the round-1 order)
+        a = ctx.sweep_psi_host(Xp, yp, yv, out=(o1, o2), packed=True)
+        a = (a[0], a[1].copy(), a[2].copy(), a[3])
+        f = ctx.sweep_psi_host(X, y, yv)                   # pageable buffers, full square
+        ctx.set_data(X, y, yv); b = ctx.sweep_psi()
+        assert a[0] == b[0] == f[0] and a[3] == b[3] == f[3]
+        assert np.array_equal(a[1], b[1]) and np.array_equal(f[1], b[1]) and np.array_equal(f[2], b[2])
+        assert np.array_equal(a[2], pack_lower(b[2])) and np.array_equal(unpack_lower(a[2], M), b[2])
+        assert np.array_equal(ctx.fetch_psi2_packed(), a[2])
+        if N:
+            o0, r1, r2, oy = batched.psi_stats_point(X, y, Z, 1.2, np.full(D, 1.6), yvar=yv)
+            assert fro(b[2], r2) <= TOL and fro(b[1], r1) <= TOL and abs(b[3] - oy) <= TOL * abs(oy)
+
+
 @pytest.mark.parametrize("N,D,M,slab_mb,kind", [(20000, 8, 1024, "1", 0), (20000, 3, 300, "0.3", 0), (9000, 2, 100, "0.05", 0), (6000, 8, 300, "0.2", 2)])
 def test_many_slabs_ring_wraparound(ctx, N, D, M, slab_mb, kind, monkeypatch):
     # the generate-once kernel cuts N into slabs whose K_uf panel lives in a ring of three L2 panels; tiny panels force dozens of slabs
