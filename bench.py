@@ -272,11 +272,16 @@ def main():
         # K steps enqueued back to back on the library's stream: [256 MB L2 flush] [event] sweep (+ exchange over the ranks) [event];
         # the flush is outside the timed intervals, and no host synchronisation sits between the steps (ranks stay in lock step
         # through the exchange itself instead of accumulating host launch skew)
-        ms_step_loc, ms_main_loc = ctx.sweep_timed_flushed(args.steps, 256)
+        # ... and nothing else inside a timed interval: the event pair around the main kernel alone (the roofline's launch duration) is taken in a
+        # second pass of K steps (each event record costs about a microsecond of stream time)
+        ms_step_loc, _ = ctx.sweep_timed_flushed(args.steps, 256, main_kernel=False)
         barrier()
         t_wall = time.perf_counter() - t_wall0
+        ms_step_inner_loc, ms_main_loc = ctx.sweep_timed_flushed(args.steps, 256)
+        barrier()
     ms_step = max_over_ranks(ms_step_loc)
     ms_main = max_over_ranks(ms_main_loc)
+    ms_step_inner = max_over_ranks(ms_step_inner_loc)
     info = ctx.last_sweep_info()
     value = world * cfg["N"] / (ms_step * 1e-3)
 
@@ -379,6 +384,7 @@ def main():
                      "frac_vs_round1_peak_%.1f" % peak_file: achieved / peak_file,
                      "kernel": "sweep4_kernel<128,32,8,256> (generate-once sweep: one cooperative launch per sweep) grid=%d block=%d smem=%d" % (info["grid"], info["block"], info["smem_bytes"]),
                      "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_main, "peak_source": peak_src,
+                     "ms_per_launch_source": "CUDA event pair around the kernel alone on the library's stream, mean over a second pass of %d flushed steps (ms_per_step of that pass, with the inner events: %.4f)" % (args.steps, ms_step_inner),
                      "note": "kin40k shape is 2.6 GFLOP: launch/latency-bound (71 us at peak); see synthetic_10M for the throughput-bound case"},
         "clocks": clk.summary(),
     }
@@ -421,15 +427,17 @@ def main():
             "clocks": clk2.summary()}
         # the same sweep with 32 MB panels (ring of 96 MB: fewer slab turnovers, but the K_uf panels no longer stay in L2 -- they are
         # written back to and partly re-read from HBM); reported beside the default, not instead of it
+        # ... and with 16 MB panels (ring of 48 MB): the configuration whose DRAM traffic stays within 1.5x of the algorithmic bytes (ncu at N = 400k:
+        # 36 + 18 MB per launch against 29 + 8; the default's 60 MB ring leaks ~6 % of its lines: 89 + 194 MB), about 2 % slower
         try:
-            os.environ["SGP_SWEEP_SLAB_MB"] = "32"
-            for _ in range(2):
-                ctx.sweep_timed(1)
-            barrier()
-            ts2 = [ctx.sweep_timed(1)[1] for _ in range(args.syn_steps)]
-            ms2 = max_over_ranks(float(np.mean(ts2)))
-            line["synthetic_10M"]["slab_32MB_spilling"] = {"ms_per_launch": ms2, "tflops": fl / (ms2 * 1e-3) * 1e-12,
-                                                           "frac": fl / (ms2 * 1e-3) * 1e-12 / peak}
+            for mb, key, note in (("32", "slab_32MB_spilling", "K_uf panels round-trip HBM"), ("16", "slab_16MB_hbm_clean", "DRAM traffic <= 1.5x algorithmic (ncu, N = 400k: 36 + 18 MB per launch)")):
+                os.environ["SGP_SWEEP_SLAB_MB"] = mb
+                for _ in range(2):
+                    ctx.sweep_timed(1)
+                barrier()
+                ts2 = [ctx.sweep_timed(1)[1] for _ in range(args.syn_steps)]
+                ms2 = max_over_ranks(float(np.mean(ts2)))
+                line["synthetic_10M"][key] = {"ms_per_launch": ms2, "tflops": fl / (ms2 * 1e-3) * 1e-12, "frac": fl / (ms2 * 1e-3) * 1e-12 / peak, "note": note}
         finally:
             os.environ.pop("SGP_SWEEP_SLAB_MB", None)
         del Xd, yd

@@ -356,8 +356,8 @@ static int sweep_host(sgp_ctx* ctx, int64_t N, const double* X, const double* yb
     ctx->want_packed = packed && psi2 != nullptr;
     rc = sgp_sweep_resident(ctx, false);
     ctx->want_packed = false;
-    const int rcj = sgp_join_upload(ctx);      // (an error path that never launched a consumer of the ready word)
-    if (rc) return rc;
+    const int rcj = sgp_join_upload(ctx);      // (a path that never launched a consumer of the ready word)
+    if (rc) { cudaStreamSynchronize(ctx->stream2); return rc; }      // a failed sweep: nothing of this call stays in flight on the copy stream
     if (rcj) return rcj;
     return fetch_stats(ctx, psi0, psi1, psi2, sum_y2, packed);       // the one host synchronisation of the step
 }
@@ -424,6 +424,9 @@ int sgp_sweep_timed_flushed(sgp_ctx* ctx, int reps, int flush_mb, float* ms_per_
     }
     // everything is enqueued without a host synchronisation: [flush] [e0] sweep (+ exchange) [e1] per repetition, so that the ranks of a
     // multi-GPU job stay in lock step through the exchange itself instead of accumulating host-side launch skew
+    // ms_main_kernel == NULL: no inner event pair around the main kernel -- the timed interval then holds the sweep and nothing else (each event
+    // record costs about a microsecond of stream time; the headline measurement runs without them)
+    const bool inner = ms_main_kernel != nullptr;
     std::vector<cudaEvent_t> ev(4 * (size_t)reps, nullptr);
     for (auto& e : ev) SGP_CUDA(ctx, cudaEventCreate(&e));
     cudaEvent_t keep2 = ctx->ev[2], keep3 = ctx->ev[3];
@@ -435,7 +438,7 @@ int sgp_sweep_timed_flushed(sgp_ctx* ctx, int reps, int flush_mb, float* ms_per_
         if (ctx->comm && sgp_comm_barrier(ctx) != SGP_OK) { rc = SGP_ERR_CUDA; break; }
         if (cudaEventRecord(ev[4 * r], ctx->stream) != cudaSuccess) { rc = SGP_ERR_CUDA; break; }
         ctx->ev[2] = ev[4 * r + 2]; ctx->ev[3] = ev[4 * r + 3];       // the launcher brackets the main kernel with ev[2] / ev[3]
-        rc = sgp_sweep_resident(ctx, true);
+        rc = sgp_sweep_resident(ctx, inner);
         if (rc == SGP_OK && cudaEventRecord(ev[4 * r + 1], ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
     }
     ctx->ev[2] = keep2; ctx->ev[3] = keep3;
@@ -443,14 +446,13 @@ int sgp_sweep_timed_flushed(sgp_ctx* ctx, int reps, int flush_mb, float* ms_per_
     if (rc == SGP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = SGP_ERR_CUDA;
     for (int r = 0; r < reps && rc == SGP_OK; ++r) {
         float a = 0.f, b = 0.f;
-        if (cudaEventElapsedTime(&a, ev[4 * r], ev[4 * r + 1]) != cudaSuccess || cudaEventElapsedTime(&b, ev[4 * r + 2], ev[4 * r + 3]) != cudaSuccess) rc = SGP_ERR_CUDA;
+        if (cudaEventElapsedTime(&a, ev[4 * r], ev[4 * r + 1]) != cudaSuccess || (inner && cudaEventElapsedTime(&b, ev[4 * r + 2], ev[4 * r + 3]) != cudaSuccess)) rc = SGP_ERR_CUDA;
         tot += a; main_sum += b;
     }
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (rc != SGP_OK) { if (ctx->err.empty()) ctx->err = "sweep_timed_flushed: CUDA failure"; return rc; }
     if (ms_per_sweep) *ms_per_sweep = (float)(tot / reps);
-    if (ms_main_kernel) *ms_main_kernel = (float)(main_sum / reps);
-    ctx->last_main_ms = (float)(main_sum / reps);
+    if (ms_main_kernel) { *ms_main_kernel = (float)(main_sum / reps); ctx->last_main_ms = (float)(main_sum / reps); }
     return SGP_OK;
 }
 

@@ -209,12 +209,13 @@ class SGPContext:
         self._ck(self.lib.sgp_sweep_timed(self.h, int(reps), ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
-    def sweep_timed_flushed(self, reps=1, flush_mb=256):
+    def sweep_timed_flushed(self, reps=1, flush_mb=256, main_kernel=True):
         """Mean device time of one sweep (and of its main kernel) over `reps` back-to-back repetitions, each preceded by an
-        L2 flush on the library's stream (outside the timed intervals); no host synchronisation between repetitions."""
+        L2 flush on the library's stream (outside the timed intervals); no host synchronisation between repetitions.
+        main_kernel=False: no inner event pair around the main kernel (the timed interval holds the sweep alone); returns (ms, None)."""
         a, b = ctypes.c_float(), ctypes.c_float()
-        self._ck(self.lib.sgp_sweep_timed_flushed(self.h, int(reps), int(flush_mb), ctypes.byref(a), ctypes.byref(b)))
-        return a.value, b.value
+        self._ck(self.lib.sgp_sweep_timed_flushed(self.h, int(reps), int(flush_mb), ctypes.byref(a), ctypes.byref(b) if main_kernel else None))
+        return a.value, (b.value if main_kernel else None)
 
     def sweep_debug_clocks(self, cap=8192):
         """First call switches per-segment clock recording on; later calls return an (n, 4) int64 array

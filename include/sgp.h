@@ -205,7 +205,8 @@ int sgp_sweep_timed(sgp_ctx* ctx, int reps, float* ms_per_sweep, float* ms_main_
 /* The same with an L2 flush (a `flush_mb` MB device buffer is rewritten on the ctx stream) before every repetition, all repetitions
  * enqueued without a host synchronisation; the flush is outside the timed intervals (one event pair per repetition).  With a
  * communicator attached the ranks are aligned by a flag barrier on the stream between the flush and the start of every timed interval,
- * and stay in lock step through the exchange itself. */
+ * and stay in lock step through the exchange itself.  ms_main_kernel == NULL: the main kernel is not bracketed by its own event pair (the
+ * timed interval then contains the sweep alone). */
 int sgp_sweep_timed_flushed(sgp_ctx* ctx, int reps, int flush_mb, float* ms_per_sweep, float* ms_main_kernel);
 /* Device time of the M x M entry points on the resident state (CUDA events on the ctx stream around the call's kernels; no host copies):
  * what = 0: sgp_kuu_factor(jitter), 1: sgp_posterior_v_stream(w, carry = 0) with Uv, 2: the same without Uv, 3: sgp_w_terms(NULL, NULL).

@@ -197,6 +197,19 @@ function sweep_psi_host!(meta::UniSGPMeta, X::Matrix{Float64}, y::Vector{Float64
     return ψ0[], sy2[]
 end
 
+# the same with Ψ2 as its packed lower triangle (LAPACK uplo = 'L' packed storage, M(M+1)/2 doubles): half the bytes over the bus.
+# `ap` is best a vector over sgp_pinned_alloc memory; Ψ2[i, j] = ap[i + (j - 1) * (2M - j) ÷ 2] for i ≥ j (1-based).
+function sweep_psi_host_packed!(meta::UniSGPMeta, X::Matrix{Float64}, y::Vector{Float64}, ap::Vector{Float64})
+    M = size(meta.Ψ2, 1)
+    @assert length(ap) == M * (M + 1) ÷ 2
+    ψ0 = Ref(0.0); sy2 = Ref(0.0)
+    sgp_check(meta.h, ccall((:sgp_sweep_psi_host_packed, libsgp), Cint,
+                            (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}),
+                            meta.h.ptr, size(X, 2), X, y, C_NULL, C_NULL, ψ0, vec(meta.Ψ1_trans), ap, sy2))
+    meta.resident = UInt64(0); meta.swept = true
+    return ψ0[], sy2[]
+end
+
 # ---- MultiSGP :in messages for a whole chain (GPnode/MultiSGPnode.jl:162-236, prod override :38-45) ------------------------------
 # Xp: d×P×N cubature points (P per node), R: D×N columns W μ_y,n (row-major N×D for the library = this array's memory), Mv = reshape(μ_v, M, D),
 # S = sum(create_blockmatrix(Σ_v + μ_v μ_v', D, M) .* W).  Returns f (P×N); with derivatives = true also ∇f (d×P×N) and ∇²f (d×d×P×N).

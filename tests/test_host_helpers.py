@@ -66,3 +66,23 @@ def test_sweep_psi_host_caches_its_marshalling_only_for_the_same_plain_arrays():
     c.sweep_psi_host(X, y, out=out); c.M = 5
     with __import__("pytest").raises(AssertionError):
         c.sweep_psi_host(X, y, out=out)                               # M changed: the cached outputs no longer fit -> rebuilt and checked
+
+
+def test_packed_lower_triangle_is_lapack_L_packed_storage():
+    # the layout of sgp_sweep_psi_host_packed / sgp_fetch_psi2_packed and of the exchange buffers (csrc/xchg.cuh: tri_col):
+    # AP[i + j (2M - j - 1) / 2] = A[i, j] for i >= j (0-based), which is what LAPACK's uplo = 'L' packed routines take
+    from gaussianprocessnode_b200.sgp import pack_lower, unpack_lower
+    from gaussianprocessnode_b200 import shard
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(5)
+    for M in (1, 2, 7, 33):
+        B = rng.normal(size=(M, M + 3)); A = B @ B.T + M * np.eye(M)
+        ap = pack_lower(A)
+        assert ap.size == M * (M + 1) // 2
+        for j in range(M):
+            assert shard.tri_col(j, M) == j * (2 * M - j - 1) // 2 + j
+            for i in range(j, M):
+                assert ap[i + j * (2 * M - j - 1) // 2] == A[i, j]
+        assert np.array_equal(unpack_lower(ap, M), A)
+        c, info = lapack.dpptrf(M, ap, lower=1)                  # packed Cholesky straight on the vector
+        assert info == 0 and np.allclose(np.tril(unpack_lower(c, M)), np.linalg.cholesky(A), rtol=1e-12, atol=1e-12)
