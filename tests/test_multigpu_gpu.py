@@ -40,6 +40,15 @@ def _worker(rank, world, port, out, p2p, M):
     same = bool(np.array_equal(p2, q2) and np.array_equal(p1, q1) and p0 == q0 and sy == qy)
     digest = hashlib.sha256(p2.tobytes() + p1.tobytes()).hexdigest()
     info = ctx.last_sweep_info()
+    # the one-call host step under sharding (collective): upload beside the launch, device-side ready word, then the exchange; Psi2 packed =
+    # this rank's result buffer of the exchange (peer-memory path) or a packed copy of the all-reduced square (NCCL path, first fused kernel)
+    from gaussianprocessnode_b200.sgp import pack_lower
+    lo, hi = shard.shard_bounds(N, world, rank)
+    for it in range(3):
+        h0, h1, hk, hy = ctx.sweep_psi_host(X[lo:hi], y[lo:hi], yv[lo:hi], packed=True)
+        g0, g1, g2, gy = ctx.sweep_psi_host(X[lo:hi], y[lo:hi], yv[lo:hi])
+        same = same and bool(np.array_equal(hk, pack_lower(p2)) and np.array_equal(g2, p2) and np.array_equal(h1, p1) and np.array_equal(g1, p1)
+                             and h0 == p0 == g0 and hy == sy == gy and np.array_equal(ctx.fetch_psi2_packed(), hk))
     ctx.close()
     single = SGPContext(rank); single.set_kernel(1.2, ell); single.set_inducing(Z); single.set_data(X, y, yv)
     f0, f1, f2, fy = single.sweep_psi(); single.close()
