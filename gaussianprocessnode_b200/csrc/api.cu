@@ -126,6 +126,7 @@ void sgp_destroy(sgp_ctx* ctx) {
     if (ctx->ready_dev) cudaFree(ctx->ready_dev);
     if (ctx->ready_host) cudaFreeHost(ctx->ready_host);
     if (ctx->packed_dev) cudaFree(ctx->packed_dev);
+    if (ctx->p2plan_dev) cudaFree(ctx->p2plan_dev);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -65,6 +65,9 @@ struct sgp_ctx {
     void* flush_dev = nullptr; size_t flush_cap = 0;       // L2 flush buffer of sgp_sweep_timed_flushed
     unsigned sweep_bar_epoch = 0;                          // launch counter of the plain-launch grid barrier (SGP_SWEEP_COOP=0)
     unsigned* sweep_flags_dev = nullptr;                   // generation / consumption counters of the generate-once sweep
+    int* p2plan_dev = nullptr; size_t p2plan_cap = 0;      // phase-2 plan of the generate-once sweep (sweep.cu: build_p2_plan) ...
+    long long p2plan_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // ... and the configuration it was built for
+    int p2plan_off[4] = {0, 0, 0, 0};                      // int offsets of {cta_off, items, tile_off, slots} inside p2plan_dev
     double* exptab_dev = nullptr;
     double* dense_dev = nullptr; size_t dense_cap = 0;     // M x M scratch for factorisations
     int* info_dev = nullptr;

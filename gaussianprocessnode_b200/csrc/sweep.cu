@@ -32,10 +32,107 @@
 // instructions per value are paid from the same budget: (TI+TJ)*16 / (TI*TJ) = 25 % on top of the MMA work for a 128x128
 // off-diagonal tile.
 #include "sweep4_kernel.cuh"
+#include <cstring>
+#include <vector>
+#include <algorithm>
 
 using namespace sgp_sweep;
 
 int sgp_sweep_chunk() { return 32; }
+
+// Phase-2 plan of the generate-once sweep, built once per configuration and kept on the device:
+//   * per tile, the workspace slots (= cta + tile) of its segments in CTA order -- the same cta_pos / seg_range arithmetic the kernel uses for its
+//     own segment table, evaluated here for all CTAs (the kernel used to redo it after the grid barrier: ~7 64-bit divisions per thread);
+//   * per CTA, the (tile, stripe range) entries it reduces.  With at least as many CTAs as tiles every CTA gets stripes of ONE tile (a CTA whose
+//     range straddled two tiles paid the slot set-up and a batch of loads twice and was the last to finish); the CTAs are dealt to the tiles in
+//     proportion to the tiles' reduction cost (a stripe of a diagonal tile moves about 0.6 of an off-diagonal one).  More tiles than CTAs: contiguous
+//     (tile, stripe) ranges, split at the tile boundaries.
+// Every output element is still produced by one thread that adds the tile's partials in CTA order: bits do not depend on the plan.
+static int build_p2_plan(sgp_ctx* ctx, sgp_sweep4::Params& p, int TM) {
+    const long long key[8] = {p.total_cost, p.slab_units, p.ncta, p.ntiles, p.w_diag, p.w_off, p.w_fixed, TM};
+    const int SR = 4, STRIPES = TM / SR;
+    const int ncta = p.ncta, ntiles = p.ntiles;
+    if (!ctx->p2plan_dev || std::memcmp(key, ctx->p2plan_key, sizeof(key)) != 0) {
+        std::vector<int> tile_off(ntiles + 1, 0), slots;
+        {
+            long long pre = 0;
+            int I = 0, J = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const int wt = (I == J) ? p.w_diag : p.w_off;
+                for (int c = 0; c < ncta; ++c) {
+                    long long lo, hi;
+                    seg_range(cta_pos(p.total_cost, ncta, c), cta_pos(p.total_cost, ncta, c + 1), pre, wt, p.w_fixed, p.slab_units, lo, hi);
+                    if (lo < hi) slots.push_back(c + t);
+                }
+                tile_off[t + 1] = (int)slots.size();
+                pre += (long long)wt * p.slab_units + p.w_fixed;
+                if (++J > I) { ++I; J = 0; }
+            }
+        }
+        std::vector<int> cta_off(ncta + 1, 0), items;
+        if (ncta >= ntiles) {
+            // CTAs per tile in proportion to the reduction cost, at least one each; largest-remainder rounding keeps the total at ncta
+            std::vector<double> cost(ntiles);
+            double tot = 0.0;
+            { int I = 0, J = 0; for (int t = 0; t < ntiles; ++t) { cost[t] = (I == J) ? 0.6 : 1.0; tot += cost[t]; if (++J > I) { ++I; J = 0; } } }
+            std::vector<int> cnt(ntiles, 1);
+            int left = ncta - ntiles;
+            std::vector<double> want(ntiles);
+            for (int t = 0; t < ntiles; ++t) want[t] = cost[t] / tot * ncta;
+            for (int t = 0; t < ntiles; ++t) { const int extra = std::max(0, std::min(left, (int)want[t] - 1)); cnt[t] += extra; left -= extra; }
+            while (left > 0) {      // the largest shortfall first (ties: the lower tile index -- deterministic)
+                int best = 0;
+                for (int t = 1; t < ntiles; ++t) if (want[t] - cnt[t] > want[best] - cnt[best]) best = t;
+                ++cnt[best]; --left;
+            }
+            int c = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const int k = std::min(cnt[t], STRIPES);      // (more CTAs than stripes: the surplus idles in phase 2)
+                for (int q = 0; q < cnt[t]; ++q, ++c) {
+                    cta_off[c] = (int)items.size() / 3;
+                    if (q < k) {
+                        const int lo = STRIPES * q / k, hi = STRIPES * (q + 1) / k;
+                        if (lo < hi) { items.push_back(t); items.push_back(lo); items.push_back(hi); }
+                    }
+                }
+            }
+            cta_off[ncta] = (int)items.size() / 3;
+        } else {
+            const long long nitems = (long long)ntiles * STRIPES;
+            for (int c = 0; c < ncta; ++c) {
+                cta_off[c] = (int)items.size() / 3;
+                long long it = nitems * c / ncta;
+                const long long it1 = nitems * (c + 1) / ncta;
+                while (it < it1) {
+                    const int tile = (int)(it / STRIPES), lo = (int)(it - (long long)tile * STRIPES);
+                    const int hi = (int)std::min<long long>(STRIPES, lo + (it1 - it));
+                    items.push_back(tile); items.push_back(lo); items.push_back(hi);
+                    it += hi - lo;
+                }
+            }
+            cta_off[ncta] = (int)items.size() / 3;
+        }
+        std::vector<int> all;
+        int off[4];
+        off[0] = 0; all.insert(all.end(), cta_off.begin(), cta_off.end());
+        off[1] = (int)all.size(); all.insert(all.end(), items.begin(), items.end());
+        off[2] = (int)all.size(); all.insert(all.end(), tile_off.begin(), tile_off.end());
+        off[3] = (int)all.size(); all.insert(all.end(), slots.begin(), slots.end());
+        if (ctx->p2plan_cap < all.size()) {
+            if (ctx->p2plan_dev) SGP_CUDA(ctx, cudaFree(ctx->p2plan_dev));
+            ctx->p2plan_dev = nullptr; ctx->p2plan_cap = 0;
+            SGP_CUDA(ctx, cudaMalloc((void**)&ctx->p2plan_dev, (all.size() + 1024) * sizeof(int)));
+            ctx->p2plan_cap = all.size() + 1024;
+        }
+        // (a pageable source: the runtime stages it before the call returns; an earlier sweep still reading the old plan is ordered before it on the stream)
+        SGP_CUDA(ctx, cudaMemcpyAsync(ctx->p2plan_dev, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        std::memcpy(ctx->p2plan_key, key, sizeof(key));
+        std::memcpy(ctx->p2plan_off, off, sizeof(off));
+    }
+    p.p2_cta_off = ctx->p2plan_dev + ctx->p2plan_off[0]; p.p2_items = ctx->p2plan_dev + ctx->p2plan_off[1];
+    p.p2_tile_off = ctx->p2plan_dev + ctx->p2plan_off[2]; p.p2_slots = ctx->p2plan_dev + ctx->p2plan_off[3];
+    return SGP_OK;
+}
 
 // ---- generate-once sweep (sweep4_kernel.cuh): every K_uf value is generated once per sweep into an L2-resident slab panel and
 // consumed by a TMA-fed DMMA SYRK.  Returns 1 when the shape is outside its range (nblk > CTAs): the caller falls back.
@@ -99,6 +196,7 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     p.log_var_s = SGP_EXP_SCALE * std::log(ctx->variance); p.variance = ctx->variance;
     p.Z = ctx->Z_dev; p.exptab = ctx->exptab_dev; p.Kbuf = ctx->kbuf_dev; p.flags = ctx->sweep_flags_dev;
     p.slab_doubles = (long long)(slab_chunks * chunk_doubles); p.nring = nring;
+    rc = build_p2_plan(ctx, p, TM); if (rc) return rc;
     // launch form: cooperative (co-residency of the persistent CTAs guaranteed by the driver) unless SGP_SWEEP_COOP=0 asks for a plain launch
     // with the kernel's own ticket barrier (the grid is one CTA per SM: resident as long as nothing else occupies the device)
     {

@@ -71,6 +71,12 @@ struct Params {
     SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none): phase 2 then writes [packed lower triangle of Psi2 | Psi1 | scalars] into this rank's contribution buffer
     double* stats_out;            // ... and the sums over the ranks land here (full symmetric Psi2 | Psi1 | scalars); = psi2 without exchange
     double* packed_out;           // optional (no exchange): phase 2 also writes the packed lower triangle of Psi2 here (LAPACK 'L' packed storage, for the host)
+    // phase-2 plan, built on the host once per configuration (sweep.cu: build_p2_plan): which (tile, stripe range) every CTA reduces and, per tile,
+    // the workspace slots of its segments in CTA order -- the kernel neither divides nor searches after the last grid barrier
+    const int* p2_cta_off;        // [ncta + 1] offsets into p2_items
+    const int* p2_items;          // {tile, first stripe, last stripe + 1} per entry
+    const int* p2_tile_off;       // [ntiles + 1] offsets into p2_slots
+    const int* p2_slots;          // workspace slots (= cta + tile) of the tile's segments, in CTA order
     const unsigned* ready;        // optional: a word the copy engine writes AFTER the input data of this sweep (sgp_sweep_psi_host): nothing reads
     unsigned ready_val;           // X / y / w / yv before *ready == ready_val
 };
@@ -578,50 +584,51 @@ __host__ __device__ inline int gen_lo(int b, int ncta, int nblk) { return (int)(
 // phase 2 (after the last grid barrier): as reduce_items of sweep_kernel.cuh, with Psi1 summed over the generator CTAs of the
 // row block and the scalars over all CTAs -- always in CTA order: deterministic
 template <int TM, int NT>
-__device__ __forceinline__ void reduce_items4(const Params& p, double* __restrict__ S_, int* __restrict__ ibuf, long long* tr) {
+__device__ __forceinline__ void reduce_items4(const Params& p, double* __restrict__ S_, int* __restrict__ ibuf, const int* __restrict__ hdr, long long* tr) {
     constexpr int SR = 4, STRIPES = TM / SR, NWARPS = NT / 32, LDS_ = TM + 1;
     constexpr int NBATCH = 4;                        // stripes whose loads are in flight together (S_ holds NBATCH stripes)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nitems = p.ntiles * STRIPES;
     const bool packed = p.xr.nranks > 1;
     const long long tri = (long long)p.M * (p.M + 1) / 2;
-    const int it0 = (int)((long long)nitems * blockIdx.x / gridDim.x), it1 = (int)((long long)nitems * (blockIdx.x + 1) / gridDim.x);
     int* slots = ibuf + NWARPS;
-    int it = it0;
-    while (it < it1) {
+    // hdr (shared memory, read from the plan at kernel start): {first entry, last entry + 1, and of the first entry: tile, first stripe, last stripe + 1,
+    // offset of the tile's slot list, its length} -- no chain of dependent global loads after the grid barrier for the usual one-entry CTA
+    const int en_lo = hdr[0], en_hi = hdr[1];
+    for (int en = en_lo; en < en_hi; ++en) {
         long long r0_ = 0, r1_ = 0, r2_ = 0;
         if (p.dbg) r0_ = clock64();
-        const int tile = it / STRIPES;
-        const int s_lo = it - tile * STRIPES, s_hi = min(STRIPES, s_lo + (it1 - it));      // this CTA's stripes of the tile
-        // the tile's workspace slots in CTA order: one candidate CTA per thread (ncta <= NT)
-        long long pre = 0;
-        int I = 0, J = 0;
-        for (int t = 0; t < tile; ++t) {
-            pre += (long long)(I == J ? p.w_diag : p.w_off) * p.slab_units + p.w_fixed;
-            if (++J > I) { ++I; J = 0; }
+        int tile, s_lo, s_hi, so, nseg;                      // this CTA's stripes of the tile; the tile's workspace slots in CTA order (host-built table)
+        if (en == en_lo) { tile = hdr[2]; s_lo = hdr[3]; s_hi = hdr[4]; so = hdr[5]; nseg = hdr[6]; }
+        else {
+            tile = p.p2_items[3 * en]; s_lo = p.p2_items[3 * en + 1]; s_hi = p.p2_items[3 * en + 2];
+            so = p.p2_tile_off[tile]; nseg = p.p2_tile_off[tile + 1] - so;
         }
-        int mine = 0;
-        if (tid < p.ncta) {
-            long long lo, hi;
-            seg_range(cta_pos(p.total_cost, p.ncta, tid), cta_pos(p.total_cost, p.ncta, tid + 1), pre, I == J ? p.w_diag : p.w_off, p.w_fixed,
-                      p.slab_units, lo, hi);
-            mine = lo < hi;
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, mine);
-        __syncthreads();                                     // the previous tile is done with ibuf / S_
-        if (lane == 0) ibuf[warp] = (int)ballot;
-        const int nseg = __syncthreads_count(mine);
-        if (mine) {
-            int before = __popc(ballot & ((1u << lane) - 1u));
-            for (int wq = 0; wq < warp; ++wq) before += __popc((unsigned)ibuf[wq]);
-            slots[before] = tid + tile;
-        }
+        int I = 0;
+        while ((I + 1) * (I + 2) / 2 <= tile) ++I;
+        const int J = tile - I * (I + 1) / 2;
+        __syncthreads();                                     // the previous entry is done with ibuf / S_
+        for (int i = tid; i < nseg; i += NT) slots[i] = p.p2_slots[so + i];
         __syncthreads();
         if (p.dbg) { r1_ = clock64(); tr[0] += r1_ - r0_; }
         const bool diag = (I == J);
         for (int sb = s_lo; sb < s_hi; sb += NBATCH) {
             if (p.dbg) r1_ = clock64();
             const int nb = min(NBATCH, s_hi - sb);
+            // Psi1 rows of the batch's stripes (diagonal tiles; warp w < SR owns row w of every stripe): a lane per generator CTA of the row block, all
+            // stripes' loads in flight together and ahead of the partial-tile loads below; fixed-shape tree -> deterministic
+            double p1v[NBATCH];
+#pragma unroll
+            for (int q = 0; q < NBATCH; ++q) p1v[q] = 0.0;
+            if (diag && warp < SR) {
+                const int lo = gen_lo(I, p.ncta, p.nblk), hi = gen_lo(I + 1, p.ncta, p.nblk);
+#pragma unroll 2
+                for (int qq = lo + lane; qq < hi; qq += 32) {
+                    const double* src1 = p.psi1_partial + (size_t)qq * TM + sb * SR + warp;
+#pragma unroll
+                    for (int q = 0; q < NBATCH; ++q)
+                        if (q < nb) p1v[q] += __ldcg(src1 + q * SR);
+                }
+            }
             if (tid < SR * TM / 2) {
                 const int e = 2 * tid, rl = e / TM, c = e - rl * TM;
                 double2 v[NBATCH];
@@ -662,11 +669,11 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                         if (gi < p.M && gj < p.M && (diag ? c < r : true)) p.psi2[(size_t)gj + (size_t)gi * p.M] = Sq[rl * LDS_ + c];
                     }
                 }
-                if (diag && warp < SR) {      // Psi1 row r0 + warp: a lane per generator CTA of the row block, fixed-shape tree -> deterministic
+                if (diag && warp < SR) {      // Psi1 row r0 + warp (loaded at the top of the batch)
                     const int r = r0 + warp, gi = I * TM + r;
-                    const int lo = gen_lo(I, p.ncta, p.nblk), hi = gen_lo(I + 1, p.ncta, p.nblk);
                     double v = 0.0;
-                    for (int qq = lo + lane; qq < hi; qq += 32) v += __ldcg(p.psi1_partial + (size_t)qq * TM + r);
+#pragma unroll
+                    for (int qs = 0; qs < NBATCH; ++qs) if (qs == q) v = p1v[qs];      // (static register indices)
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     if (lane == 0 && gi < p.M) {
@@ -692,7 +699,6 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                 }
             }
         }
-        it += s_hi - s_lo;
     }
 }
 
@@ -729,6 +735,18 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
         for (int gi = 0; gi < kXStages - 1 && gi < ngr; ++gi) issue_points<TM, NB, DPAD, WEIGHTED>(p, sm, c_lo, nch, gi, 0u);
     };
     if (!p.ready && tid == 0) first_points();
+    int* p2hdr = reinterpret_cast<int*>(smem + S::bars + 9);       // (the nine mbarriers use the first 9 of the 16 words)
+    if (tid == 64) {   // this CTA's phase-2 work from the host-built plan: the dependent loads (DRAM after an L2 flush) complete under the sweep
+        const int e0 = p.p2_cta_off[bcta], e1 = p.p2_cta_off[bcta + 1];
+        p2hdr[0] = e0; p2hdr[1] = e1;
+        if (e0 < e1) {
+            const int t = p.p2_items[3 * e0];
+            p2hdr[2] = t; p2hdr[3] = p.p2_items[3 * e0 + 1]; p2hdr[4] = p.p2_items[3 * e0 + 2];
+            const int so = p.p2_tile_off[t];
+            p2hdr[5] = so; p2hdr[6] = p.p2_tile_off[t + 1] - so;
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.p2_slots + so));
+        }
+    }
     // exp table: loads first, stores after the scalar sums below (their loads overlap)
     double tabv[SGP_EXP_TAB / NT];
 #pragma unroll
@@ -908,7 +926,7 @@ __global__ void __launch_bounds__(NT, 1) sweep4_kernel(const __grid_constant__ P
     }
     if (p.dbg) t_k3 = clock64();
     long long tr[3] = {0, 0, 0};
-    reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)), tr);
+    reduce_items4<TM, NT>(p, sm.u, reinterpret_cast<int*>(sm.u + 16 * (TM + 1)), p2hdr, tr);
     // the dependency counters are dead after the last grid barrier: leave them zeroed for the next launch (no memset per sweep on the host)
     if (bcta == 0)
         for (int i = tid; i < p.nring * (p.nblk + 1); i += NT) p.flags[i] = 0u;
