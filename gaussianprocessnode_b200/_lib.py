@@ -53,6 +53,8 @@ SIGNATURES = {
     "sgp_sweep_timed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p]),
     "sgp_sweep_timed_flushed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_float_p, c_float_p]),
     "sgp_last_sweep_info": (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "sgp_debug_p2_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int,
+                                        c_int_p]),
     "sgp_sweep_debug_clocks": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, c_int_p]),
     "sgp_stats_dev": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_void_pp, c_void_pp]),
 }

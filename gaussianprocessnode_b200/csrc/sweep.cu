@@ -45,79 +45,106 @@ int sgp_sweep_chunk() { return 32; }
 //     own segment table, evaluated here for all CTAs (the kernel used to redo it after the grid barrier: ~7 64-bit divisions per thread);
 //   * per CTA, the (tile, stripe range) entries it reduces.  With at least as many CTAs as tiles every CTA gets stripes of ONE tile (a CTA whose
 //     range straddled two tiles paid the slot set-up and a batch of loads twice and was the last to finish); the CTAs are dealt to the tiles in
-//     proportion to the tiles' reduction cost (a stripe of a diagonal tile moves about 0.6 of an off-diagonal one).  More tiles than CTAs: contiguous
+//     proportion to the tiles' reduction cost (a stripe of a diagonal tile counts 1.25 off-diagonal ones -- half the partial loads, but its Psi1 rows ride along; measured, tools/p2_knob.py; SGP_SWEEP4_P2_DIAG).  More tiles than CTAs: contiguous
 //     (tile, stripe) ranges, split at the tile boundaries.
 // Every output element is still produced by one thread that adds the tile's partials in CTA order: bits do not depend on the plan.
-static int build_p2_plan(sgp_ctx* ctx, sgp_sweep4::Params& p, int TM) {
-    const long long key[8] = {p.total_cost, p.slab_units, p.ncta, p.ntiles, p.w_diag, p.w_off, p.w_fixed, TM};
+// (pure host arithmetic: also exported as sgp_debug_p2_plan for the CPU tests)
+static void p2_plan_host(int ncta, int ntiles, int TM, long long total_cost, long long slab_units, int w_diag, int w_off, int w_fixed, double diag_cost,
+                         std::vector<int>& all, int off[4]) {
     const int SR = 4, STRIPES = TM / SR;
-    const int ncta = p.ncta, ntiles = p.ntiles;
-    if (!ctx->p2plan_dev || std::memcmp(key, ctx->p2plan_key, sizeof(key)) != 0) {
-        std::vector<int> tile_off(ntiles + 1, 0), slots;
-        {
-            long long pre = 0;
-            int I = 0, J = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const int wt = (I == J) ? p.w_diag : p.w_off;
-                for (int c = 0; c < ncta; ++c) {
-                    long long lo, hi;
-                    seg_range(cta_pos(p.total_cost, ncta, c), cta_pos(p.total_cost, ncta, c + 1), pre, wt, p.w_fixed, p.slab_units, lo, hi);
-                    if (lo < hi) slots.push_back(c + t);
-                }
-                tile_off[t + 1] = (int)slots.size();
-                pre += (long long)wt * p.slab_units + p.w_fixed;
-                if (++J > I) { ++I; J = 0; }
-            }
-        }
-        std::vector<int> cta_off(ncta + 1, 0), items;
-        if (ncta >= ntiles) {
-            // CTAs per tile in proportion to the reduction cost, at least one each; largest-remainder rounding keeps the total at ncta
-            std::vector<double> cost(ntiles);
-            double tot = 0.0;
-            { int I = 0, J = 0; for (int t = 0; t < ntiles; ++t) { cost[t] = (I == J) ? 0.6 : 1.0; tot += cost[t]; if (++J > I) { ++I; J = 0; } } }
-            std::vector<int> cnt(ntiles, 1);
-            int left = ncta - ntiles;
-            std::vector<double> want(ntiles);
-            for (int t = 0; t < ntiles; ++t) want[t] = cost[t] / tot * ncta;
-            for (int t = 0; t < ntiles; ++t) { const int extra = std::max(0, std::min(left, (int)want[t] - 1)); cnt[t] += extra; left -= extra; }
-            while (left > 0) {      // the largest shortfall first (ties: the lower tile index -- deterministic)
-                int best = 0;
-                for (int t = 1; t < ntiles; ++t) if (want[t] - cnt[t] > want[best] - cnt[best]) best = t;
-                ++cnt[best]; --left;
-            }
-            int c = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const int k = std::min(cnt[t], STRIPES);      // (more CTAs than stripes: the surplus idles in phase 2)
-                for (int q = 0; q < cnt[t]; ++q, ++c) {
-                    cta_off[c] = (int)items.size() / 3;
-                    if (q < k) {
-                        const int lo = STRIPES * q / k, hi = STRIPES * (q + 1) / k;
-                        if (lo < hi) { items.push_back(t); items.push_back(lo); items.push_back(hi); }
-                    }
-                }
-            }
-            cta_off[ncta] = (int)items.size() / 3;
-        } else {
-            const long long nitems = (long long)ntiles * STRIPES;
+    std::vector<int> tile_off(ntiles + 1, 0), slots;
+    {
+        long long pre = 0;
+        int I = 0, J = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int wt = (I == J) ? w_diag : w_off;
             for (int c = 0; c < ncta; ++c) {
+                long long lo, hi;
+                seg_range(cta_pos(total_cost, ncta, c), cta_pos(total_cost, ncta, c + 1), pre, wt, w_fixed, slab_units, lo, hi);
+                if (lo < hi) slots.push_back(c + t);
+            }
+            tile_off[t + 1] = (int)slots.size();
+            pre += (long long)wt * slab_units + w_fixed;
+            if (++J > I) { ++I; J = 0; }
+        }
+    }
+    std::vector<int> cta_off(ncta + 1, 0), items;
+    if (ncta >= ntiles) {
+        // CTAs per tile in proportion to the reduction cost, at least one each; largest-remainder rounding keeps the total at ncta
+        std::vector<double> want(ntiles);
+        double tot = 0.0;
+        { int I = 0, J = 0; for (int t = 0; t < ntiles; ++t) { want[t] = (I == J) ? diag_cost : 1.0; tot += want[t]; if (++J > I) { ++I; J = 0; } } }
+        std::vector<int> cnt(ntiles, 1);
+        int left = ncta - ntiles;
+        for (int t = 0; t < ntiles; ++t) want[t] = want[t] / tot * ncta;
+        for (int t = 0; t < ntiles; ++t) { const int extra = std::max(0, std::min(left, (int)want[t] - 1)); cnt[t] += extra; left -= extra; }
+        while (left > 0) {      // the largest shortfall first (ties: the lower tile index -- deterministic)
+            int best = 0;
+            for (int t = 1; t < ntiles; ++t) if (want[t] - cnt[t] > want[best] - cnt[best]) best = t;
+            ++cnt[best]; --left;
+        }
+        int c = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int k = std::min(cnt[t], STRIPES);      // (more CTAs than stripes: the surplus idles in phase 2)
+            for (int q = 0; q < cnt[t]; ++q, ++c) {
                 cta_off[c] = (int)items.size() / 3;
-                long long it = nitems * c / ncta;
-                const long long it1 = nitems * (c + 1) / ncta;
-                while (it < it1) {
-                    const int tile = (int)(it / STRIPES), lo = (int)(it - (long long)tile * STRIPES);
-                    const int hi = (int)std::min<long long>(STRIPES, lo + (it1 - it));
-                    items.push_back(tile); items.push_back(lo); items.push_back(hi);
-                    it += hi - lo;
+                if (q < k) {
+                    const int lo = STRIPES * q / k, hi = STRIPES * (q + 1) / k;
+                    if (lo < hi) { items.push_back(t); items.push_back(lo); items.push_back(hi); }
                 }
             }
-            cta_off[ncta] = (int)items.size() / 3;
         }
+        cta_off[ncta] = (int)items.size() / 3;
+    } else {
+        const long long nitems = (long long)ntiles * STRIPES;
+        for (int c = 0; c < ncta; ++c) {
+            cta_off[c] = (int)items.size() / 3;
+            long long it = nitems * c / ncta;
+            const long long it1 = nitems * (c + 1) / ncta;
+            while (it < it1) {
+                const int tile = (int)(it / STRIPES), lo = (int)(it - (long long)tile * STRIPES);
+                const int hi = (int)std::min<long long>(STRIPES, lo + (it1 - it));
+                items.push_back(tile); items.push_back(lo); items.push_back(hi);
+                it += hi - lo;
+            }
+        }
+        cta_off[ncta] = (int)items.size() / 3;
+    }
+    all.clear();
+    off[0] = 0; all.insert(all.end(), cta_off.begin(), cta_off.end());
+    off[1] = (int)all.size(); all.insert(all.end(), items.begin(), items.end());
+    off[2] = (int)all.size(); all.insert(all.end(), tile_off.begin(), tile_off.end());
+    off[3] = (int)all.size(); all.insert(all.end(), slots.begin(), slots.end());
+}
+
+static double p2_diag_cost() {
+    double diag_cost = 1.25;      // reduction cost of a diagonal tile's stripe relative to an off-diagonal one (half the partial loads, plus its Psi1 rows): measured
+    if (const char* e = std::getenv("SGP_SWEEP4_P2_DIAG")) { const double v = std::atof(e); if (v > 0.05 && v < 20.0) diag_cost = v; }
+    return diag_cost;
+}
+
+// The plan of a configuration as the kernel would get it, without a device (tests/test_host_helpers.py): out = [cta_off (ncta + 1) | items (3 per entry) |
+// tile_off (ntiles + 1) | slots], off4 = the four offsets; returns the number of ints (or -needed when cap is too small).
+extern "C" int sgp_debug_p2_plan(int ncta, int ntiles, int TM, long long slab_units, int w_diag, int w_off, int w_fixed, int* out, int cap, int* off4) {
+    if (ncta < 1 || ntiles < 1 || (TM != 64 && TM != 128) || slab_units < 1 || !out || !off4) return 0;
+    int nblk = 0;
+    while ((nblk + 1) * (nblk + 2) / 2 <= ntiles) ++nblk;
+    if (nblk * (nblk + 1) / 2 != ntiles) return 0;
+    const long long total_cost = slab_units * ((long long)nblk * w_diag + (long long)(ntiles - nblk) * w_off) + (long long)ntiles * w_fixed;
+    std::vector<int> all;
+    p2_plan_host(ncta, ntiles, TM, total_cost, slab_units, w_diag, w_off, w_fixed, p2_diag_cost(), all, off4);
+    if ((int)all.size() > cap) return -(int)all.size();
+    std::memcpy(out, all.data(), all.size() * sizeof(int));
+    return (int)all.size();
+}
+
+static int build_p2_plan(sgp_ctx* ctx, sgp_sweep4::Params& p, int TM) {
+    const double diag_cost = p2_diag_cost();
+    const long long key[8] = {p.total_cost, p.slab_units, p.ncta, p.ntiles, p.w_diag, p.w_off, ((long long)p.w_fixed << 20) + (long long)(diag_cost * 1000.0), TM};
+    if (!ctx->p2plan_dev || std::memcmp(key, ctx->p2plan_key, sizeof(key)) != 0) {
         std::vector<int> all;
         int off[4];
-        off[0] = 0; all.insert(all.end(), cta_off.begin(), cta_off.end());
-        off[1] = (int)all.size(); all.insert(all.end(), items.begin(), items.end());
-        off[2] = (int)all.size(); all.insert(all.end(), tile_off.begin(), tile_off.end());
-        off[3] = (int)all.size(); all.insert(all.end(), slots.begin(), slots.end());
+        p2_plan_host(p.ncta, p.ntiles, TM, p.total_cost, p.slab_units, p.w_diag, p.w_off, p.w_fixed, diag_cost, all, off);
         if (ctx->p2plan_cap < all.size()) {
             if (ctx->p2plan_dev) SGP_CUDA(ctx, cudaFree(ctx->p2plan_dev));
             ctx->p2plan_dev = nullptr; ctx->p2plan_cap = 0;

@@ -221,6 +221,10 @@ int sgp_last_sweep_info(sgp_ctx* ctx, int* n_launches, int* grid, int* block, in
  * recording on; later calls copy out up to `cap` records {chunks, SM clocks, is_diagonal_tile, cta} (-1 = unused slot)
  * of the last sweep and return their number in *nrec. */
 int sgp_sweep_debug_clocks(sgp_ctx* ctx, int64_t* out, int cap, int* nrec);
+/* The plan of the generate-once sweep's last phase (deterministic reduction of the segment partials) for a configuration, as the kernel gets it -- pure host
+ * arithmetic, no device needed (CPU tests): out = [cta_off (ncta + 1) | items {tile, first stripe, last stripe + 1} | tile_off (ntiles + 1) | slots],
+ * off4 = the four offsets into out; returns the number of ints written, -needed when cap is too small, 0 for bad arguments. */
+int sgp_debug_p2_plan(int ncta, int ntiles, int TM, long long slab_units, int w_diag, int w_off, int w_fixed, int* out, int cap, int* off4);
 /* device pointers of the resident statistics of the last sweep: [psi2 (M*M) | psi1 (M*D_out) | psi0 | sum_y2] */
 int sgp_stats_dev(sgp_ctx* ctx, double** psi2_dev, double** psi1_dev, double** scal_dev);
 

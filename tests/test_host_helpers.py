@@ -1,5 +1,6 @@
 """Driver-side helpers mirrored from helper_functions/gp_helperfunction.jl (CPU only) against the golden chains."""
 import numpy as np
+import pytest
 
 from gaussianprocessnode_b200 import nodes as nd
 from oracle import batched, kernels
@@ -86,3 +87,56 @@ def test_packed_lower_triangle_is_lapack_L_packed_storage():
         assert np.array_equal(unpack_lower(ap, M), A)
         c, info = lapack.dpptrf(M, ap, lower=1)                  # packed Cholesky straight on the vector
         assert info == 0 and np.allclose(np.tril(unpack_lower(c, M)), np.linalg.cholesky(A), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("ncta,nblk,TM", [(148, 4, 128), (148, 2, 64), (148, 8, 128), (148, 16, 128), (148, 20, 128), (148, 32, 128), (37, 4, 128), (3, 2, 64), (1, 1, 128)])
+@pytest.mark.parametrize("diag_cost", [None, "0.5", "3.0"])
+def test_phase2_plan_covers_every_stripe_once_and_lists_the_partition_slots(ncta, nblk, TM, diag_cost, monkeypatch):
+    # host logic of the generate-once sweep's last phase (csrc/sweep.cu: p2_plan_host, through sgp_debug_p2_plan -- no device): every (tile, stripe) of the
+    # lower triangle is reduced by exactly one CTA, a CTA never straddles tiles when there are at least as many CTAs as tiles, and the slot list of a tile is
+    # the set of CTAs whose share of the cost-weighted (tile, k-step) sequence touches it, in CTA order (slot = cta + tile: a CTA's slots are distinct)
+    import ctypes
+    from gaussianprocessnode_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    if diag_cost is not None:
+        monkeypatch.setenv("SGP_SWEEP4_P2_DIAG", diag_cost)
+    ntiles = nblk * (nblk + 1) // 2
+    stripes = TM // 4
+    slab_units = 2504
+    w_diag, w_off, w_fixed = 5, 8, 64
+    cap = 1 << 20
+    out = (ctypes.c_int * cap)(); off = (ctypes.c_int * 4)()
+    n = lib.sgp_debug_p2_plan(ncta, ntiles, TM, slab_units, w_diag, w_off, w_fixed, out, cap, off)
+    assert n > 0
+    a = np.frombuffer(out, dtype=np.int32, count=n)
+    cta_off = a[off[0]:off[1]]; items = a[off[1]:off[2]].reshape(-1, 3); tile_off = a[off[2]:off[3]]; slots = a[off[3]:]
+    assert len(cta_off) == ncta + 1 and cta_off[0] == 0 and cta_off[-1] == len(items) and np.all(np.diff(cta_off) >= 0)
+    cover = np.zeros((ntiles, stripes), dtype=int)
+    for c in range(ncta):
+        ent = items[cta_off[c]:cta_off[c + 1]]
+        if ncta >= ntiles:
+            assert len(ent) <= 1
+        for t, lo, hi in ent:
+            assert 0 <= lo < hi <= stripes and 0 <= t < ntiles
+            cover[t, lo:hi] += 1
+    assert np.all(cover == 1)
+    assert items[0][0] == 0 and items[0][1] == 0 and cta_off[1] >= 1          # CTA 0 starts tile 0, stripe 0: it also finishes the scalars
+    # the partition, restated: contiguous shares of the cost sequence [tile 0: w_fixed + w_diag * slab_units | tile 1: ...]
+    total = slab_units * (nblk * w_diag + (ntiles - nblk) * w_off) + ntiles * w_fixed
+    pos = lambda b: total // ncta * b + total % ncta * b // ncta
+    assert len(tile_off) == ntiles + 1 and tile_off[-1] == len(slots)
+    pre = 0; t = 0
+    for I in range(nblk):
+        for J in range(I + 1):
+            wt = w_diag if I == J else w_off
+            want = []
+            for c in range(ncta):
+                d0, d1 = pos(c) - pre - w_fixed, pos(c + 1) - pre - w_fixed
+                lo = 0 if d0 <= 0 else min(-(-d0 // wt), slab_units)
+                hi = 0 if d1 <= 0 else min(-(-d1 // wt), slab_units)
+                if lo < hi:
+                    want.append(c + t)
+            assert list(slots[tile_off[t]:tile_off[t + 1]]) == want and len(want) >= 1
+            pre += wt * slab_units + w_fixed; t += 1
+    assert len(set(slots.tolist())) == len(slots)
