@@ -44,8 +44,8 @@ def fp64_peak_file():
 
 def traffic(which):
     """(bytes per launch, source) of dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel from the newest committed
-    `ncu --set full` capture (profiles/r02_traffic.json, else round 1's).  A static figure from a capture, NOT sampled in this run."""
-    for name in ("r02_traffic.json", "r01g_traffic.json"):
+    `ncu --set full` capture (profiles/r02z_traffic.json, else earlier ones).  A static figure from a capture, NOT sampled in this run."""
+    for name in ("r02z_traffic.json", "r02_traffic.json", "r01g_traffic.json"):
         p = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(p):
             continue
