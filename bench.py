@@ -5,7 +5,7 @@ One "step" = one pass of the hot path over one batch: the generate-once K_uf + D
 for the kin40k-shape workload (N = 10000 points per GPU, D = 8, M = 512, SE-ARD, Float64).  `value` = data-points/s with
 inputs resident in HBM (K steps enqueued back to back, an L2 flush on the stream before each, one CUDA event pair per step);
 `e2e` = the same through the C-ABI call with HOST buffers (sgp_sweep_psi_host_packed: H2D of X / y -- beside the kernel's launch -- and D2H of
-Psi1 and the packed lower triangle of Psi2 inside the timed region; `e2e.full_square` = sgp_sweep_psi_host, Psi2 as the full square).  With --gpus N every rank sweeps its own N-shard and the statistics are summed over the ranks inside the
+one packed buffer [lower triangle of Psi2 | Psi1 | scalars] inside the timed region; `e2e.full_square` = sgp_sweep_psi_host, Psi2 as the full square).  With --gpus N every rank sweeps its own N-shard and the statistics are summed over the ranks inside the
 sweep kernel through NVLink peer memory ("weak": per-GPU work fixed); after the timed loop every rank checks its all-reduced
 statistics against a single-GPU sweep of ALL ranks' points (`parity`, exit code 3 above 1e-12).  The synthetic N = 10M /
 M = 1024 configuration, where the path is throughput-bound and the FP64 roofline is meaningful, is timed as well (strong scaling
@@ -293,7 +293,7 @@ def main():
     # Psi2 comes back as its packed lower triangle (LAPACK 'L' packed storage, sgp_sweep_psi_host_packed): the running sum of `prod` is symmetric, so
     # that is all of it at half the bytes over the bus; the full-square form of the same call is timed beside it (`full_square`)
     Mb = cfg["M"]
-    psi1p = pinned_empty((Mb,)); psi2p = pinned_empty((Mb, Mb), order="F"); psi2k = pinned_empty((Mb * (Mb + 1) // 2,))
+    psi1p = pinned_empty((Mb,)); psi2p = pinned_empty((Mb, Mb), order="F"); statsk = pinned_empty((Mb * (Mb + 1) // 2 + Mb + 4,))
     n_e2e = max(10, min(args.steps, 50))
 
     def e2e_loop(outbuf, packed):
@@ -307,13 +307,13 @@ def main():
         return max_over_ranks((time.perf_counter() - t0) / n_e2e), o
 
     e2e_full_s, out_full = e2e_loop((psi1p, psi2p), False)
-    e2e_s, out = e2e_loop((psi1p, psi2k), True)
+    e2e_s, out = e2e_loop(statsk, True)        # ONE buffer [packed lower triangle | Psi1 | scalars], ONE device-to-host copy
     from gaussianprocessnode_b200.sgp import pack_lower
     ref_stats = ctx.sweep_psi()            # the resident-data sweep the device-timed `value` runs
     e2e_same = bool(np.array_equal(out[2], pack_lower(ref_stats[2])) and np.array_equal(out[1], ref_stats[1]) and out[0] == ref_stats[0]
                     and np.array_equal(out_full[2], ref_stats[2]))
     h2d = X.nbytes + y.nbytes
-    d2h = out[2].nbytes + out[1].nbytes + 32
+    d2h = statsk.nbytes
     e2e_val = world * cfg["N"] / e2e_s
 
     # ------------------------------------------------------------------ parity of the sum over the ranks (world > 1)
@@ -375,7 +375,7 @@ def main():
                    "l2": "256 MB buffer rewritten on the stream before every timed step (inputs are smaller than L2); flush outside the timed intervals",
                    "parallelism": "N sharded over %d GPU(s)" % world, "wall_s_timed_region": t_wall},
         "e2e": {"value": e2e_val, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_call": e2e_s * 1e3,
-                "call": "sgp_sweep_psi_host_packed: pinned host X / y in, Psi0 / Psi1 / sum_y2 and Psi2 as its packed lower triangle (LAPACK 'L' packed storage) out, one host synchronisation",
+                "call": "sgp_sweep_psi_host_packed: pinned host X / y in (uploaded on the copy stream beside the kernel's launch), ONE packed buffer out -- [Psi2 as its lower triangle in LAPACK 'L' packed storage | Psi1 | Psi0, sum_y2, sum_w, n] with one device-to-host copy --, one host synchronisation",
                 "bitwise_equal_to_resident_sweep": e2e_same,
                 "full_square": {"value": world * cfg["N"] / e2e_full_s, "ms_per_call": e2e_full_s * 1e3, "d2h_bytes_per_step": int(out_full[2].nbytes + out_full[1].nbytes + 32),
                                 "call": "sgp_sweep_psi_host (Psi2 as the full symmetric M x M square)"}},

@@ -268,23 +268,34 @@ __global__ void pack_lower_kernel(const double* __restrict__ A, double* __restri
     for (int i = j + threadIdx.x; i < M; i += blockDim.x) packed[off + i] = A[(size_t)i + (size_t)j * M];
 }
 
-static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2, bool packed = false) {
+// packed: 0 = Psi2 as the full square; 1 = only the packed lower triangle of Psi2 into psi2 (M (M + 1) / 2 doubles); 2 = ALL statistics packed into psi2 --
+// [lower triangle | Psi1 (M * D_out) | Psi0, sum_y2, sum_w, n], the layout of the multi-GPU exchange -- with ONE device-to-host copy
+static int fetch_stats(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double* sum_y2, int packed = 0) {
     SGP_RANGE("sgp_fetch");
     const size_t M = (size_t)ctx->M, Do = (size_t)ctx->Dout;
     double* s2 = ctx->stats_dev; double* s1 = s2 + M * M; double* sc = s1 + M * Do;
+    const size_t small = M * Do + 4;
     if (psi2 && packed) {
         const size_t tri = M * (M + 1) / 2;
         const double* src = ctx->packed_src;
-        if (!src) {      // the sweep did not leave a packed copy (first fused kernel, NCCL path): pack the resident square
-            int rc = sgp_ensure(ctx, &ctx->packed_dev, &ctx->packed_cap, tri + 2); if (rc) return rc;
+        if (!src) {      // the sweep did not leave a packed copy (first fused kernel, NCCL path): pack the resident statistics
+            int rc = sgp_ensure(ctx, &ctx->packed_dev, &ctx->packed_cap, tri + small + 2); if (rc) return rc;
             pack_lower_kernel<<<(unsigned)M, 128, 0, ctx->stream>>>(s2, ctx->packed_dev, (int)M);
             SGP_CUDA(ctx, cudaGetLastError());
+            if (packed == 2) SGP_CUDA(ctx, cudaMemcpyAsync(ctx->packed_dev + tri, s1, small * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
             src = ctx->packed_dev;
         }
-        SGP_CUDA(ctx, cudaMemcpyAsync(psi2, src, tri * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SGP_CUDA(ctx, cudaMemcpyAsync(psi2, src, (tri + (packed == 2 ? small : 0)) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (packed == 2) {      // everything came with that one copy: the scalars and Psi1 are read from the tail of the caller's buffer
+            SGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const double* tail = psi2 + tri;
+            if (psi1) memcpy(psi1, tail, M * Do * sizeof(double));
+            if (psi0) *psi0 = tail[M * Do];
+            if (sum_y2) *sum_y2 = tail[M * Do + 1];
+            return SGP_OK;
+        }
     } else if (psi2) SGP_CUDA(ctx, cudaMemcpyAsync(psi2, s2, M * M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     // Psi1 and the scalars are adjacent on the device: ONE copy into a pinned staging buffer, split on the host
-    const size_t small = M * Do + 4;
     if (ctx->fetch_cap < small) {
         if (ctx->fetch_host) cudaFreeHost(ctx->fetch_host);
         ctx->fetch_host = nullptr; ctx->fetch_cap = 0;
@@ -360,7 +371,7 @@ static int sweep_host(sgp_ctx* ctx, int64_t N, const double* X, const double* yb
     const int rcj = sgp_join_upload(ctx);      // (a path that never launched a consumer of the ready word)
     if (rc) { cudaStreamSynchronize(ctx->stream2); return rc; }      // a failed sweep: nothing of this call stays in flight on the copy stream
     if (rcj) return rcj;
-    return fetch_stats(ctx, psi0, psi1, psi2, sum_y2, packed);       // the one host synchronisation of the step
+    return fetch_stats(ctx, psi0, psi1, psi2, sum_y2, packed ? 2 : 0);       // the one host synchronisation of the step
 }
 
 int sgp_sweep_psi_host(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts, double* psi0,
@@ -369,15 +380,15 @@ int sgp_sweep_psi_host(sgp_ctx* ctx, int64_t N, const double* X, const double* y
 }
 
 int sgp_sweep_psi_host_packed(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts, double* psi0,
-                              double* psi1, double* psi2_packed, double* sum_y2) {
-    return sweep_host(ctx, N, X, ybar, yvar, wts, psi0, psi1, psi2_packed, sum_y2, true);
+                              double* psi1, double* stats_packed, double* sum_y2) {
+    return sweep_host(ctx, N, X, ybar, yvar, wts, psi0, psi1, stats_packed, sum_y2, true);
 }
 
 int sgp_fetch_psi2_packed(sgp_ctx* ctx, double* psi2_packed) {
     if (check(ctx) || !psi2_packed) return SGP_ERR_ARG;
     if (!ctx->have_stats) SGP_FAIL(ctx, SGP_ERR_ARG, "fetch_psi2_packed: no statistics (sweep first)");
     SGP_CUDA(ctx, cudaSetDevice(ctx->dev));
-    return fetch_stats(ctx, nullptr, nullptr, psi2_packed, nullptr, true);
+    return fetch_stats(ctx, nullptr, nullptr, psi2_packed, nullptr, 1);
 }
 
 int sgp_sweep_psi_uncertain(sgp_ctx* ctx, int method, int p, int64_t N, const double* mean, const double* cov, int D_out, const double* R,

@@ -245,7 +245,7 @@ static int sweep_launch4(sgp_ctx* ctx, const double* X, const double* y, const d
     if (ctx->want_packed) {
         if (ctx->last_sweep_exchanged) ctx->packed_src = reinterpret_cast<const double*>(p.xr.peers[p.xr.rank] + p.xr.slot0_off + p.xr.slot_bytes);
         else {
-            rc = sgp_ensure(ctx, &ctx->packed_dev, &ctx->packed_cap, (size_t)M * (M + 1) / 2 + 2); if (rc) return rc;
+            rc = sgp_ensure(ctx, &ctx->packed_dev, &ctx->packed_cap, (size_t)M * (M + 1) / 2 + M + 8); if (rc) return rc;
             p.packed_out = ctx->packed_dev; ctx->packed_src = ctx->packed_dev;
         }
     }

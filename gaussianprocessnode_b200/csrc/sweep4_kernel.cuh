@@ -70,7 +70,7 @@ struct Params {
     int coop;                     // 1: cooperative launch (grid.sync), 0: plain launch + ticket barrier
     SgpXchg xr;                   // multi-GPU exchange (nranks = 1: none): phase 2 then writes [packed lower triangle of Psi2 | Psi1 | scalars] into this rank's contribution buffer
     double* stats_out;            // ... and the sums over the ranks land here (full symmetric Psi2 | Psi1 | scalars); = psi2 without exchange
-    double* packed_out;           // optional (no exchange): phase 2 also writes the packed lower triangle of Psi2 here (LAPACK 'L' packed storage, for the host)
+    double* packed_out;           // optional (no exchange): phase 2 also writes [packed lower triangle of Psi2 (LAPACK 'L' packed storage) | Psi1 | scalars] here, for the host
     // phase-2 plan, built on the host once per configuration (sweep.cu: build_p2_plan): which (tile, stripe range) every CTA reduces and, per tile,
     // the workspace slots of its segments in CTA order -- the kernel neither divides nor searches after the last grid barrier
     const int* p2_cta_off;        // [ncta + 1] offsets into p2_items
@@ -678,7 +678,7 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     if (lane == 0 && gi < p.M) {
                         if (packed) sgp_xchg::put1(p.xr, tri + gi, v);
-                        else p.psi1[gi] = v;
+                        else { p.psi1[gi] = v; if (p.packed_out) p.packed_out[tri + gi] = v; }
                     }
                 }
             }
@@ -695,7 +695,7 @@ __device__ __forceinline__ void reduce_items4(const Params& p, double* __restric
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (packed) sgp_xchg::put1(p.xr, tri + p.M + q, sc[q]);
-                    else p.scal[q] = sc[q];
+                    else { p.scal[q] = sc[q]; if (p.packed_out) p.packed_out[tri + p.M + q] = sc[q]; }
                 }
             }
         }

@@ -153,31 +153,39 @@ class SGPContext:
 
     def sweep_psi_host(self, X, ybar=None, yvar=None, wts=None, out=None, packed=False):
         """set_data + sweep_psi in one call (one host synchronisation); `out` = (psi1, psi2) preallocated arrays.
-        packed=True: Psi2 comes back as its packed lower triangle (M (M + 1) / 2 doubles, column by column = LAPACK 'L' packed storage;
-        `unpack_lower` expands it) -- half the bytes over the bus (sgp_sweep_psi_host_packed)."""
+        packed=True (sgp_sweep_psi_host_packed): ALL statistics come back in ONE buffer with ONE device-to-host copy --
+        [packed lower triangle of Psi2 (M (M + 1) / 2 doubles, column by column = LAPACK 'L' packed storage; `unpack_lower` expands it) | Psi1 (M) |
+        Psi0, sum_y2, sum_w, n] -- half the bytes over the bus; `out` is then that ONE 1-D array of M (M + 1) / 2 + M + 4 doubles (e.g. pinned_empty),
+        and the returned psi1 / psi2 are views into it."""
         # Steady-state callers pass the SAME (pinned) arrays every step: the argument marshalling (~20 us of ctypes / numpy work, a tenth of the
         # call at the kin40k shape) is cached on the identity of the array objects -- their buffers cannot move while we hold references.
         c = self._host_call
-        if (c is not None and out is not None and c[0] is X and c[1] is ybar and c[2] is yvar and c[3] is wts and c[4] is out[0] and c[5] is out[1]
+        o0, o1 = (out, None) if (packed or out is None) else out
+        if (c is not None and out is not None and c[0] is X and c[1] is ybar and c[2] is yvar and c[3] is wts and c[4] is o0 and c[5] is o1
                 and c[6] == X.shape and c[7] == (self.M, self.D, bool(packed))):
-            N, args, psi0, sy2 = c[8], c[9], c[10], c[11]
-            psi1, psi2 = out
+            N, args, psi0, sy2, psi1, psi2 = c[8:14]
         else:
             Xc = _f64(X).reshape(-1, self.D)
             N = Xc.shape[0]; M = self.M
             yb, yv, w = _f64(ybar, (N,)), _f64(yvar, (N,)), _f64(wts, (N,))
             if packed:
-                psi1, psi2 = out if out is not None else (np.empty(M), np.empty(M * (M + 1) // 2))
-                assert psi1.size == M and psi2.shape == (M * (M + 1) // 2,) and psi2.flags.c_contiguous and psi1.dtype == psi2.dtype == np.float64
+                tri = M * (M + 1) // 2
+                buf = out if out is not None else np.empty(tri + M + 4)
+                assert buf.shape == (tri + M + 4,) and buf.flags.c_contiguous and buf.dtype == np.float64
+                psi2, psi1 = buf[:tri], buf[tri:tri + M]
+                psi0, sy2 = buf[tri + M:tri + M + 1], buf[tri + M + 1:tri + M + 2]                  # the scalars are read from the buffer's tail
+                args = (self.h, N, _p(Xc), _p(yb), _p(yv), _p(w), None, None, _p(buf), None)
             else:
                 psi1, psi2 = out if out is not None else (np.empty(M), np.empty((M, M), order="F"))
                 assert psi1.size == M and psi2.shape == (M, M) and psi2.flags.f_contiguous and psi1.dtype == psi2.dtype == np.float64
-            psi0, sy2 = ctypes.c_double(), ctypes.c_double()
-            args = (self.h, N, _p(Xc), _p(yb), _p(yv), _p(w), ctypes.byref(psi0), _p(psi1), _p(psi2), ctypes.byref(sy2))
+                psi0, sy2 = ctypes.c_double(), ctypes.c_double()
+                args = (self.h, N, _p(Xc), _p(yb), _p(yv), _p(w), ctypes.byref(psi0), _p(psi1), _p(psi2), ctypes.byref(sy2))
             cacheable = out is not None and all(_is_plain(a) for a in (X, ybar, yvar, wts))      # (no converted temporaries behind the pointers)
-            self._host_call = (X, ybar, yvar, wts, out[0], out[1], X.shape, (M, self.D, bool(packed)), N, args, psi0, sy2) if cacheable else None
+            self._host_call = (X, ybar, yvar, wts, o0, o1, X.shape, (M, self.D, bool(packed)), N, args, psi0, sy2, psi1, psi2) if cacheable else None
         self._ck((self.lib.sgp_sweep_psi_host_packed if packed else self.lib.sgp_sweep_psi_host)(*args))
         self.N = N
+        if packed:
+            return float(psi0[0]), psi1, psi2, float(sy2[0])
         return psi0.value, psi1, psi2, sy2.value
 
     def fetch_psi2_packed(self, out=None):

@@ -91,13 +91,15 @@ int sgp_sweep_psi(sgp_ctx* ctx, double* psi0, double* psi1, double* psi2, double
  * SGP_HOST_OVERLAP=0 restores upload-then-launch); the host buffers must stay untouched until the call returns, as before. */
 int sgp_sweep_psi_host(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts,
                        double* psi0, double* psi1, double* psi2, double* sum_y2);
-/* The same call with Psi2 returned as its PACKED lower triangle, column by column -- psi2_packed[i + j (2M - j - 1) / 2] = Psi2[i, j], i >= j,
- * M (M + 1) / 2 doubles: LAPACK's packed storage for uplo = 'L' (dpptrf / dspmv take it as is; Julia: the vector behind a
- * `LinearAlgebra.SymmetricPacked`-style wrapper).  The running sum of `prod` (GPnode/UniSGPnode.jl:62-73) is symmetric, so this is all of it at
- * half the bytes over the bus; the sweep's last phase writes the packed copy itself (no extra pass, no extra launch). */
+/* The same call with ALL statistics returned in ONE packed buffer -- the layout the multi-GPU exchange uses --:
+ *   stats_packed = [ lower triangle of Psi2, column by column: stats_packed[i + j (2M - j - 1) / 2] = Psi2[i, j], i >= j  (M (M + 1) / 2 doubles: LAPACK's packed
+ *                    storage for uplo = 'L'; dpptrf / dspmv take it as is)  |  Psi1 (M)  |  Psi0, sum_y2, sum_w, n ]
+ * i.e. M (M + 1) / 2 + M + 4 doubles, filled by ONE device-to-host copy.  The running sum of `prod` (GPnode/UniSGPnode.jl:62-73) is symmetric, so this is all of
+ * it at half the bytes over the bus; the sweep's last phase writes the packed copy itself (no extra pass, no extra launch).  psi0 / psi1 / sum_y2 are optional
+ * conveniences (copied out of the tail of stats_packed on the host; NULL to skip). */
 int sgp_sweep_psi_host_packed(sgp_ctx* ctx, int64_t N, const double* X, const double* ybar, const double* yvar, const double* wts,
-                              double* psi0, double* psi1, double* psi2_packed, double* sum_y2);
-/* Psi2 of the last sweep (any of the sweeps above), packed as in sgp_sweep_psi_host_packed. */
+                              double* psi0, double* psi1, double* stats_packed, double* sum_y2);
+/* Psi2 of the last sweep (any of the sweeps above) as its packed lower triangle alone: M (M + 1) / 2 doubles, laid out as in sgp_sweep_psi_host_packed. */
 int sgp_fetch_psi2_packed(sgp_ctx* ctx, double* psi2_packed);
 
 /* Uncertain inputs q(x_n) = N(mean_n, cov_n): replaces the cubature loop `approximate_kernel_expectation(!)`

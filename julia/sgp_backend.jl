@@ -197,17 +197,17 @@ function sweep_psi_host!(meta::UniSGPMeta, X::Matrix{Float64}, y::Vector{Float64
     return ψ0[], sy2[]
 end
 
-# the same with Ψ2 as its packed lower triangle (LAPACK uplo = 'L' packed storage, M(M+1)/2 doubles): half the bytes over the bus.
-# `ap` is best a vector over sgp_pinned_alloc memory; Ψ2[i, j] = ap[i + (j - 1) * (2M - j) ÷ 2] for i ≥ j (1-based).
-function sweep_psi_host_packed!(meta::UniSGPMeta, X::Matrix{Float64}, y::Vector{Float64}, ap::Vector{Float64})
-    M = size(meta.Ψ2, 1)
-    @assert length(ap) == M * (M + 1) ÷ 2
-    ψ0 = Ref(0.0); sy2 = Ref(0.0)
+# the same with ALL statistics in one packed buffer (one device-to-host copy, half the bytes over the bus):
+# buf = [lower triangle of Ψ2 column by column (LAPACK uplo = 'L' packed storage, M(M+1)/2) | Ψ1 (M) | Ψ0, Σw(ȳ²+v), Σw, n].
+# `buf` is best a vector over sgp_pinned_alloc memory; Ψ2[i, j] = buf[i + (j - 1) * (2M - j) ÷ 2] for i ≥ j (1-based).
+function sweep_psi_host_packed!(meta::UniSGPMeta, X::Matrix{Float64}, y::Vector{Float64}, buf::Vector{Float64})
+    M = size(meta.Ψ2, 1); tri = M * (M + 1) ÷ 2
+    @assert length(buf) == tri + M + 4
     sgp_check(meta.h, ccall((:sgp_sweep_psi_host_packed, libsgp), Cint,
-                            (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}),
-                            meta.h.ptr, size(X, 2), X, y, C_NULL, C_NULL, ψ0, vec(meta.Ψ1_trans), ap, sy2))
+                            (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                            meta.h.ptr, size(X, 2), X, y, C_NULL, C_NULL, C_NULL, C_NULL, buf, C_NULL))
     meta.resident = UInt64(0); meta.swept = true
-    return ψ0[], sy2[]
+    return buf[tri + M + 1], buf[tri + M + 2]          # Ψ0, Σw(ȳ²+v); Ψ1 = view(buf, tri+1:tri+M)
 end
 
 # ---- MultiSGP :in messages for a whole chain (GPnode/MultiSGPnode.jl:162-236, prod override :38-45) ------------------------------

@@ -48,7 +48,7 @@ def _worker(rank, world, port, out, p2p, M):
         h0, h1, hk, hy = ctx.sweep_psi_host(X[lo:hi], y[lo:hi], yv[lo:hi], packed=True)
         g0, g1, g2, gy = ctx.sweep_psi_host(X[lo:hi], y[lo:hi], yv[lo:hi])
         same = same and bool(np.array_equal(hk, pack_lower(p2)) and np.array_equal(g2, p2) and np.array_equal(h1, p1) and np.array_equal(g1, p1)
-                             and h0 == p0 == g0 and hy == sy == gy and np.array_equal(ctx.fetch_psi2_packed(), hk))
+                             and h0 == p0 == g0 and hy == sy == gy and np.array_equal(ctx.fetch_psi2_packed(), hk) and hk.base[-1] == N)
     ctx.close()
     single = SGPContext(rank); single.set_kernel(1.2, ell); single.set_inducing(Z); single.set_data(X, y, yv)
     f0, f1, f2, fy = single.sweep_psi(); single.close()

@@ -217,13 +217,14 @@ def test_host_step_with_packed_psi2_and_upload_beside_the_launch(ctx, N, D, M, m
     ctx.set_kernel(1.2, np.full(D, 1.6)); ctx.set_inducing(Z)
     tri = M * (M + 1) // 2
     Xp = pinned_empty((max(N, 1), D))[:N]; yp = pinned_empty((max(N, 1),))[:N]
-    o1 = pinned_empty((M,)); o2 = pinned_empty((tri,))
+    buf = pinned_empty((tri + M + 4,))
     for it in range(4):
         X = rng.normal(size=(N, D)); y = rng.normal(size=N); yv = rng.uniform(0, 0.3, N) if it % 2 else None
         Xp[...] = X; yp[...] = y
         if it == 3:
             monkeypatch.setenv("SGP_HOST_OVERLAP", "0")     # upload, then launch (the round-1 order)
-        a = ctx.sweep_psi_host(Xp, yp, yv, out=(o1, o2), packed=True)
+        a = ctx.sweep_psi_host(Xp, yp, yv, out=buf, packed=True)
+        assert buf[tri + M + 3] == N and np.shares_memory(a[2], buf) and np.shares_memory(a[1], buf)       # [triangle | Psi1 | Psi0, sum_y2, sum_w, n]
         a = (a[0], a[1].copy(), a[2].copy(), a[3])
         f = ctx.sweep_psi_host(X, y, yv)                   # pageable buffers, full square
         ctx.set_data(X, y, yv); b = ctx.sweep_psi()

@@ -21,12 +21,12 @@ def timeit(f, reps=50):
     return (time.perf_counter() - t0) / reps * 1e3
 
 
-psi2k = pinned_empty((M * (M + 1) // 2,))
+psi2k = pinned_empty((M * (M + 1) // 2 + M + 4,))
 print("sweep_psi_host (H2D beside the launch + sweep + D2H)   %.3f ms" % timeit(lambda: ctx.sweep_psi_host(Xp, yp, out=(psi1p, psi2p))))
-print("sweep_psi_host packed Psi2                              %.3f ms" % timeit(lambda: ctx.sweep_psi_host(Xp, yp, out=(psi1p, psi2k), packed=True)))
+print("sweep_psi_host packed Psi2                              %.3f ms" % timeit(lambda: ctx.sweep_psi_host(Xp, yp, out=psi2k, packed=True)))
 os.environ["SGP_HOST_OVERLAP"] = "0"
 print("sweep_psi_host, upload then launch (SGP_HOST_OVERLAP=0) %.3f ms" % timeit(lambda: ctx.sweep_psi_host(Xp, yp, out=(psi1p, psi2p))))
-print("... packed                                              %.3f ms" % timeit(lambda: ctx.sweep_psi_host(Xp, yp, out=(psi1p, psi2k), packed=True)))
+print("... packed                                              %.3f ms" % timeit(lambda: ctx.sweep_psi_host(Xp, yp, out=psi2k, packed=True)))
 del os.environ["SGP_HOST_OVERLAP"]
 print("set_data (H2D + sync)               %.3f ms" % timeit(lambda: ctx.set_data(Xp, yp)))
 print("sweep_psi(fetch=False) (sweep, sync) %.3f ms" % timeit(lambda: ctx.sweep_psi(fetch=False)))
