@@ -1,6 +1,6 @@
 """Sharded sweep over 2 (and 4) GPUs through the C ABI: N is cut into slices, one process / sgp_ctx per GPU, the packed
 statistics are summed over the ranks inside sgp_sweep_psi -- by the sweep kernel itself through NVLink peer memory (CUDA IPC,
-one-shot pull of the packed lower triangle in the kernel's tail; a kernel of its own for the sweeps without that tail), or by one
+two-shot all-reduce of the packed lower triangle in the kernel's tail; a kernel of its own for the sweeps without that tail), or by one
 NCCL all-reduce when SGP_COMM_P2P=0; every rank must hold the single-GPU result (tolerance: the summation order differs, relative
 Frobenius <= 1e-12) and all ranks the same bits.  Skipped on boxes with fewer GPUs (bench.py --gpus N carries the same check in
 its `parity` block, which the driver's scaling run records)."""
