@@ -184,6 +184,7 @@ bool sgp_comm_xchg(sgp_ctx* ctx, size_t need_doubles, SgpXchg* x) {
     SgpComm* c = ctx->comm;
     if (!c || !c->p2p || need_doubles > c->cap_doubles) return false;
     x->nranks = c->nranks; x->rank = c->rank; x->epoch = ++c->epoch;
+    ctx->packed_src = nullptr;      // the result buffer is about to be rewritten: a packed copy the host was pointed at (sweep.cu) is no longer there
     for (int q = 0; q < 8; ++q) x->peers[q] = c->peers[q];
     x->slot0_off = kFlagBytes; x->slot_bytes = c->cap_doubles * sizeof(double);
     return true;

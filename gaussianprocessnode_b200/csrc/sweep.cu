@@ -292,6 +292,7 @@ int sgp_sweep_launch(sgp_ctx* ctx, const double* X, const double* y, const doubl
                      bool time_main) {
     if (!ctx->have_kernel || !ctx->have_Z) SGP_FAIL(ctx, SGP_ERR_ARG, "sweep: set_kernel and set_inducing first");
     ctx->stats_of_data = false;      // set again by the caller that sweeps the resident data set (sgp_sweep_resident)
+    ctx->packed_src = nullptr;       // EVERY sweep rewrites the resident statistics: a packed copy of the previous ones is stale (set again below on request)
     constexpr int NB = 32;
     {
         const long long chunks_ = (N + NB - 1) / NB;

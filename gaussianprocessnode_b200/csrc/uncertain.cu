@@ -466,6 +466,7 @@ int sgp_uncertain_sweep(sgp_ctx* ctx, int method, int p, int64_t N, const double
     rc = sgp_ensure_stats(ctx, MM + (size_t)M * (D_out > 1 ? D_out : 1) + 8);
     if (rc) { cleanup(); return rc; }
     double* s_psi2 = ctx->stats_dev; double* s_psi1 = s_psi2 + MM; double* s_scal = s_psi1 + (size_t)M * D_out;
+    ctx->packed_src = nullptr;       // the resident statistics are rewritten below: a packed copy of the previous ones is stale
 
     if (method != SGP_METHOD_CLOSED_FORM_SE) {
         const size_t NS = (size_t)N * S, cap = ((NS + 31) / 32) * 32;

@@ -237,6 +237,27 @@ def test_host_step_with_packed_psi2_and_upload_beside_the_launch(ctx, N, D, M, m
             assert fro(b[2], r2) <= TOL and fro(b[1], r1) <= TOL and abs(b[3] - oy) <= TOL * abs(oy)
 
 
+def test_packed_fetch_follows_the_latest_sweep(ctx):
+    # sgp_fetch_psi2_packed must return the triangle of the statistics that are resident NOW: a packed copy left by an earlier
+    # sgp_sweep_psi_host_packed goes stale with every later sweep (plain, uncertain-input by sigma points, closed form)
+    from gaussianprocessnode_b200.sgp import pack_lower
+    rng = np.random.default_rng(77)
+    N, D, M = 4000, 2, 450
+    X = rng.normal(size=(N, D)); y = rng.normal(size=N); Z = rng.normal(size=(M, D))
+    ctx.set_kernel(1.1, np.array([1.3, 0.9])); ctx.set_inducing(Z)
+    a = ctx.sweep_psi_host(X, y, packed=True)
+    assert np.array_equal(ctx.fetch_psi2_packed(), a[2])
+    X2 = rng.normal(size=(N // 2, D)); ctx.set_data(X2, y[:N // 2])
+    b = ctx.sweep_psi()
+    assert np.array_equal(ctx.fetch_psi2_packed(), pack_lower(b[2])) and not np.array_equal(pack_lower(b[2]), a[2])
+    ctx.sweep_psi_host(X, y, packed=True)
+    mean = rng.normal(size=(300, D)); A_ = rng.normal(size=(300, D, D)) * 0.2; cov = A_ @ np.swapaxes(A_, 1, 2) + 1e-2 * np.eye(D)
+    for method in (0, 3):       # srcubature (through the fused sweep), closed-form SE (its own kernels)
+        ctx.sweep_psi_host(X, y, packed=True)
+        u = ctx.sweep_psi_uncertain(method, mean, cov)
+        assert np.array_equal(ctx.fetch_psi2_packed(), pack_lower(u[2]))
+
+
 @pytest.mark.parametrize("N,D,M,slab_mb,kind", [(20000, 8, 1024, "1", 0), (20000, 3, 300, "0.3", 0), (9000, 2, 100, "0.05", 0), (6000, 8, 300, "0.2", 2)])
 def test_many_slabs_ring_wraparound(ctx, N, D, M, slab_mb, kind, monkeypatch):
     # the generate-once kernel cuts N into slabs whose K_uf panel lives in a ring of three L2 panels; tiny panels force dozens of slabs
